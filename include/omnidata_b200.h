@@ -1,0 +1,158 @@
+/* omnidata_b200 — C ABI of the B200-native DPT-Hybrid-384 hot path.
+ *
+ * This header is the drop-in boundary.  The reference (EPFL-VILAB/omnidata) is pure
+ * Python/PyTorch on this path and has no FFI of its own; every entry point below replaces a chain
+ * of torch library calls made by a reference function, cited as `file:line` under
+ * omnidata_tools/torch/ (M/ = modules/midas/, L/ = losses/).  timm 0.4.12 (pinned by
+ * requirements.txt:15, called at M/vit.py:483) is not vendored in the reference; its arithmetic
+ * is cited as "timm <symbol>".
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says host; no torch types cross this ABI;
+ *   - activations are channels-last (NHWC / token-major) bf16 unless stated; strides are in
+ *     ELEMENTS, the channel stride is always 1;
+ *   - every function only enqueues work on `stream` (a cudaStream_t passed as void*); nothing
+ *     allocates, synchronises or touches the host heap — safe under CUDA-graph capture;
+ *   - return value: 0 on success, a negative odb_status otherwise; odb_last_error() returns a
+ *     thread-local message.  There is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with ODB_ERR_CUDA.
+ */
+#ifndef OMNIDATA_B200_H_
+#define OMNIDATA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODB_ABI_VERSION 1
+
+typedef enum odb_status {
+  ODB_OK = 0,
+  ODB_ERR_INVALID = -1, /* bad argument / unsupported shape */
+  ODB_ERR_CUDA = -2,    /* CUDA runtime or driver error (message has the detail) */
+  ODB_ERR_UNSUPPORTED = -3
+} odb_status;
+
+typedef enum odb_act { ODB_ACT_NONE = 0, ODB_ACT_RELU = 1, ODB_ACT_GELU = 2 } odb_act;
+
+/* A strided channels-last view [b][h][w][c] over bf16 storage. */
+typedef struct odb_view {
+  const void* ptr;
+  int32_t c, w, h, b;
+  int64_t sx, sy, sb; /* element strides of w, h, b */
+} odb_view;
+
+#define ODB_MAX_VIEWS 4
+#define ODB_MAX_TAPS 9
+
+/* Implicit-GEMM convolution / linear layer on tcgen05 tensor cores:
+ *
+ *   out[b,y,x,n] = epilogue( sum_{t<num_taps} sum_{c<C} view[tap_view[t]][b, y+tap_dy[t], x+tap_dx[t], c]
+ *                                                     * weight[n][t*C + c] )
+ *
+ * Reads outside a view are zero (TMA out-of-bounds fill) — this is the convolution padding.
+ * A stride-2 convolution is expressed with up to four parity-plane views (doubled strides).
+ * A linear layer is the degenerate case num_taps = 1, h = b = 1, w = rows.
+ *
+ * epilogue(v) = residual + act(v + bias)        (each term optional), stored as bf16 to `out`
+ *               and, if out2.ptr != NULL, relu(.) of the same value to `out2`.
+ *
+ * Replaces, depending on the call site: nn.Linear in timm Attention/Mlp (loop M/vit.py:150-151),
+ * timm HybridEmbed.proj (M/vit.py:133), ProjectReadout.project (M/vit.py:36-47),
+ * act_postprocess convs (M/vit.py:431-462), scratch.layerN_rn (M/blocks.py:49-75, used
+ * M/dpt_depth.py:73-76), ResidualConvUnit_custom.conv1/conv2 (M/blocks.py:263-286),
+ * FeatureFusionBlock_custom.out_conv (M/blocks.py:339), output_conv[0] (M/dpt_depth.py:91),
+ * timm ResNetV2 StdConv2dSame layers.
+ */
+typedef struct odb_conv_gemm_desc {
+  int32_t num_views;
+  odb_view views[ODB_MAX_VIEWS]; /* all views share c = C (multiple of 8; K blocks of 64) */
+  int32_t num_taps;
+  int8_t tap_view[ODB_MAX_TAPS];
+  int8_t tap_dx[ODB_MAX_TAPS];
+  int8_t tap_dy[ODB_MAX_TAPS];
+  const void* weight; /* bf16 [n][num_taps * C], K contiguous */
+  int32_t n;          /* output channels */
+  odb_view out;       /* c = n; w,h,b = output extent */
+  odb_view out2;      /* optional relu copy (ptr may be NULL) */
+  const float* bias;  /* fp32 [n] or NULL */
+  int64_t bias_sb;    /* 0, or n for a per-image bias [b][n] (ProjectReadout cls term) */
+  odb_view residual;  /* optional bf16 residual, same extent as out (ptr may be NULL); sb may be 0 */
+  int32_t act;        /* odb_act */
+  int32_t tile_w, tile_h; /* spatial tile of the 128-row MMA tile, tile_w*tile_h <= 128; 0 = auto */
+  int32_t block_n;        /* N tile: 256, 128, 64 (32 with the head tail); 0 = auto */
+  /* Fused DPT head tail (M/dpt_depth.py:93-97): only with n == 32.  When head_out != NULL the
+   * 32-channel result relu(v + bias) is not stored; instead
+   *   head_out[b][k][y][x] = relu?(head_b[k] + sum_j head_w[k][j] * relu(v_j + bias_j))  (fp32, NCHW) */
+  const float* head_w; /* fp32 [head_c][32] */
+  const float* head_b; /* fp32 [head_c] */
+  int32_t head_c;
+  int32_t head_relu;
+  float* head_out;
+} odb_conv_gemm_desc;
+
+int odb_conv_gemm(const odb_conv_gemm_desc* desc, void* stream);
+
+/* LayerNorm over the last dim (timm Block.norm1/norm2, eps 1e-6): y = (x-mean)/sqrt(var+eps)*g + b.
+ * x, y bf16 [rows][cols] (cols multiple of 256, <= 1024); gamma/beta fp32. */
+int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
+                  int32_t cols, float eps, void* stream);
+
+/* Fused multi-head attention (timm Attention.forward): qkv bf16 [b][tokens][3][heads][64] as written
+ * by the qkv linear; out bf16 [b][tokens][heads*64]; softmax(q k^T * scale) v, fp32 softmax. */
+int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
+                  void* stream);
+
+/* GroupNorm statistics (timm GroupNormAct, 32 groups): stats fp32 [b][groups][2] += (sum, sum of
+ * squares) over x bf16 [b][hw][c].  The caller zeroes `stats` first (odb_fill_zero). */
+int odb_groupnorm_stats(const void* x, float* stats, int32_t b, int32_t hw, int32_t c,
+                        int32_t groups, void* stream);
+
+/* GroupNorm apply (+ optional shortcut, + optional ReLU), timm Bottleneck.forward:
+ *   y = relu?( gn(x; stats, gamma, beta) + shortcut )
+ * shortcut = 0 (res == NULL) | res (res_stats == NULL) | gn(res; res_stats, res_gamma, res_beta). */
+int odb_groupnorm_apply(const void* x, const float* stats, const float* gamma, const float* beta,
+                        const void* res, const float* res_stats, const float* res_gamma,
+                        const float* res_beta, void* y, int32_t b, int32_t hw, int32_t c,
+                        int32_t groups, float eps, int32_t relu, void* stream);
+
+/* Stem tail (timm ResNetV2 stem.norm + stem.pool): GroupNorm+ReLU then MaxPool 3x3 stride 2 with
+ * TF-SAME padding (0,1).  x bf16 [b][h][w][c] -> y bf16 [b][h/2][w/2][c]. */
+int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const float* gamma,
+                             const float* beta, void* y, int32_t b, int32_t h, int32_t w, int32_t c,
+                             int32_t groups, float eps, void* stream);
+
+/* im2col for the 7x7 stride-2 TF-SAME stem conv (timm StdConv2dSame 3->64): x fp32 NCHW
+ * [b][3][h][w] -> cols bf16 [b*(h/2)*(w/2)][kpad], column (ky*7+kx)*3+ch, zero padded. */
+int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h, int32_t w, int32_t kpad,
+                    void* stream);
+
+/* Bilinear x2 upsampling, align_corners=True (M/blocks.py:335-337, M/dpt_depth.py:93), fused with
+ * the skip add of the next fusion block (M/blocks.py:330): out = up2(z) + res; out_relu = relu(out).
+ * z bf16 [b][h][w][c]; res/out/out_relu bf16 [b][2h][2w][c]; res and out_relu may be NULL. */
+int odb_upsample2x_add(const void* z, const void* res, void* out, void* out_relu, int32_t b,
+                       int32_t h, int32_t w, int32_t c, void* stream);
+
+/* tokens[b][0][:] = cls + pos[0]  (M/vit.py:135-147); tokens bf16 [b][tokens][c]; cls, pos0 fp32 [c]. */
+int odb_write_cls_row(void* tokens, const float* cls, const float* pos0, int32_t b, int32_t tokens_n,
+                      int32_t c, void* stream);
+
+/* ProjectReadout cls term (M/vit.py:43-47): out[b][n] = bias[n] + sum_k w[n][c + k] * tokens[b][0][k]
+ * w bf16 [c][2c] (the Linear(2c, c) weight), tokens bf16 [b][tokens][c], out fp32 [b][c]. */
+int odb_readout_cls_bias(const void* w, const float* bias, const void* tokens, float* out, int32_t b,
+                         int32_t tokens_n, int32_t c, void* stream);
+
+int odb_fill_zero(void* ptr, int64_t bytes, void* stream);
+
+/* Introspection (no GPU needed). */
+int odb_abi_version(void);
+const char* odb_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t odb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMNIDATA_B200_H_ */

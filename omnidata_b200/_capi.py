@@ -1,0 +1,108 @@
+"""ctypes binding of include/omnidata_b200.h (the C-ABI shared library).
+
+There is deliberately no fallback: if the library is missing or a call fails, this raises.
+Only plain pointers and integers cross the boundary; torch is used by callers for device memory
+and streams, never passed through.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libomnidata_b200.so"
+
+ODB_MAX_VIEWS = 4
+ODB_MAX_TAPS = 9
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+
+class OdbError(RuntimeError):
+    pass
+
+
+class View(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("c", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("b", C.c_int32),
+        ("sx", C.c_int64), ("sy", C.c_int64), ("sb", C.c_int64),
+    ]
+
+
+class ConvGemmDesc(C.Structure):
+    _fields_ = [
+        ("num_views", C.c_int32),
+        ("views", View * ODB_MAX_VIEWS),
+        ("num_taps", C.c_int32),
+        ("tap_view", C.c_int8 * ODB_MAX_TAPS),
+        ("tap_dx", C.c_int8 * ODB_MAX_TAPS),
+        ("tap_dy", C.c_int8 * ODB_MAX_TAPS),
+        ("weight", C.c_void_p),
+        ("n", C.c_int32),
+        ("out", View),
+        ("out2", View),
+        ("bias", C.c_void_p),
+        ("bias_sb", C.c_int64),
+        ("residual", View),
+        ("act", C.c_int32),
+        ("tile_w", C.c_int32), ("tile_h", C.c_int32),
+        ("block_n", C.c_int32),
+        ("head_w", C.c_void_p),
+        ("head_b", C.c_void_p),
+        ("head_c", C.c_int32),
+        ("head_relu", C.c_int32),
+        ("head_out", C.c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    "odb_conv_gemm": (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p]),
+    "odb_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                C.c_float, C.c_void_p]),
+    "odb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                C.c_void_p]),
+    "odb_groupnorm_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p]),
+    "odb_groupnorm_apply": (C.c_int, [C.c_void_p] * 9 + [C.c_int32] * 4 + [C.c_float, C.c_int32,
+                                                                           C.c_void_p]),
+    "odb_stem_gn_relu_maxpool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
+    "odb_stem_im2col": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p]),
+    "odb_upsample2x_add": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
+    "odb_write_cls_row": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p]),
+    "odb_readout_cls_bias": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
+    "odb_fill_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "odb_abi_version": (C.c_int, []),
+    "odb_last_error": (C.c_char_p, []),
+    "odb_launch_count": (C.c_int64, []),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise OdbError(
+                f"{LIB_PATH} is missing: build it with `python -m omnidata_b200.build` "
+                "(there is no CPU / eager fallback)")
+        _lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(_lib, name)  # raises AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().odb_last_error().decode(errors="replace")
+        raise OdbError(f"{what or 'omnidata_b200'} failed (status {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().odb_launch_count())

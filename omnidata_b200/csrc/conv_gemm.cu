@@ -1,0 +1,491 @@
+// Implicit-GEMM convolution / linear layer for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM
+// -> fused epilogue -> TMA store.  One persistent CTA per SM, warp-specialised:
+//   warp 0    TMA producer (one elected lane)
+//   warp 1    TMEM allocation + tcgen05.mma issue (one elected lane)
+//   warps 2-5 epilogue: tcgen05.ld -> bias/act/residual -> bf16 -> swizzled smem -> TMA store
+//
+// The A operand of the GEMM (rows = output pixels, K = taps x input channels) is never
+// materialised: each K block is a 4-D TMA box {64 ch, tile_w, tile_h, 1} of the channels-last
+// input, shifted by the tap offset; out-of-bounds rows/columns are zero-filled by the TMA unit,
+// which is exactly the convolution zero padding.  The box lands in shared memory as dense
+// 128-byte rows with the 128B swizzle, i.e. directly in the canonical K-major UMMA layout.
+//
+// What this replaces in the reference is listed in include/omnidata_b200.h (odb_conv_gemm).
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/omnidata_b200.h"
+
+namespace odb {
+
+constexpr int kTileRows = 128;                 // UMMA M
+constexpr int kKBlock = 64;                    // bf16 elements per K block = one 128B swizzle row
+constexpr int kABytes = kTileRows * 128;       // 16 KiB per stage
+constexpr int kStagingBytes = kTileRows * 128; // one 128 x 64 bf16 output chunk
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+
+struct ConvGemmParams {
+  CUtensorMap a_map[ODB_MAX_VIEWS];
+  CUtensorMap b_map;
+  CUtensorMap out_map;
+  CUtensorMap out2_map;
+  int num_taps;
+  int kb_per_tap;
+  int8_t tap_view[12];
+  int8_t tap_dx[12];
+  int8_t tap_dy[12];
+  int tiles_n, tiles_x, tiles_y, tiles_b;
+  int tile_w, tile_h;
+  int out_w, out_h, out_b, n_total;
+  const float* bias;
+  long long bias_sb;
+  const bf16* residual;
+  long long res_sx, res_sy, res_sb;
+  int act;
+  int has_out2;
+  const float* head_w;
+  const float* head_b;
+  int head_c;
+  int head_relu;
+  float* head_out;
+};
+
+template <int BLOCK_N, int STAGES, int NSTAGING>
+struct SmemPlan {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = STAGES * kABytes;
+  static constexpr int kCOff = kBOff + STAGES * kBBytes;
+  static constexpr int kBarOff = kCOff + NSTAGING * kStagingBytes;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base pointer
+  static constexpr int kBarBytes = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int kTotal = kBarOff + kBarBytes + 1024;  // +1024: manual 1 KiB alignment
+};
+
+template <int BLOCK_N>
+struct TmemCols {
+  static constexpr uint32_t value =
+      2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128 : 2 * BLOCK_N <= 256 ? 256 : 512;
+};
+
+template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Plan::kBarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+    for (int v = 0; v < ODB_MAX_VIEWS; ++v) tma_prefetch_desc(&p.a_map[v]);
+    tma_prefetch_desc(&p.b_map);
+    if (!HEAD) tma_prefetch_desc(&p.out_map);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TmemCols<BLOCK_N>::value);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_tiles = p.tiles_n * p.tiles_x * p.tiles_y * p.tiles_b;
+  const int num_kb = p.num_taps * p.kb_per_tap;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.tile_w * p.tile_h) * 128u;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tn = t % p.tiles_n; t /= p.tiles_n;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int tb = t / p.tiles_y;
+        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const CUtensorMap* amap = &p.a_map[p.tap_view[tap]];
+          const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), a_bytes + Plan::kBBytes);
+            tma_load_4d(smem_base + Plan::kAOff + stage * kABytes, amap, full_bar(stage),
+                        kb * kKBlock, ax, ay, tb);
+            tma_load_2d(smem_base + Plan::kBOff + stage * Plan::kBBytes, &p.b_map, full_bar(stage),
+                        (tap * p.kb_per_tap + kb) * kKBlock, tn * BLOCK_N);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileRows, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const uint32_t acc = iter & 1u;
+        const uint32_t acc_phase = (iter >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_base + Plan::kAOff + stage * kABytes);
+          const uint64_t bdesc = umma_desc_sw128(smem_base + Plan::kBOff + stage * Plan::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kKBlock / 16; ++k) {
+            // +32 bytes (= 2 in 16-byte units) per UMMA_K=16 inside the 128B swizzle row
+            umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;      // accumulator row == pixel within the tile
+    const bool store_leader = (warp == 2 && lane == 0);
+    const int tw = p.tile_w;
+    const int ly = row / tw, lx = row - ly * tw;
+    const bool row_in_tile = row < p.tile_w * p.tile_h;
+    uint32_t iter = 0;
+    uint32_t chunk_counter = 0;
+    const int bufs_per_chunk = p.has_out2 ? 2 : 1;
+    const int slots = NSTAGING > 0 ? NSTAGING / bufs_per_chunk : 1;
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      int t = tile;
+      const int tn = t % p.tiles_n; t /= p.tiles_n;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int tb = t / p.tiles_y;
+      const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+      const int x = x0 + lx, y = y0 + ly;
+      const bool valid = row_in_tile && x < p.out_w && y < p.out_h;
+      const uint32_t acc = iter & 1u;
+      const uint32_t acc_phase = (iter >> 1) & 1u;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+
+      if constexpr (HEAD) {
+        // ---- DPT head tail: relu(conv + bias) (32 ch) -> 1x1 conv to head_c channels -> relu -> NCHW fp32
+        uint32_t r[32];
+        tmem_ld_32x32(t_row, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float f = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
+          v[j] = fmaxf(f, 0.f);
+        }
+        if (valid) {
+          for (int k = 0; k < p.head_c; ++k) {
+            float o = __ldg(p.head_b + k);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o = fmaf(v[j], __ldg(p.head_w + k * 32 + j), o);
+            if (p.head_relu) o = fmaxf(o, 0.f);
+            p.head_out[((static_cast<long long>(tb) * p.head_c + k) * p.out_h + y) * p.out_w + x] = o;
+          }
+        }
+      } else {
+        const int n0 = tn * BLOCK_N;
+        const float* bias = p.bias ? p.bias + static_cast<long long>(tb) * p.bias_sb + n0 : nullptr;
+        const bf16* res = p.residual
+                              ? p.residual + tb * p.res_sb + y * p.res_sy + x * p.res_sx + n0
+                              : nullptr;
+        constexpr int kChunks = BLOCK_N / 64;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c, ++chunk_counter) {
+          uint32_t r[64];
+          tmem_ld_32x32(t_row + c * 64, r);
+          tmem_ld_32x32(t_row + c * 64 + 32, r + 32);
+          // residual loads overlap the TMEM read
+          uint4 rv[8];
+          if (res != nullptr && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res + c * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = __ldg(rp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = make_uint4(0, 0, 0, 0);
+          }
+          tmem_ld_wait();
+          if (c == kChunks - 1) {
+            // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          uint32_t packed[32], packed_relu[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
+            if (bias) {
+              f0 += __ldg(bias + c * 64 + 2 * j);
+              f1 += __ldg(bias + c * 64 + 2 * j + 1);
+            }
+            if (p.act == ODB_ACT_RELU) {
+              f0 = fmaxf(f0, 0.f);
+              f1 = fmaxf(f1, 0.f);
+            } else if (p.act == ODB_ACT_GELU) {
+              f0 = gelu_erf(f0);
+              f1 = gelu_erf(f1);
+            }
+            const uint32_t ru = reinterpret_cast<const uint32_t*>(rv)[j];
+            const float2 rr = unpack_bf16x2(ru);
+            f0 += rr.x;
+            f1 += rr.y;
+            packed[j] = pack_bf16x2(f0, f1);
+            packed_relu[j] = pack_bf16x2(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
+          }
+          // ---- staging slot handshake
+          const int slot = static_cast<int>(chunk_counter % static_cast<uint32_t>(slots));
+          if (store_leader) {
+            if (slots >= 4) tma_store_wait_read<3>();
+            else if (slots == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
+          named_bar_sync(1, kEpiThreads);
+          const uint32_t buf0 = smem_base + Plan::kCOff + (slot * bufs_per_chunk) * kStagingBytes;
+          const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = buf0 + rowoff + (static_cast<uint32_t>(j ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j]),
+                         "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                         : "memory");
+          }
+          if (p.has_out2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t addr =
+                  buf0 + kStagingBytes + rowoff + (static_cast<uint32_t>(j ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                           "r"(packed_relu[4 * j]), "r"(packed_relu[4 * j + 1]),
+                           "r"(packed_relu[4 * j + 2]), "r"(packed_relu[4 * j + 3])
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, kEpiThreads);
+          if (store_leader) {
+            tma_store_4d(&p.out_map, buf0, n0 + c * 64, x0, y0, tb);
+            if (p.has_out2) tma_store_4d(&p.out2_map, buf0 + kStagingBytes, n0 + c * 64, x0, y0, tb);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (store_leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TmemCols<BLOCK_N>::value);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+
+static int encode_view_map(CUtensorMap* map, const odb_view& v, int box_c, int box_w, int box_h,
+                           CUtensorMapSwizzle swz) {
+  if (v.ptr == nullptr) return fail(ODB_ERR_INVALID, "conv_gemm: null view pointer");
+  if ((reinterpret_cast<uintptr_t>(v.ptr) & 15u) != 0)
+    return fail(ODB_ERR_INVALID, "conv_gemm: view pointer must be 16-byte aligned");
+  if (v.c % 8 != 0) return fail(ODB_ERR_INVALID, "conv_gemm: channel count must be a multiple of 8");
+  cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.b};
+  // strides of dims 1..3 in bytes; a unit extent may carry any (16B-multiple) stride
+  long long sx = v.sx, sy = v.sy, sb = v.sb;
+  if (v.w == 1 && sx == 0) sx = v.c;
+  if (v.h == 1 && sy == 0) sy = (long long)v.w * sx;
+  if (v.b == 1 && sb == 0) sb = (long long)v.h * sy;
+  if (sx % 8 != 0 || sy % 8 != 0 || sb % 8 != 0 || sx <= 0 || sy <= 0 || sb <= 0)
+    return fail(ODB_ERR_INVALID, "conv_gemm: view strides must be positive multiples of 8 elements");
+  cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims,
+                      strides, box, estr, swz);
+}
+
+template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD>
+static int launch_instance(const ConvGemmParams& p, int grid, cudaStream_t stream) {
+  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, STAGES, NSTAGING, HEAD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kTotal);
+    if (e != cudaSuccess) return fail_cuda(e, "conv_gemm: cudaFuncSetAttribute");
+    configured = true;
+  }
+  kernel<<<grid, kNumThreads, Plan::kTotal, stream>>>(p);
+  count_launch();
+  return check_launch("conv_gemm");
+}
+
+}  // namespace odb
+
+using namespace odb;
+
+extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (d == nullptr) return fail(ODB_ERR_INVALID, "conv_gemm: null descriptor");
+  if (d->num_views < 1 || d->num_views > ODB_MAX_VIEWS || d->num_taps < 1 ||
+      d->num_taps > ODB_MAX_TAPS)
+    return fail(ODB_ERR_INVALID, "conv_gemm: bad view/tap count");
+  const int C = d->views[0].c;
+  for (int v = 0; v < d->num_views; ++v)
+    if (d->views[v].c != C) return fail(ODB_ERR_INVALID, "conv_gemm: views disagree on channels");
+  for (int t = 0; t < d->num_taps; ++t)
+    if (d->tap_view[t] < 0 || d->tap_view[t] >= d->num_views)
+      return fail(ODB_ERR_INVALID, "conv_gemm: tap refers to a missing view");
+  const bool head = d->head_out != nullptr;
+  const int N = d->n;
+  if (head) {
+    if (N != 32 || d->head_c < 1 || d->head_w == nullptr || d->head_b == nullptr)
+      return fail(ODB_ERR_INVALID, "conv_gemm: head tail needs n == 32, head_w, head_b");
+  } else {
+    if (N % 64 != 0) return fail(ODB_ERR_INVALID, "conv_gemm: n must be a multiple of 64");
+    if (d->out.ptr == nullptr) return fail(ODB_ERR_INVALID, "conv_gemm: null output");
+  }
+  if (d->weight == nullptr || (reinterpret_cast<uintptr_t>(d->weight) & 15u) != 0)
+    return fail(ODB_ERR_INVALID, "conv_gemm: weight must be non-null and 16-byte aligned");
+  const long long K = (long long)d->num_taps * C;
+
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int ow = d->out.w, oh = d->out.h, ob = d->out.b;
+  if (ow < 1 || oh < 1 || ob < 1) return fail(ODB_ERR_INVALID, "conv_gemm: empty output extent");
+  int tw = d->tile_w, th = d->tile_h;
+  if (tw <= 0 || th <= 0) {
+    if (oh == 1) { tw = 128; th = 1; }
+    else if (ow % 16 == 0 && oh % 8 == 0) { tw = 16; th = 8; }
+    else if (ow % 32 == 0 && oh % 4 == 0) { tw = 32; th = 4; }
+    else if (ow <= 128) { tw = ow; th = 128 / ow; if (th > oh) th = oh; }
+    else { tw = 128; th = 1; }
+  }
+  if (tw * th > kTileRows || tw > 256 || th > 256)
+    return fail(ODB_ERR_INVALID, "conv_gemm: tile_w * tile_h must be <= 128");
+  p.tile_w = tw; p.tile_h = th;
+  p.tiles_x = (ow + tw - 1) / tw;
+  p.tiles_y = (oh + th - 1) / th;
+  p.tiles_b = ob;
+  p.out_w = ow; p.out_h = oh; p.out_b = ob; p.n_total = N;
+
+  int block_n = d->block_n;
+  if (head) block_n = 32;
+  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
+  if (block_n == 0) {
+    block_n = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
+    const int sms = num_sms();
+    while (block_n > 64 && m_tiles * (N / block_n) < sms) block_n /= 2;
+  }
+  if (!(block_n == 256 || block_n == 128 || block_n == 64 || block_n == 32) || N % block_n != 0)
+    return fail(ODB_ERR_INVALID, "conv_gemm: unsupported block_n");
+  p.tiles_n = N / block_n;
+  if (m_tiles * p.tiles_n > 0x7fffffffLL) return fail(ODB_ERR_INVALID, "conv_gemm: too many tiles");
+
+  p.num_taps = d->num_taps;
+  p.kb_per_tap = (C + kKBlock - 1) / kKBlock;
+  for (int t = 0; t < d->num_taps; ++t) {
+    p.tap_view[t] = d->tap_view[t];
+    p.tap_dx[t] = d->tap_dx[t];
+    p.tap_dy[t] = d->tap_dy[t];
+  }
+  int rc;
+  for (int v = 0; v < ODB_MAX_VIEWS; ++v) {
+    // unused slots alias view 0 so that prefetch.tensormap always sees a valid descriptor
+    const odb_view& src = d->views[v < d->num_views ? v : 0];
+    rc = encode_view_map(&p.a_map[v], src, kKBlock, tw, th, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    if ((K * 2) % 16 != 0) return fail(ODB_ERR_INVALID, "conv_gemm: K must be a multiple of 8");
+    cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    rc = encode_tiled(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->weight),
+                      dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  if (!head) {
+    if (d->out.c != N) return fail(ODB_ERR_INVALID, "conv_gemm: out.c must equal n");
+    rc = encode_view_map(&p.out_map, d->out, 64, tw, th, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (d->out2.ptr) {
+      odb_view o2 = d->out2;
+      if (o2.c != N || o2.w != ow || o2.h != oh || o2.b != ob)
+        return fail(ODB_ERR_INVALID, "conv_gemm: out2 extent mismatch");
+      rc = encode_view_map(&p.out2_map, o2, 64, tw, th, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      p.has_out2 = 1;
+    } else {
+      p.out2_map = p.out_map;
+    }
+  } else {
+    p.out_map = p.a_map[0];
+    p.out2_map = p.a_map[0];
+  }
+  p.bias = d->bias;
+  p.bias_sb = d->bias_sb;
+  if (d->residual.ptr) {
+    if ((reinterpret_cast<uintptr_t>(d->residual.ptr) & 15u) || d->residual.sx % 8 ||
+        d->residual.sy % 8 || d->residual.sb % 8)
+      return fail(ODB_ERR_INVALID, "conv_gemm: residual must be 16-byte aligned / strided");
+    p.residual = static_cast<const bf16*>(d->residual.ptr);
+    p.res_sx = d->residual.sx; p.res_sy = d->residual.sy; p.res_sb = d->residual.sb;
+  }
+  p.act = d->act;
+  p.head_w = d->head_w; p.head_b = d->head_b; p.head_c = d->head_c; p.head_relu = d->head_relu;
+  p.head_out = d->head_out;
+
+  const long long total = m_tiles * p.tiles_n;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  switch (block_n) {
+    case 256: return launch_instance<256, 4, 2, false>(p, grid, stream);
+    case 128: return launch_instance<128, 5, 4, false>(p, grid, stream);
+    case 64: return launch_instance<64, 6, 4, false>(p, grid, stream);
+    case 32:
+      if (!head) return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: block_n 32 only with the head tail");
+      return launch_instance<32, 8, 0, true>(p, grid, stream);
+  }
+  return fail(ODB_ERR_INVALID, "conv_gemm: unreachable");
+}

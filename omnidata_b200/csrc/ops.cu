@@ -1,0 +1,481 @@
+// HBM-bound kernels of the DPT-Hybrid path: LayerNorm, GroupNorm (stats / apply / stem tail),
+// stem im2col, bilinear x2 (+ skip add), cls row, ProjectReadout cls term.
+// All activations are channels-last bf16; every thread moves 16-byte vectors (8 channels),
+// consecutive threads touch consecutive addresses.  What each replaces in the reference is
+// documented in include/omnidata_b200.h.
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/omnidata_b200.h"
+
+namespace odb {
+
+ODB_DEVINL void load8(const bf16* p, float* v) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+               d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+ODB_DEVINL void store8(bf16* p, const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (cols <= 1024 -> <= 4 vectors / lane).
+template <int VPL>  // 16-byte vectors per lane; cols = VPL * 256
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta,
+                                                        bf16* __restrict__ y, long long rows,
+                                                        float eps) {
+  constexpr int COLS = VPL * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* xr = x + row * COLS;
+  float v[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    load8(xr + (i * 32 + lane) * 8, v[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+  }
+  const float mean = warp_sum(s) * (1.0f / COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[i][j] - mean;
+      q += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / COLS) + eps);
+  bf16* yr = y + row * COLS;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c0 = (i * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + bb[j];
+    store8(yr + c0, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics.  Block = (image, pixel slab); thread = (channel octet, pixel lane).
+// Per-channel partial sums are combined per group in shared memory, one atomicAdd pair per
+// (block, group).
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const bf16* __restrict__ x,
+                                                              float* __restrict__ stats, int hw,
+                                                              int c, int groups,
+                                                              int pixels_per_block) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int b = blockIdx.y;
+  const int octets = c >> 3;
+  const int cpg = c / groups;
+  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int p0 = blockIdx.x * pixels_per_block;
+  const int p1 = min(hw, p0 + pixels_per_block);
+  const int oct = threadIdx.x % octets;
+  const int plane = threadIdx.x / octets;
+  const int planes = blockDim.x / octets;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (plane < planes) {
+    const bf16* base = x + ((long long)b * hw) * c + oct * 8;
+    for (int p = p0 + plane; p < p1; p += planes) {
+      float v[8];
+      load8(base + (long long)p * c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] += v[j] * v[j]; }
+    }
+  }
+  if (cpg >= 8) {
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ts += s[j]; tq += q[j]; }
+    const int g = (oct * 8) / cpg;
+    atomicAdd(&s_sum[g], ts);
+    atomicAdd(&s_sq[g], tq);
+  } else {
+    for (int j0 = 0; j0 < 8; j0 += cpg) {
+      float ts = 0.f, tq = 0.f;
+      for (int j = j0; j < j0 + cpg; ++j) { ts += s[j]; tq += q[j]; }
+      const int g = (oct * 8 + j0) / cpg;
+      atomicAdd(&s_sum[g], ts);
+      atomicAdd(&s_sq[g], tq);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    atomicAdd(&stats[((long long)b * groups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
+    atomicAdd(&stats[((long long)b * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  }
+}
+
+struct GnCoef {  // per-channel scale/shift of one image: y = x * a + b
+  float a, b;
+};
+ODB_DEVINL GnCoef gn_coef(const float* stats, const float* gamma, const float* beta, int b,
+                          int groups, int cpg, int ch, float inv_n, float eps) {
+  const int g = ch / cpg;
+  const float s = __ldg(&stats[((long long)b * groups + g) * 2 + 0]);
+  const float q = __ldg(&stats[((long long)b * groups + g) * 2 + 1]);
+  const float mean = s * inv_n;
+  const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  GnCoef k;
+  k.a = rstd * __ldg(gamma + ch);
+  k.b = __ldg(beta + ch) - mean * k.a;
+  return k;
+}
+
+// y = relu?( gn(x) + shortcut ); thread = (pixel, channel octet).
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const bf16* __restrict__ res,
+    const float* __restrict__ res_stats, const float* __restrict__ res_gamma,
+    const float* __restrict__ res_beta, bf16* __restrict__ y, int hw, int c, int groups, float eps,
+    int relu) {
+  const int b = blockIdx.y;
+  const int octets = c >> 3;
+  const int cpg = c / groups;
+  const float inv_n = 1.0f / ((float)hw * (float)cpg);
+  const long long total = (long long)hw * octets;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int oct = (int)(i % octets);
+    const long long off = ((long long)b * hw) * c + i * 8;
+    float v[8], o[8];
+    load8(x + off, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const GnCoef k = gn_coef(stats, gamma, beta, b, groups, cpg, oct * 8 + j, inv_n, eps);
+      o[j] = v[j] * k.a + k.b;
+    }
+    if (res != nullptr) {
+      float r[8];
+      load8(res + off, r);
+      if (res_stats != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const GnCoef k =
+              gn_coef(res_stats, res_gamma, res_beta, b, groups, cpg, oct * 8 + j, inv_n, eps);
+          r[j] = r[j] * k.a + k.b;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    store8(y + off, o);
+  }
+}
+
+// Stem: GroupNorm + ReLU + MaxPool 3x3 s2, TF-SAME pad (0,1): window rows/cols 2o..2o+2, clipped.
+__global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, bf16* __restrict__ y, int h, int w, int c, int groups,
+    float eps) {
+  const int b = blockIdx.y;
+  const int octets = c >> 3;
+  const int cpg = c / groups;
+  const int oh = h / 2, ow = w / 2;
+  const float inv_n = 1.0f / ((float)h * (float)w * (float)cpg);
+  const long long total = (long long)oh * ow * octets;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int oct = (int)(i % octets);
+    const long long pix = i / octets;
+    const int ox = (int)(pix % ow), oy = (int)(pix / ow);
+    GnCoef k[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      k[j] = gn_coef(stats, gamma, beta, b, groups, cpg, oct * 8 + j, inv_n, eps);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;  // relu output is >= 0, so 0 is the identity of max
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = 2 * oy + dy;
+      if (iy >= h) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = 2 * ox + dx;
+        if (ix >= w) continue;
+        float v[8];
+        load8(x + (((long long)b * h + iy) * w + ix) * c + oct * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          m[j] = fmaxf(m[j], v[j] * k[j].a + k[j].b);  // relu folded into the 0-initialised max
+        }
+      }
+    }
+    store8(y + (((long long)b * oh + oy) * ow + ox) * c + oct * 8, m);
+  }
+}
+
+// Stem im2col: fp32 NCHW -> bf16 [b*oh*ow][kpad], column (ky*7+kx)*3+ch, TF-SAME pad (2,3), stride 2.
+// Thread = (output pixel, 8-column group); the 8 columns are gathered with scalar loads that hit L1.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x,
+                                                          bf16* __restrict__ cols, int b, int h,
+                                                          int w, int kpad) {
+  const int oh = h / 2, ow = w / 2;
+  const int groups8 = kpad >> 3;
+  const long long total = (long long)b * oh * ow * groups8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups8);
+    const long long pix = i / groups8;
+    const int ox = (int)(pix % ow);
+    const int oy = (int)((pix / ow) % oh);
+    const int bi = (int)(pix / ((long long)ow * oh));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = g * 8 + j;
+      float val = 0.f;
+      if (col < 147) {
+        const int ch = col % 3;
+        const int kx = (col / 3) % 7;
+        const int ky = col / 21;
+        const int iy = 2 * oy + ky - 2, ix = 2 * ox + kx - 2;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+          val = __ldg(x + (((long long)bi * 3 + ch) * h + iy) * w + ix);
+      }
+      v[j] = val;
+    }
+    store8(cols + pix * kpad + g * 8, v);
+  }
+}
+
+// Bilinear x2, align_corners=True: src = dst * (n-1)/(2n-1).  out = up(z) (+ res); out_relu = relu(out).
+__global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restrict__ z,
+                                                             const bf16* __restrict__ res,
+                                                             bf16* __restrict__ out,
+                                                             bf16* __restrict__ out_relu, int b,
+                                                             int h, int w, int c) {
+  const int octets = c >> 3;
+  const int oh = 2 * h, ow = 2 * w;
+  const float sy = (float)(h - 1) / (float)(oh - 1), sx = (float)(w - 1) / (float)(ow - 1);
+  const long long total = (long long)b * oh * ow * octets;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int oct = (int)(i % octets);
+    const long long pix = i / octets;
+    const int ox = (int)(pix % ow);
+    const int oy = (int)((pix / ow) % oh);
+    const int bi = (int)(pix / ((long long)ow * oh));
+    const float fy = oy * sy, fx = ox * sx;
+    const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float wy = fy - (float)y0, wx = fx - (float)x0;
+    const bf16* zb = z + (long long)bi * h * w * c + oct * 8;
+    float a[8], bq[8], cc[8], d[8], o[8];
+    load8(zb + ((long long)y0 * w + x0) * c, a);
+    load8(zb + ((long long)y0 * w + x1) * c, bq);
+    load8(zb + ((long long)y1 * w + x0) * c, cc);
+    load8(zb + ((long long)y1 * w + x1) * c, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float top = a[j] + (bq[j] - a[j]) * wx;
+      const float bot = cc[j] + (d[j] - cc[j]) * wx;
+      o[j] = top + (bot - top) * wy;
+    }
+    const long long off = pix * c + oct * 8;
+    if (res != nullptr) {
+      float r[8];
+      load8(res + off, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += r[j];
+    }
+    store8(out + off, o);
+    if (out_relu != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+      store8(out_relu + off, o);
+    }
+  }
+}
+
+__global__ void write_cls_row_kernel(bf16* __restrict__ tokens, const float* __restrict__ cls,
+                                     const float* __restrict__ pos0, int tokens_n, int c) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < c; i += blockDim.x)
+    tokens[(long long)b * tokens_n * c + i] = __float2bfloat16_rn(cls[i] + pos0[i]);
+}
+
+// out[b][n] = bias[n] + sum_k w[n][c + k] * tokens[b][0][k];  one warp per (b, n).
+__global__ void __launch_bounds__(256) readout_cls_bias_kernel(const bf16* __restrict__ w,
+                                                               const float* __restrict__ bias,
+                                                               const bf16* __restrict__ tokens,
+                                                               float* __restrict__ out, int b_n,
+                                                               int tokens_n, int c) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)b_n * c) return;
+  const int n = (int)(wid % c), b = (int)(wid / c);
+  const bf16* wr = w + (long long)n * 2 * c + c;
+  const bf16* t = tokens + (long long)b * tokens_n * c;
+  float acc = 0.f;
+  for (int k = lane * 8; k < c; k += 256) {
+    float a[8], x[8];
+    load8(wr + k, a);
+    load8(t + k, x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(a[j], x[j], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[wid] = acc + __ldg(bias + n);
+}
+
+static int grid_for(long long work_items, int block, int max_blocks_per_sm = 8) {
+  long long blocks = (work_items + block - 1) / block;
+  const long long cap = (long long)num_sms() * max_blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace odb
+
+using namespace odb;
+
+extern "C" int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y,
+                             int64_t rows, int32_t cols, float eps, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !gamma || !beta || !y || rows < 0) return fail(ODB_ERR_INVALID, "layernorm: bad argument");
+  if (rows == 0) return ODB_OK;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const bf16* xp = static_cast<const bf16*>(x);
+  bf16* yp = static_cast<bf16*>(y);
+  switch (cols) {
+    case 256: layernorm_kernel<1><<<grid, 256, 0, stream>>>(xp, gamma, beta, yp, rows, eps); break;
+    case 512: layernorm_kernel<2><<<grid, 256, 0, stream>>>(xp, gamma, beta, yp, rows, eps); break;
+    case 768: layernorm_kernel<3><<<grid, 256, 0, stream>>>(xp, gamma, beta, yp, rows, eps); break;
+    case 1024: layernorm_kernel<4><<<grid, 256, 0, stream>>>(xp, gamma, beta, yp, rows, eps); break;
+    default: return fail(ODB_ERR_UNSUPPORTED, "layernorm: cols must be 256/512/768/1024");
+  }
+  count_launch();
+  return check_launch("layernorm");
+}
+
+static int gn_args_ok(int b, int hw, int c, int groups) {
+  return b > 0 && hw > 0 && c > 0 && groups > 0 && groups <= 64 && c % 8 == 0 && c % groups == 0 &&
+         (c / 8) <= 256 && ((c / groups) >= 8 ? (c / groups) % 8 == 0 : 8 % (c / groups) == 0);
+}
+
+extern "C" int odb_groupnorm_stats(const void* x, float* stats, int32_t b, int32_t hw, int32_t c,
+                                   int32_t groups, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !stats || !gn_args_ok(b, hw, c, groups))
+    return fail(ODB_ERR_INVALID, "groupnorm_stats: bad argument");
+  // ~4 slabs per SM across the batch keeps every SM busy without drowning in atomics
+  int slabs = (num_sms() * 4 + b - 1) / b;
+  if (slabs < 1) slabs = 1;
+  int ppb = (hw + slabs - 1) / slabs;
+  const int planes = 256 / (c / 8);
+  if (ppb < planes * 4) ppb = planes * 4;
+  dim3 grid((hw + ppb - 1) / ppb, b);
+  groupnorm_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), stats, hw, c,
+                                                   groups, ppb);
+  count_launch();
+  return check_launch("groupnorm_stats");
+}
+
+extern "C" int odb_groupnorm_apply(const void* x, const float* stats, const float* gamma,
+                                   const float* beta, const void* res, const float* res_stats,
+                                   const float* res_gamma, const float* res_beta, void* y, int32_t b,
+                                   int32_t hw, int32_t c, int32_t groups, float eps, int32_t relu,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !stats || !gamma || !beta || !y || !gn_args_ok(b, hw, c, groups))
+    return fail(ODB_ERR_INVALID, "groupnorm_apply: bad argument");
+  if (res_stats && (!res || !res_gamma || !res_beta))
+    return fail(ODB_ERR_INVALID, "groupnorm_apply: res_stats needs res, res_gamma, res_beta");
+  int gx = grid_for((long long)hw * (c / 8), 256) / b;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, b);
+  groupnorm_apply_kernel<<<grid, 256, 0, stream>>>(
+      static_cast<const bf16*>(x), stats, gamma, beta, static_cast<const bf16*>(res), res_stats,
+      res_gamma, res_beta, static_cast<bf16*>(y), hw, c, groups, eps, relu);
+  count_launch();
+  return check_launch("groupnorm_apply");
+}
+
+extern "C" int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const float* gamma,
+                                        const float* beta, void* y, int32_t b, int32_t h, int32_t w,
+                                        int32_t c, int32_t groups, float eps, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !stats || !gamma || !beta || !y || h < 2 || w < 2 || (h & 1) || (w & 1) ||
+      !gn_args_ok(b, h * w, c, groups))
+    return fail(ODB_ERR_INVALID, "stem_gn_relu_maxpool: bad argument");
+  int gx = grid_for((long long)(h / 2) * (w / 2) * (c / 8), 256) / b;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, b);
+  stem_gn_relu_maxpool_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), stats, gamma,
+                                                        beta, static_cast<bf16*>(y), h, w, c,
+                                                        groups, eps);
+  count_launch();
+  return check_launch("stem_gn_relu_maxpool");
+}
+
+extern "C" int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h, int32_t w,
+                               int32_t kpad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !cols || b < 1 || h < 2 || w < 2 || (h & 1) || (w & 1) || kpad < 152 || kpad % 8)
+    return fail(ODB_ERR_INVALID, "stem_im2col: bad argument");
+  const long long total = (long long)b * (h / 2) * (w / 2) * (kpad / 8);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, static_cast<bf16*>(cols), b, h, w,
+                                                               kpad);
+  count_launch();
+  return check_launch("stem_im2col");
+}
+
+extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, void* out_relu,
+                                  int32_t b, int32_t h, int32_t w, int32_t c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!z || !out || b < 1 || h < 1 || w < 1 || c < 8 || c % 8)
+    return fail(ODB_ERR_INVALID, "upsample2x_add: bad argument");
+  const long long total = (long long)b * 4 * h * w * (c / 8);
+  upsample2x_add_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
+      static_cast<const bf16*>(z), static_cast<const bf16*>(res), static_cast<bf16*>(out),
+      static_cast<bf16*>(out_relu), b, h, w, c);
+  count_launch();
+  return check_launch("upsample2x_add");
+}
+
+extern "C" int odb_write_cls_row(void* tokens, const float* cls, const float* pos0, int32_t b,
+                                 int32_t tokens_n, int32_t c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!tokens || !cls || !pos0 || b < 1 || tokens_n < 1 || c < 1)
+    return fail(ODB_ERR_INVALID, "write_cls_row: bad argument");
+  write_cls_row_kernel<<<b, 256, 0, stream>>>(static_cast<bf16*>(tokens), cls, pos0, tokens_n, c);
+  count_launch();
+  return check_launch("write_cls_row");
+}
+
+extern "C" int odb_readout_cls_bias(const void* w, const float* bias, const void* tokens, float* out,
+                                    int32_t b, int32_t tokens_n, int32_t c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!w || !bias || !tokens || !out || b < 1 || tokens_n < 1 || c < 8 || c % 8)
+    return fail(ODB_ERR_INVALID, "readout_cls_bias: bad argument");
+  const long long warps = (long long)b * c;
+  const unsigned grid = (unsigned)((warps + 7) / 8);
+  readout_cls_bias_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(w), bias,
+                                                    static_cast<const bf16*>(tokens), out, b,
+                                                    tokens_n, c);
+  count_launch();
+  return check_launch("readout_cls_bias");
+}

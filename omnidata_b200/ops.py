@@ -1,0 +1,213 @@
+"""Thin torch-tensor front end of the C-ABI kernels (pointers + sizes only cross the boundary).
+
+Every function enqueues on torch's current CUDA stream and returns immediately.  Activations are
+channels-last bf16 tensors ([B, H, W, C] or [rows, C]); strides are taken from the tensors, so
+sliced / strided views (parity planes, token windows) are passed without copies.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+from ._capi import ACT_GELU, ACT_NONE, ACT_RELU, ConvGemmDesc, View, check, lib
+
+__all__ = [
+    "ACT_NONE", "ACT_RELU", "ACT_GELU", "conv_gemm", "linear", "conv1x1", "conv3x3", "conv3x3_s2",
+    "layernorm", "attention", "groupnorm_stats", "groupnorm_apply", "stem_gn_relu_maxpool",
+    "stem_im2col", "upsample2x_add", "write_cls_row", "readout_cls_bias", "pack_conv_weight",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _capi.OdbError(f"{name}: tensor must live on a CUDA device (no CPU path exists)")
+    if t.dtype != dtype:
+        raise _capi.OdbError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def _view4(t: torch.Tensor, name: str) -> View:
+    """[B,H,W,C] (or [rows,C] -> B=H=1) bf16 tensor with unit channel stride -> odb_view."""
+    _need(t, torch.bfloat16, name)
+    if t.dim() == 2:
+        t = t.unsqueeze(0).unsqueeze(0)
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise _capi.OdbError(f"{name}: need a channels-last [B,H,W,C] view with unit channel stride")
+    b, h, w, c = t.shape
+    return View(t.data_ptr(), c, w, h, b, t.stride(2), t.stride(1), t.stride(0))
+
+
+def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]], weight: torch.Tensor,
+              out: Optional[torch.Tensor], *, bias: Optional[torch.Tensor] = None,
+              bias_per_image: bool = False, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+              out2: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None, block_n: int = 0,
+              head: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, bool]] = None,
+              out_extent: Optional[Tuple[int, int, int]] = None) -> None:
+    """taps: (view index, dx, dy).  head = (w[head_c,32] f32, b[head_c] f32, out[B,head_c,H,W] f32, relu)."""
+    d = ConvGemmDesc()
+    d.num_views = len(views)
+    for i, v in enumerate(views):
+        d.views[i] = _view4(v, f"view{i}")
+    d.num_taps = len(taps)
+    for i, (vi, dx, dy) in enumerate(taps):
+        d.tap_view[i], d.tap_dx[i], d.tap_dy[i] = vi, dx, dy
+    _need(weight, torch.bfloat16, "weight")
+    if not weight.is_contiguous():
+        raise _capi.OdbError("weight must be contiguous [n][taps*C]")
+    d.weight = weight.data_ptr()
+    d.n = weight.shape[0]
+    if out is not None:
+        d.out = _view4(out, "out")
+    if out2 is not None:
+        d.out2 = _view4(out2, "out2")
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+        d.bias = bias.data_ptr()
+        d.bias_sb = d.n if bias_per_image else 0
+    if residual is not None:
+        r = residual
+        if r.dim() == 3:  # [rows_per_image, C] broadcast over batch is passed as [1,H,W,C] with sb=0
+            r = r.unsqueeze(0)
+        rv = _view4(r, "residual")
+        if residual.dim() == 4 and residual.shape[0] == 1 and out is not None and out.dim() == 4 and out.shape[0] > 1:
+            rv.sb = 0
+        d.residual = rv
+    d.act = act
+    if tile is not None:
+        d.tile_w, d.tile_h = tile
+    d.block_n = block_n
+    if head is not None:
+        hw, hb, hout, hrelu = head
+        _need(hw, torch.float32, "head_w"); _need(hb, torch.float32, "head_b"); _need(hout, torch.float32, "head_out")
+        d.head_w, d.head_b, d.head_out = hw.data_ptr(), hb.data_ptr(), hout.data_ptr()
+        d.head_c = hw.shape[0]
+        d.head_relu = 1 if hrelu else 0
+        b, _, h, w = hout.shape
+        d.out = View(None, 32, w, h, b, 0, 0, 0)
+    check(lib().odb_conv_gemm(C.byref(d), _stream()), "odb_conv_gemm")
+
+
+TAPS_1 = [(0, 0, 0)]
+TAPS_3X3 = [(0, kx - 1, ky - 1) for ky in range(3) for kx in range(3)]
+
+
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """[N, Cin, kh, kw] (any float dtype) -> bf16 [N, kh*kw*Cin], tap-major / channel-minor."""
+    n = w.shape[0]
+    return w.permute(0, 2, 3, 1).reshape(n, -1).to(torch.bfloat16).contiguous()
+
+
+def linear(x, weight, out, **kw):
+    conv_gemm([x], TAPS_1, weight, out, **kw)
+
+
+def conv1x1(x, weight, out, **kw):
+    conv_gemm([x], TAPS_1, weight, out, **kw)
+
+
+def conv3x3(x, weight, out, **kw):
+    conv_gemm([x], TAPS_3X3, weight, out, **kw)
+
+
+def _parity_taps(mode: str):
+    # input index = 2*o + k - pad_before ; parity plane p, plane coordinate o + d
+    taps = []
+    for ky in range(3):
+        for kx in range(3):
+            if mode == "same":      # TF-SAME for even sizes: pad (0,1)
+                py, dy = (ky & 1), (1 if ky == 2 else 0)
+                px, dx = (kx & 1), (1 if kx == 2 else 0)
+            elif mode == "sym1":    # padding=1 both sides
+                py, dy = ((ky + 1) & 1), (-1 if ky == 0 else 0)
+                px, dx = ((kx + 1) & 1), (-1 if kx == 0 else 0)
+            else:
+                raise ValueError(mode)
+            taps.append((py * 2 + px, dx, dy))
+    return taps
+
+
+def conv3x3_s2(x, weight, out, mode: str, **kw):
+    """Stride-2 3x3 conv through four parity-plane views of x (no im2col, no copies)."""
+    planes = [x[:, py::2, px::2, :] for py in range(2) for px in range(2)]
+    conv_gemm(planes, _parity_taps(mode), weight, out, **kw)
+
+
+def layernorm(x, gamma, beta, out, eps: float = 1e-6):
+    _need(x, torch.bfloat16, "x"); _need(out, torch.bfloat16, "out")
+    _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
+    if not (x.is_contiguous() and out.is_contiguous()):
+        raise _capi.OdbError("layernorm: contiguous tensors required")
+    rows = x.numel() // x.shape[-1]
+    check(lib().odb_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows,
+                              x.shape[-1], eps, _stream()), "odb_layernorm")
+
+
+def attention(qkv, out, heads: int = 12, scale: float = 0.125):
+    _need(qkv, torch.bfloat16, "qkv"); _need(out, torch.bfloat16, "out")
+    b, n, c3 = qkv.shape
+    if not (qkv.is_contiguous() and out.is_contiguous()) or c3 != 3 * heads * 64:
+        raise _capi.OdbError("attention: qkv must be contiguous [B, tokens, 3*heads*64]")
+    check(lib().odb_attention(qkv.data_ptr(), out.data_ptr(), b, n, heads, scale, _stream()), "odb_attention")
+
+
+def groupnorm_stats(x, stats, groups: int = 32):
+    _need(x, torch.bfloat16, "x"); _need(stats, torch.float32, "stats")
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    check(lib().odb_fill_zero(stats.data_ptr(), stats.numel() * 4, _stream()), "odb_fill_zero")
+    check(lib().odb_groupnorm_stats(x.data_ptr(), stats.data_ptr(), b, hw, c, groups, _stream()),
+          "odb_groupnorm_stats")
+
+
+def groupnorm_apply(x, stats, gamma, beta, out, *, relu: bool, res=None, res_stats=None, res_gamma=None,
+                    res_beta=None, groups: int = 32, eps: float = 1e-5):
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    check(lib().odb_groupnorm_apply(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                    _ptr(res), _ptr(res_stats), _ptr(res_gamma), _ptr(res_beta),
+                                    out.data_ptr(), b, hw, c, groups, eps, 1 if relu else 0, _stream()),
+          "odb_groupnorm_apply")
+
+
+def stem_gn_relu_maxpool(x, stats, gamma, beta, out, groups: int = 32, eps: float = 1e-5):
+    b, h, w, c = x.shape
+    check(lib().odb_stem_gn_relu_maxpool(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                         out.data_ptr(), b, h, w, c, groups, eps, _stream()),
+          "odb_stem_gn_relu_maxpool")
+
+
+def stem_im2col(x, cols):
+    _need(x, torch.float32, "x"); _need(cols, torch.bfloat16, "cols")
+    b, ch, h, w = x.shape
+    if ch != 3 or not x.is_contiguous():
+        raise _capi.OdbError("stem_im2col: contiguous [B,3,H,W] fp32 input required")
+    check(lib().odb_stem_im2col(x.data_ptr(), cols.data_ptr(), b, h, w, cols.shape[-1], _stream()),
+          "odb_stem_im2col")
+
+
+def upsample2x_add(z, out, res=None, out_relu=None):
+    b, h, w, c = z.shape
+    check(lib().odb_upsample2x_add(z.data_ptr(), _ptr(res), out.data_ptr(), _ptr(out_relu), b, h, w, c,
+                                   _stream()), "odb_upsample2x_add")
+
+
+def write_cls_row(tokens, cls, pos0):
+    b, n, c = tokens.shape
+    check(lib().odb_write_cls_row(tokens.data_ptr(), cls.data_ptr(), pos0.data_ptr(), b, n, c, _stream()),
+          "odb_write_cls_row")
+
+
+def readout_cls_bias(w, bias, tokens, out):
+    b, n, c = tokens.shape
+    check(lib().odb_readout_cls_bias(w.data_ptr(), bias.data_ptr(), tokens.data_ptr(), out.data_ptr(), b, n,
+                                     c, _stream()), "odb_readout_cls_bias")

@@ -1,0 +1,308 @@
+"""Per-kernel numerics: each CUDA kernel (called through the C ABI) against a plain PyTorch fp32
+evaluation of the same op on the same bf16 inputs.  Tolerance: rel-L2 <= 1e-3 against the fp32
+result rounded to bf16 (the kernels compute bf16 x bf16 -> fp32 accumulate -> one bf16 rounding)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup(lib_built):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dev())
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def check(out, ref_fp32, name, tol=TOL):
+    ref = ref_fp32.to(torch.bfloat16).float()
+    err = rel_l2(out.float(), ref)
+    maxabs = float((out.float() - ref).abs().max())
+    assert math.isfinite(err) and err <= tol, f"{name}: rel-L2 {err:.3e} (max abs {maxabs:.3e}) > {tol}"
+
+
+def ops():
+    from omnidata_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("m,k,n,block_n", [
+    (300, 64, 64, 64), (128, 128, 64, 64), (1000, 768, 768, 0), (1000, 768, 768, 256), (1000, 768, 768, 128),
+    (577 * 4, 768, 2304, 0), (2000, 3072, 768, 0), (333, 160, 64, 64), (40000, 768, 768, 256), (20000, 256, 512, 0),
+])
+def test_linear_plain(m, k, n, block_n):
+    o = ops()
+    x = rnd(m, k).to(torch.bfloat16)
+    w = rnd(n, k, scale=k ** -0.5).to(torch.bfloat16)
+    out = torch.full((m, n), float("nan"), device=dev(), dtype=torch.bfloat16)
+    o.linear(x, w, out, block_n=block_n)
+    torch.cuda.synchronize()
+    check(out, x.float() @ w.float().t(), f"linear {m}x{k}x{n} bn{block_n}")
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_linear_epilogue(act):
+    o = ops()
+    m, k, n = 1500, 768, 1024
+    x = rnd(m, k).to(torch.bfloat16)
+    w = rnd(n, k, scale=k ** -0.5).to(torch.bfloat16)
+    bias = rnd(n)
+    res = rnd(m, n).to(torch.bfloat16)
+    out = torch.empty((m, n), device=dev(), dtype=torch.bfloat16)
+    out2 = torch.empty_like(out)
+    o.linear(x, w, out, bias=bias, residual=res, act=act, out2=out2)
+    torch.cuda.synchronize()
+    v = x.float() @ w.float().t() + bias
+    v = [v, F.relu(v), F.gelu(v)][act] + res.float()
+    check(out, v, f"linear epilogue act{act}")
+    check(out2, F.relu(v), f"linear epilogue act{act} relu copy")
+
+
+def conv_ref(x, w, stride=1, padding=1):
+    """x [B,H,W,C] bf16, w [N,C,kh,kw] bf16 -> [B,Ho,Wo,N] fp32."""
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=stride, padding=padding)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("b,h,w_,c,n,tile", [
+    (2, 24, 24, 64, 128, None), (2, 48, 48, 256, 256, None), (1, 96, 96, 64, 64, None), (3, 12, 12, 128, 256, None),
+    (1, 24, 24, 768, 256, (8, 16)), (1, 192, 192, 64, 128, (32, 4)),
+])
+def test_conv3x3(b, h, w_, c, n, tile):
+    o = ops()
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    w = rnd(n, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    bias = rnd(n)
+    out = torch.full((b, h, w_, n), float("nan"), device=dev(), dtype=torch.bfloat16)
+    o.conv3x3(x, o.pack_conv_weight(w), out, bias=bias, act=o.ACT_RELU, tile=tile)
+    torch.cuda.synchronize()
+    check(out, F.relu(conv_ref(x, w) + bias), f"conv3x3 {b}x{h}x{w_}x{c}->{n}")
+
+
+def test_conv3x3_residual_dual():
+    o = ops()
+    b, h, w_, c = 2, 48, 48, 256
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    skip = rnd(b, h, w_, c, seed=5).to(torch.bfloat16)
+    w = rnd(c, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    bias = rnd(c)
+    for bn in (128, 256):
+        out = torch.empty((b, h, w_, c), device=dev(), dtype=torch.bfloat16)
+        out2 = torch.empty_like(out)
+        o.conv3x3(x, o.pack_conv_weight(w), out, bias=bias, residual=skip, out2=out2, block_n=bn)
+        torch.cuda.synchronize()
+        ref = conv_ref(x, w) + bias + skip.float()
+        check(out, ref, f"conv3x3 residual bn{bn}")
+        check(out2, F.relu(ref), f"conv3x3 residual relu copy bn{bn}")
+
+
+@pytest.mark.parametrize("mode", ["same", "sym1"])
+def test_conv3x3_stride2(mode):
+    o = ops()
+    b, h, w_, c, n = 2, 48, 48, 128, 128
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    w = rnd(n, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    out = torch.empty((b, h // 2, w_ // 2, n), device=dev(), dtype=torch.bfloat16)
+    o.conv3x3_s2(x, o.pack_conv_weight(w), out, mode)
+    torch.cuda.synchronize()
+    xn = x.float().permute(0, 3, 1, 2)
+    if mode == "same":
+        xn = F.pad(xn, (0, 1, 0, 1))
+        ref = F.conv2d(xn, w.float(), stride=2)
+    else:
+        ref = F.conv2d(xn, w.float(), stride=2, padding=1)
+    check(out, ref.permute(0, 2, 3, 1), f"conv3x3 s2 {mode}")
+
+
+def test_conv1x1_stride2_view():
+    o = ops()
+    b, h, w_, c, n = 2, 48, 48, 256, 512
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    w = rnd(n, c, 1, 1, scale=c ** -0.5).to(torch.bfloat16)
+    out = torch.empty((b, h // 2, w_ // 2, n), device=dev(), dtype=torch.bfloat16)
+    o.conv1x1(x[:, ::2, ::2, :], o.pack_conv_weight(w), out)
+    torch.cuda.synchronize()
+    check(out, conv_ref(x, w, stride=2, padding=0), "conv1x1 s2")
+
+
+@pytest.mark.parametrize("hc", [1, 3])
+def test_head_tail(hc):
+    o = ops()
+    b, h, w_, c = 2, 64, 96, 128
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    w = rnd(32, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    bias = rnd(32)
+    hw = rnd(hc, 32, scale=0.3)
+    hb = rnd(hc, scale=0.1)
+    hout = torch.full((b, hc, h, w_), float("nan"), device=dev(), dtype=torch.float32)
+    o.conv3x3(x, o.pack_conv_weight(w), None, bias=bias, head=(hw, hb, hout, True))
+    torch.cuda.synchronize()
+    v = F.relu(conv_ref(x, w) + bias)                      # [b,h,w,32]
+    ref = F.relu(torch.einsum("bhwj,kj->bkhw", v, hw) + hb[None, :, None, None])
+    err = rel_l2(hout, ref)
+    assert err < 1e-4, f"head tail rel-L2 {err:.3e}"
+
+
+def test_readout_style_token_window():
+    """A = tokens[:, 1:, :] (strided window), per-image bias, GELU, output [B,24,24,C]."""
+    o = ops()
+    b, n, c = 3, 577, 768
+    tok = rnd(b, n, c).to(torch.bfloat16)
+    w = rnd(c, c, scale=c ** -0.5).to(torch.bfloat16)
+    bias = rnd(b, c)
+    out = torch.full((b, 1, 576, c), float("nan"), device=dev(), dtype=torch.bfloat16)
+    o.linear(tok[:, 1:, :].unsqueeze(1), w, out, bias=bias, bias_per_image=True, act=o.ACT_GELU)
+    torch.cuda.synchronize()
+    ref = F.gelu(tok[:, 1:, :].float() @ w.float().t() + bias[:, None, :])
+    check(out.view(b, 576, c), ref, "token window linear")
+
+
+def test_patch_proj_style_pos_residual():
+    """Output written into tokens[:, 1:, :] with a batch-broadcast residual (pos_embed)."""
+    o = ops()
+    b, c, k = 3, 768, 1024
+    x = rnd(b, 1, 576, k).to(torch.bfloat16)
+    w = rnd(c, k, scale=k ** -0.5).to(torch.bfloat16)
+    bias = rnd(c)
+    pos = rnd(1, 1, 577, c).to(torch.bfloat16)
+    tokens = torch.zeros(b, 577, c, device=dev(), dtype=torch.bfloat16)
+    o.linear(x, w, tokens[:, 1:, :].unsqueeze(1), bias=bias, residual=pos[:, :, 1:, :])
+    torch.cuda.synchronize()
+    ref = x.float().view(b, 576, k) @ w.float().t() + bias + pos[0, 0, 1:].float()
+    check(tokens[:, 1:, :], ref, "patch proj + pos")
+    assert float(tokens[:, 0, :].abs().max()) == 0.0
+
+
+def test_layernorm():
+    o = ops()
+    x = (rnd(4 * 577, 768) * 3 + 0.5).to(torch.bfloat16)
+    g, bta = rnd(768) * 0.1 + 1, rnd(768) * 0.1
+    out = torch.empty_like(x)
+    o.layernorm(x, g, bta, out, 1e-6)
+    torch.cuda.synchronize()
+    check(out, F.layer_norm(x.float(), (768,), g, bta, 1e-6), "layernorm")
+
+
+@pytest.mark.parametrize("b,tokens", [(2, 577), (1, 64), (1, 100)])
+def test_attention(b, tokens):
+    o = ops()
+    qkv = rnd(b, tokens, 2304).to(torch.bfloat16)
+    out = torch.full((b, tokens, 768), float("nan"), device=dev(), dtype=torch.bfloat16)
+    o.attention(qkv, out)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(b, tokens, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    ref = (p @ v).transpose(1, 2).reshape(b, tokens, 768)
+    # P is rounded to bf16 before the PV product (flash-style); budget 2e-3
+    check(out, ref, f"attention b{b} n{tokens}", tol=2e-3)
+
+
+@pytest.mark.parametrize("c,hw", [(64, 96 * 96), (256, 96 * 96), (128, 48 * 48), (1024, 24 * 24), (512, 100)])
+def test_groupnorm(c, hw):
+    o = ops()
+    b = 3
+    x = (rnd(b, hw, c) * 2 + 0.3).to(torch.bfloat16)
+    g, bta = rnd(c) * 0.1 + 1, rnd(c) * 0.1
+    stats = torch.empty(b, 32, 2, device=dev())
+    o.groupnorm_stats(x, stats)
+    out = torch.empty_like(x)
+    o.groupnorm_apply(x, stats, g, bta, out, relu=True)
+    torch.cuda.synchronize()
+    xn = x.float().transpose(1, 2)  # [b,c,hw]
+    ref = F.relu(F.group_norm(xn, 32, g, bta, 1e-5)).transpose(1, 2)
+    check(out, ref, f"groupnorm c{c}")
+    # with a normalised shortcut
+    s = (rnd(b, hw, c, seed=9) * 1.5).to(torch.bfloat16)
+    sstats = torch.empty(b, 32, 2, device=dev())
+    o.groupnorm_stats(s, sstats)
+    g2, b2 = rnd(c, seed=3) * 0.1 + 1, rnd(c, seed=4) * 0.1
+    o.groupnorm_apply(x, stats, g, bta, out, relu=True, res=s, res_stats=sstats, res_gamma=g2, res_beta=b2)
+    torch.cuda.synchronize()
+    ref = F.relu(F.group_norm(xn, 32, g, bta, 1e-5) + F.group_norm(s.float().transpose(1, 2), 32, g2, b2, 1e-5))
+    check(out, ref.transpose(1, 2), f"groupnorm+gn shortcut c{c}")
+    o.groupnorm_apply(x, stats, g, bta, out, relu=True, res=s)
+    torch.cuda.synchronize()
+    ref = F.relu(F.group_norm(xn, 32, g, bta, 1e-5) + s.float().transpose(1, 2))
+    check(out, ref.transpose(1, 2), f"groupnorm+identity shortcut c{c}")
+
+
+def test_stem_path():
+    o = ops()
+    b, h, w_ = 2, 64, 96
+    x = rnd(b, 3, h, w_)
+    cols = torch.full((b * (h // 2) * (w_ // 2), 160), float("nan"), device=dev(), dtype=torch.bfloat16)
+    o.stem_im2col(x, cols)
+    torch.cuda.synchronize()
+    xp = F.pad(x, (2, 3, 2, 3))
+    ref = F.unfold(xp, 7, stride=2)  # [b, 3*49, L] with channel-major (c, ky, kx)
+    ref = ref.view(b, 3, 49, -1).permute(0, 3, 2, 1).reshape(b * (h // 2) * (w_ // 2), 147)
+    assert torch.equal(cols[:, :147].float(), ref.to(torch.bfloat16).float())
+    assert float(cols[:, 147:].abs().max()) == 0.0
+    # GN + ReLU + maxpool (TF-SAME (0,1))
+    c = 64
+    y = (rnd(b, h, w_, c) * 2).to(torch.bfloat16)
+    g, bta = rnd(c) * 0.1 + 1, rnd(c) * 0.1
+    stats = torch.empty(b, 32, 2, device=dev())
+    o.groupnorm_stats(y, stats)
+    out = torch.empty(b, h // 2, w_ // 2, c, device=dev(), dtype=torch.bfloat16)
+    o.stem_gn_relu_maxpool(y, stats, g, bta, out)
+    torch.cuda.synchronize()
+    yn = F.relu(F.group_norm(y.float().permute(0, 3, 1, 2), 32, g, bta, 1e-5))
+    ref = F.max_pool2d(F.pad(yn, (0, 1, 0, 1), value=float("-inf")), 3, 2).permute(0, 2, 3, 1)
+    check(out, ref, "stem gn relu maxpool")
+
+
+@pytest.mark.parametrize("h,w_,c", [(12, 12, 256), (96, 96, 256), (48, 40, 128)])
+def test_upsample2x_add(h, w_, c):
+    o = ops()
+    b = 2
+    z = rnd(b, h, w_, c).to(torch.bfloat16)
+    res = rnd(b, 2 * h, 2 * w_, c, seed=2).to(torch.bfloat16)
+    out = torch.empty_like(res)
+    outr = torch.empty_like(res)
+    o.upsample2x_add(z, out, res=res, out_relu=outr)
+    torch.cuda.synchronize()
+    up = F.interpolate(z.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+    ref = up.permute(0, 2, 3, 1) + res.float()
+    check(out, ref, "upsample2x+add")
+    check(outr, F.relu(ref), "upsample2x+add relu")
+    o.upsample2x_add(z, out)
+    torch.cuda.synchronize()
+    check(out, up.permute(0, 2, 3, 1), "upsample2x")
+
+
+def test_cls_and_readout_bias():
+    o = ops()
+    b, c = 4, 768
+    tokens = rnd(b, 577, c).to(torch.bfloat16)
+    cls, pos0 = rnd(c), rnd(c, seed=1)
+    t2 = tokens.clone()
+    o.write_cls_row(t2, cls, pos0)
+    w = rnd(c, 2 * c, scale=(2 * c) ** -0.5).to(torch.bfloat16)
+    bias = rnd(c)
+    out = torch.empty(b, c, device=dev())
+    o.readout_cls_bias(w, bias, tokens, out)
+    torch.cuda.synchronize()
+    assert torch.equal(t2[:, 0].float(), (cls + pos0).to(torch.bfloat16).float().expand(b, c))
+    assert torch.equal(t2[:, 1:], tokens[:, 1:])
+    ref = tokens[:, 0].float() @ w[:, c:].float().t() + bias
+    assert rel_l2(out, ref) < 1e-5
