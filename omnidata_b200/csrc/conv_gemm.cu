@@ -238,7 +238,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (res != nullptr && valid) {
             const uint4* rp = reinterpret_cast<const uint4*>(res + c * 64);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = __ldg(rp + j);
+            for (int j = 0; j < 8; ++j) rv[j] = rp[j];  // plain ld.global: out may alias residual
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) rv[j] = make_uint4(0, 0, 0, 0);

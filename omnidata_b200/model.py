@@ -1,0 +1,509 @@
+"""DPT-Hybrid-384 (`vitb_rn50_384`) dense-prediction model, B200-native.
+
+Drop-in for the reference's `modules/midas/dpt_depth.py::DPTDepthModel` (constructor kwargs,
+`state_dict()` keys / shapes / order, `forward(x)` contract: float NCHW in, `[B,H,W]` (1 channel)
+or `[B,C,H,W]` out, final ReLU when `non_negative`).  The arithmetic runs in the sm_100a kernels
+of `omnidata_b200/csrc` through the C ABI (`include/omnidata_b200.h`); this file is host-side
+orchestration only: weight pre-packing at load time, workspace management, launch order and
+optional CUDA-graph replay.  There is no CPU / eager fallback — `forward` on a CPU tensor raises.
+
+Reference call stack mirrored here (omnidata_tools/torch/): DPT.forward `modules/midas/dpt_depth.py:67-85`,
+forward_vit / forward_flex `modules/midas/vit.py:61-155`, reassemble `vit.py:431-462`,
+FeatureFusionBlock_custom / ResidualConvUnit_custom `modules/midas/blocks.py:231-341`,
+head `dpt_depth.py:91-99`; encoder arithmetic is timm 0.4.12 `vit_base_resnet50_384` (`vit.py:483`).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._capi import OdbError
+
+_STAGES = ((256, 3), (512, 4), (1024, 9))   # timm ResNetV2(layers=(3,4,9)) widths / depths
+_EMBED = 768
+_HEADS = 12
+_DEPTH = 12
+_HOOKS = (8, 11)                            # modules/midas/dpt_depth.py:41-45, ViT blocks tapped
+_FEATURES = 256
+
+
+def state_dict_spec(num_channels: int = 1, features: int = _FEATURES) -> List[Tuple[str, Tuple[int, ...]]]:
+    """(key, shape) in reference `state_dict()` order (verified against the
+    unmodified reference class in tests/test_boundary_cpu.py)."""
+    spec: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def add(key, *shape):
+        spec.append((key, tuple(shape)))
+
+    pm = "pretrained.model."
+    add(pm + "cls_token", 1, 1, _EMBED)
+    add(pm + "pos_embed", 1, 577, _EMBED)
+    bb = pm + "patch_embed.backbone."
+    add(bb + "stem.conv.weight", 64, 3, 7, 7)
+    add(bb + "stem.norm.weight", 64)
+    add(bb + "stem.norm.bias", 64)
+    cin = 64
+    for s, (cout, depth) in enumerate(_STAGES):
+        mid = cout // 4
+        for b in range(depth):
+            p = f"{bb}stages.{s}.blocks.{b}."
+            if b == 0:
+                add(p + "downsample.conv.weight", cout, cin, 1, 1)
+                add(p + "downsample.norm.weight", cout)
+                add(p + "downsample.norm.bias", cout)
+            add(p + "conv1.weight", mid, cin if b == 0 else cout, 1, 1)
+            add(p + "norm1.weight", mid)
+            add(p + "norm1.bias", mid)
+            add(p + "conv2.weight", mid, mid, 3, 3)
+            add(p + "norm2.weight", mid)
+            add(p + "norm2.bias", mid)
+            add(p + "conv3.weight", cout, mid, 1, 1)
+            add(p + "norm3.weight", cout)
+            add(p + "norm3.bias", cout)
+        cin = cout
+    add(pm + "patch_embed.proj.weight", _EMBED, 1024, 1, 1)
+    add(pm + "patch_embed.proj.bias", _EMBED)
+    for i in range(_DEPTH):
+        p = f"{pm}blocks.{i}."
+        add(p + "norm1.weight", _EMBED)
+        add(p + "norm1.bias", _EMBED)
+        add(p + "attn.qkv.weight", 3 * _EMBED, _EMBED)
+        add(p + "attn.qkv.bias", 3 * _EMBED)
+        add(p + "attn.proj.weight", _EMBED, _EMBED)
+        add(p + "attn.proj.bias", _EMBED)
+        add(p + "norm2.weight", _EMBED)
+        add(p + "norm2.bias", _EMBED)
+        add(p + "mlp.fc1.weight", 4 * _EMBED, _EMBED)
+        add(p + "mlp.fc1.bias", 4 * _EMBED)
+        add(p + "mlp.fc2.weight", _EMBED, 4 * _EMBED)
+        add(p + "mlp.fc2.bias", _EMBED)
+    add(pm + "norm.weight", _EMBED)          # dead in the reference forward (vit.py:153) but present
+    add(pm + "norm.bias", _EMBED)
+    add(pm + "head.weight", 1000, _EMBED)    # dead: ImageNet classifier of the timm model
+    add(pm + "head.bias", 1000)
+    for n in (3, 4):
+        p = f"pretrained.act_postprocess{n}."
+        add(p + "0.project.0.weight", _EMBED, 2 * _EMBED)
+        add(p + "0.project.0.bias", _EMBED)
+        add(p + "3.weight", _EMBED, _EMBED, 1, 1)
+        add(p + "3.bias", _EMBED)
+        if n == 4:
+            add(p + "4.weight", _EMBED, _EMBED, 3, 3)
+            add(p + "4.bias", _EMBED)
+    for n, c in zip((1, 2, 3, 4), (256, 512, _EMBED, _EMBED)):
+        add(f"scratch.layer{n}_rn.weight", features, c, 3, 3)
+    for n in (1, 2, 3, 4):
+        p = f"scratch.refinenet{n}."
+        add(p + "out_conv.weight", features, features, 1, 1)
+        add(p + "out_conv.bias", features)
+        for u in (1, 2):                     # refinenet4.resConfUnit1 is dead (blocks.py:328-330)
+            for cv in (1, 2):
+                add(f"{p}resConfUnit{u}.conv{cv}.weight", features, features, 3, 3)
+                add(f"{p}resConfUnit{u}.conv{cv}.bias", features)
+    add("scratch.output_conv.0.weight", features // 2, features, 3, 3)
+    add("scratch.output_conv.0.bias", features // 2)
+    add("scratch.output_conv.2.weight", 32, features // 2, 3, 3)
+    add("scratch.output_conv.2.bias", 32)
+    add("scratch.output_conv.4.weight", num_channels, 32, 1, 1)
+    add("scratch.output_conv.4.bias", num_channels)
+    return spec
+
+
+def _std_weight(w: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """timm StdConv2dSame weight standardisation, folded offline for inference."""
+    std, mean = torch.std_mean(w.float(), dim=[1, 2, 3], keepdim=True, unbiased=False)
+    return (w.float() - mean) / (std + eps)
+
+
+class _Workspace:
+    """Named device buffers for one (batch, height, width); allocated once, reused every forward."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        t = self.bufs.get(name)
+        if t is None:
+            t = torch.empty(tuple(shape), device=self.device, dtype=dtype)
+            self.bufs[name] = t
+        return t
+
+
+class DPTDepthModel(nn.Module):
+    """B200-native DPT-Hybrid; same constructor as the reference (`dpt_depth.py:27-35,88`)."""
+
+    def __init__(self, path: Optional[str] = None, non_negative: bool = True, num_channels: int = 1,
+                 backbone: str = "vitb_rn50_384", features: int = 256, readout: str = "project",
+                 channels_last: bool = False, use_bn: bool = False, **kwargs):
+        super().__init__()
+        if backbone != "vitb_rn50_384":
+            # reference: print + assert False (modules/midas/blocks.py:42-44)
+            print(f"Backbone '{backbone}' not implemented")
+            raise AssertionError(f"Backbone '{backbone}' not implemented")
+        if features != 256 or readout != "project" or use_bn:
+            raise NotImplementedError("only features=256, readout='project', use_bn=False (the Omnidata DPT-Hybrid)")
+        self.non_negative = bool(non_negative)
+        self.num_channels = int(num_channels)
+        self.channels_last = channels_last        # a no-op in the reference as well (dpt_depth.py:68-69)
+        self.use_cuda_graph = False
+        self.keep_taps = False                    # tests: keep named intermediate activations
+        self.taps: Dict[str, torch.Tensor] = {}
+        self._packed = None
+        self._workspaces: Dict[Tuple[int, int, int], _Workspace] = {}
+        self._graphs: Dict[Tuple[int, int, int], tuple] = {}
+        self._build_parameters()
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+        if path is not None:
+            self.load(path)
+
+    # ------------------------------------------------------------------ parameters / state_dict
+    def _build_parameters(self):
+        gen = torch.Generator().manual_seed(0)
+        for key, shape in state_dict_spec(self.num_channels):
+            *path, leaf = key.split(".")
+            mod = self
+            for name in path:
+                child = mod._modules.get(name)
+                if child is None:
+                    child = nn.Module()
+                    mod.add_module(name, child)
+                mod = child
+            if key.endswith("cls_token") or key.endswith("pos_embed"):
+                t = torch.randn(shape, generator=gen) * 0.02
+            elif leaf == "bias":
+                t = torch.zeros(shape)
+            elif len(shape) == 1:
+                t = torch.ones(shape)
+            else:
+                fan_in = math.prod(shape[1:])
+                t = torch.randn(shape, generator=gen) / math.sqrt(fan_in)
+            mod.register_parameter(leaf, nn.Parameter(t))
+
+    def load(self, path: str):
+        """reference BaseModel.load (modules/midas/base_model.py:5-16)."""
+        parameters = torch.load(path, map_location=torch.device("cpu"))
+        if "optimizer" in parameters:
+            parameters = parameters["model"]
+        self.load_state_dict(parameters)
+
+    def _invalidate(self):
+        self._packed = None
+        self._graphs.clear()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._invalidate()
+        self._workspaces.clear()
+        return out
+
+    # ------------------------------------------------------------------ weight pre-pack (one-time)
+    @torch.no_grad()
+    def _prepack(self, device) -> dict:
+        sd = {k: v.detach().to(device) for k, v in self.state_dict().items()}
+        f32 = lambda k: sd[k].float().contiguous()
+        bf = lambda t: t.to(torch.bfloat16).contiguous()
+        pk: dict = {}
+        pm = "pretrained.model."
+        bb = pm + "patch_embed.backbone."
+        # stem 7x7: [64,3,7,7] -> [64, (ky,kx,c)=147] padded to 160 columns
+        w = _std_weight(sd[bb + "stem.conv.weight"]).permute(0, 2, 3, 1).reshape(64, 147)
+        pk["stem_w"] = bf(F.pad(w, (0, 13)))
+        pk["stem_g"], pk["stem_b"] = f32(bb + "stem.norm.weight"), f32(bb + "stem.norm.bias")
+        blocks = []
+        for s, (cout, depth) in enumerate(_STAGES):
+            for b in range(depth):
+                p = f"{bb}stages.{s}.blocks.{b}."
+                e = {"stride": 2 if (b == 0 and s > 0) else 1, "cout": cout, "mid": cout // 4}
+                if b == 0:
+                    e["wd"] = ops.pack_conv_weight(_std_weight(sd[p + "downsample.conv.weight"]))
+                    e["gd"], e["bd"] = f32(p + "downsample.norm.weight"), f32(p + "downsample.norm.bias")
+                for i in (1, 2, 3):
+                    e[f"w{i}"] = ops.pack_conv_weight(_std_weight(sd[p + f"conv{i}.weight"]))
+                    e[f"g{i}"], e[f"b{i}"] = f32(p + f"norm{i}.weight"), f32(p + f"norm{i}.bias")
+                blocks.append((s, b, e))
+        pk["rn_blocks"] = blocks
+        pk["proj_w"] = ops.pack_conv_weight(sd[pm + "patch_embed.proj.weight"])
+        pk["proj_b"] = f32(pm + "patch_embed.proj.bias")
+        pk["cls"] = f32(pm + "cls_token").reshape(-1)
+        pk["pos"] = f32(pm + "pos_embed")                       # [1,577,768] fp32 master copy
+        vit = []
+        for i in range(_DEPTH):
+            p = f"{pm}blocks.{i}."
+            vit.append({
+                "ln1": (f32(p + "norm1.weight"), f32(p + "norm1.bias")),
+                "qkv": (bf(sd[p + "attn.qkv.weight"]), f32(p + "attn.qkv.bias")),
+                "proj": (bf(sd[p + "attn.proj.weight"]), f32(p + "attn.proj.bias")),
+                "ln2": (f32(p + "norm2.weight"), f32(p + "norm2.bias")),
+                "fc1": (bf(sd[p + "mlp.fc1.weight"]), f32(p + "mlp.fc1.bias")),
+                "fc2": (bf(sd[p + "mlp.fc2.weight"]), f32(p + "mlp.fc2.bias")),
+            })
+        pk["vit"] = vit
+        for n in (3, 4):
+            p = f"pretrained.act_postprocess{n}."
+            wfull = bf(sd[p + "0.project.0.weight"])               # [768,1536]
+            pk[f"ro{n}_wfull"] = wfull
+            pk[f"ro{n}_wtok"] = wfull[:, :_EMBED].contiguous()     # token half of the split Linear
+            pk[f"ro{n}_b"] = f32(p + "0.project.0.bias")
+            pk[f"pp{n}_w"] = ops.pack_conv_weight(sd[p + "3.weight"])
+            pk[f"pp{n}_b"] = f32(p + "3.bias")
+        pk["pp4s_w"] = ops.pack_conv_weight(sd["pretrained.act_postprocess4.4.weight"])
+        pk["pp4s_b"] = f32("pretrained.act_postprocess4.4.bias")
+        for n in (1, 2, 3, 4):
+            pk[f"rn{n}_w"] = ops.pack_conv_weight(sd[f"scratch.layer{n}_rn.weight"])
+            p = f"scratch.refinenet{n}."
+            pk[f"ff{n}_out"] = (ops.pack_conv_weight(sd[p + "out_conv.weight"]), f32(p + "out_conv.bias"))
+            for u in (1, 2):
+                pk[f"ff{n}_rcu{u}"] = tuple(
+                    (ops.pack_conv_weight(sd[f"{p}resConfUnit{u}.conv{cv}.weight"]),
+                     f32(f"{p}resConfUnit{u}.conv{cv}.bias")) for cv in (1, 2))
+        pk["head0"] = (ops.pack_conv_weight(sd["scratch.output_conv.0.weight"]), f32("scratch.output_conv.0.bias"))
+        pk["head2"] = (ops.pack_conv_weight(sd["scratch.output_conv.2.weight"]), f32("scratch.output_conv.2.bias"))
+        pk["head4"] = (sd["scratch.output_conv.4.weight"].float().reshape(self.num_channels, 32).contiguous(),
+                       f32("scratch.output_conv.4.bias"))
+        pk["pos_cache"] = {}
+        return pk
+
+    def _pos_for_grid(self, pk, gh: int, gw: int):
+        """(pos0 fp32 [768], grid bf16 [1,1,gh*gw,768]); bilinear resize as vit.py:102-116 if needed."""
+        key = (gh, gw)
+        if key not in pk["pos_cache"]:
+            pos = pk["pos"]
+            grid = pos[0, 1:]
+            if (gh, gw) != (24, 24):
+                g = grid.reshape(1, 24, 24, -1).permute(0, 3, 1, 2)
+                g = F.interpolate(g, size=(gh, gw), mode="bilinear")
+                grid = g.permute(0, 2, 3, 1).reshape(gh * gw, -1)
+            pk["pos_cache"][key] = (pos[0, 0].contiguous(),
+                                    grid.to(torch.bfloat16).contiguous().view(1, 1, gh * gw, _EMBED))
+        return pk["pos_cache"][key]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise OdbError("omnidata_b200.DPTDepthModel runs on a CUDA (sm_100a) device only; "
+                           "there is no CPU fallback — move the model and input to cuda")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected input [B,3,H,W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if H % 32 or W % 32 or (H // 16) * (W // 16) + 1 > 640:
+            raise ValueError("H and W must be multiples of 32 with at most 639 patches (384x384 in scope)")
+        x = x.detach().float().contiguous()
+        if self._packed is None:
+            self._packed = self._prepack(x.device)
+        if self.use_cuda_graph and not self.keep_taps:
+            out = self._forward_graph(x)
+        else:
+            out = self._forward_impl(x)
+        return out.squeeze(dim=1)                     # dpt_depth.py:107
+
+    def _forward_graph(self, x: torch.Tensor) -> torch.Tensor:
+        key = tuple(x.shape[i] for i in (0, 2, 3))
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = x.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                    # warm-up: allocate workspaces, configure kernels
+                    self._forward_impl(static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_impl(static_in)
+            entry = (graph, static_in, static_out)
+            self._graphs[key] = entry
+        graph, static_in, static_out = entry
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
+
+    @torch.no_grad()
+    def _forward_impl(self, x: torch.Tensor) -> torch.Tensor:
+        pk = self._packed
+        B, _, H, W = x.shape
+        key = (B, H, W)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            ws = self._workspaces[key] = _Workspace(x.device)
+        taps = self.taps if self.keep_taps else None
+        if taps is not None:
+            taps.clear()
+        buf = ws.get
+
+        # ---------------- ResNetV2 stem + stages (timm; hooks at vit.py:363-368)
+        h2, w2 = H // 2, W // 2
+        n_gn = 1 + sum(3 * d + 1 for _, d in _STAGES)
+        stats_pool = buf("gn_stats", (n_gn, B, 32, 2), torch.float32)
+        stats_pool.zero_()
+        stat_i = iter(range(n_gn))
+
+        def gn_stats(t):
+            st = stats_pool[next(stat_i)]
+            ops.groupnorm_stats(t, st, zero=False)
+            return st
+
+        cols = buf("stem_cols", (B * h2 * w2, 160))
+        ops.stem_im2col(x, cols)
+        s0 = buf("stem_conv", (B, h2, w2, 64))
+        ops.linear(cols, pk["stem_w"], s0.view(-1, 64))
+        st = gn_stats(s0)
+        t = buf("stem_pool", (B, h2 // 2, w2 // 2, 64))
+        ops.stem_gn_relu_maxpool(s0, st, pk["stem_g"], pk["stem_b"], t)
+        feats = []
+        hh, ww = h2 // 2, w2 // 2
+        for s, b, e in pk["rn_blocks"]:
+            stride, cout, mid = e["stride"], e["cout"], e["mid"]
+            ho, wo = hh // stride, ww // stride
+            tag = f"s{s}b{b}"
+            shortcut, sc_stats = t, None
+            if b == 0:
+                d = buf(tag + "_ds", (B, ho, wo, cout))
+                ops.conv1x1(t[:, ::stride, ::stride, :] if stride > 1 else t, e["wd"], d)
+                sc_stats = gn_stats(d)
+                shortcut = d
+            y1 = buf(tag + "_y1", (B, hh, ww, mid))
+            ops.conv1x1(t, e["w1"], y1)
+            st1 = gn_stats(y1)
+            a1 = buf(tag + "_a1", (B, hh, ww, mid))
+            ops.groupnorm_apply(y1, st1, e["g1"], e["b1"], a1, relu=True)
+            y2 = buf(tag + "_y2", (B, ho, wo, mid))
+            if stride == 1:
+                ops.conv3x3(a1, e["w2"], y2)
+            else:
+                ops.conv3x3_s2(a1, e["w2"], y2, "same")
+            st2 = gn_stats(y2)
+            a2 = buf(tag + "_a2", (B, ho, wo, mid))
+            ops.groupnorm_apply(y2, st2, e["g2"], e["b2"], a2, relu=True)
+            y3 = buf(tag + "_y3", (B, ho, wo, cout))
+            ops.conv1x1(a2, e["w3"], y3)
+            st3 = gn_stats(y3)
+            out = buf(tag + "_out", (B, ho, wo, cout))
+            if b == 0:
+                ops.groupnorm_apply(y3, st3, e["g3"], e["b3"], out, relu=True, res=shortcut,
+                                    res_stats=sc_stats, res_gamma=e["gd"], res_beta=e["bd"])
+            else:
+                ops.groupnorm_apply(y3, st3, e["g3"], e["b3"], out, relu=True, res=shortcut)
+            t, hh, ww = out, ho, wo
+            if b == _STAGES[s][1] - 1:
+                feats.append(t)
+        layer_1, layer_2, f3 = feats
+        gh, gw = hh, ww
+        ntok = gh * gw + 1
+
+        # ---------------- tokens: patch proj + cls + pos (vit.py:133-147)
+        pos0, pos_grid = self._pos_for_grid(pk, gh, gw)
+        tok = buf("tok_a", (B, ntok, _EMBED))
+        tok_b = buf("tok_b", (B, ntok, _EMBED))
+        ops.write_cls_row(tok, pk["cls"], pos0)
+        ops.linear(f3.view(B, 1, gh * gw, 1024), pk["proj_w"], tok[:, 1:, :].unsqueeze(1), bias=pk["proj_b"],
+                   residual=pos_grid)
+
+        # ---------------- 12 ViT blocks (vit.py:150-151); final norm is dead compute and skipped
+        hbuf = buf("vit_h", (B, ntok, _EMBED))
+        qkv = buf("vit_qkv", (B, ntok, 3 * _EMBED))
+        att = buf("vit_att", (B, ntok, _EMBED))
+        mlp = buf("vit_mlp", (B, ntok, 4 * _EMBED))
+        rows = B * ntok
+        cur = tok
+        for i, blk in enumerate(pk["vit"]):
+            ops.layernorm(cur, blk["ln1"][0], blk["ln1"][1], hbuf)
+            ops.linear(hbuf.view(rows, -1), blk["qkv"][0], qkv.view(rows, -1), bias=blk["qkv"][1])
+            ops.attention(qkv, att, heads=_HEADS, scale=0.125)
+            nxt = tok_b if i == _HOOKS[0] + 1 else cur      # block 9 leaves tokens_8 intact in tok_a
+            ops.linear(att.view(rows, -1), blk["proj"][0], nxt.view(rows, -1), bias=blk["proj"][1],
+                       residual=cur.view(rows, -1))
+            cur = nxt
+            ops.layernorm(cur, blk["ln2"][0], blk["ln2"][1], hbuf)
+            ops.linear(hbuf.view(rows, -1), blk["fc1"][0], mlp.view(rows, -1), bias=blk["fc1"][1],
+                       act=ops.ACT_GELU)
+            ops.linear(mlp.view(rows, -1), blk["fc2"][0], cur.view(rows, -1), bias=blk["fc2"][1],
+                       residual=cur.view(rows, -1))
+        tokens_8, tokens_11 = tok, tok_b
+
+        # ---------------- reassemble (vit.py:66-97, 431-462)
+        def readout(tk, n):
+            cb = buf(f"ro{n}_cb", (B, _EMBED), torch.float32)
+            ops.readout_cls_bias(pk[f"ro{n}_wfull"], pk[f"ro{n}_b"], tk, cb)
+            r = buf(f"ro{n}_r", (B, 1, gh * gw, _EMBED))
+            ops.linear(tk[:, 1:, :].unsqueeze(1), pk[f"ro{n}_wtok"], r, bias=cb, bias_per_image=True,
+                       act=ops.ACT_GELU)
+            o = buf(f"pp{n}", (B, gh, gw, _EMBED))
+            ops.conv1x1(r.view(B, gh, gw, _EMBED), pk[f"pp{n}_w"], o, bias=pk[f"pp{n}_b"])
+            return o
+        layer_3 = readout(tokens_8, 3)
+        u4 = readout(tokens_11, 4)
+        layer_4 = buf("pp4s", (B, gh // 2, gw // 2, _EMBED))
+        ops.conv3x3_s2(u4, pk["pp4s_w"], layer_4, "sym1", bias=pk["pp4s_b"])
+
+        # ---------------- scratch.layerN_rn (dpt_depth.py:73-76): raw + relu copies feed the RCUs
+        rn_raw, rn_relu = [], []
+        for n, l in zip((1, 2, 3, 4), (layer_1, layer_2, layer_3, layer_4)):
+            shp = (B, l.shape[1], l.shape[2], _FEATURES)
+            raw, rl = buf(f"rn{n}_raw", shp), buf(f"rn{n}_relu", shp)
+            ops.conv3x3(l, pk[f"rn{n}_w"], raw, out2=rl)
+            rn_raw.append(raw)
+            rn_relu.append(rl)
+
+        # ---------------- RefineNet fusion (dpt_depth.py:78-81; blocks.py:263-341)
+        def rcu(n, u, x_raw, x_relu, out, out2=None):
+            (w1, b1), (w2, b2) = pk[f"ff{n}_rcu{u}"]
+            tmid = buf(f"ff{n}_rcu{u}_t", x_raw.shape)
+            ops.conv3x3(x_relu, w1, tmid, bias=b1, act=ops.ACT_RELU)       # relu(conv1(relu(x)))
+            ops.conv3x3(tmid, w2, out, bias=b2, residual=x_raw, out2=out2)  # conv2(.) + x
+
+        def fusion_tail(n, s_raw, s_relu):
+            """RCU2, then the 1x1 out_conv at the input resolution (it commutes with the bilinear
+            upsample: the interpolation weights sum to one)."""
+            y = buf(f"ff{n}_y", s_raw.shape)
+            rcu(n, 2, s_raw, s_relu, y)
+            z = buf(f"ff{n}_z", s_raw.shape)
+            w, bias = pk[f"ff{n}_out"]
+            ops.conv1x1(y, w, z, bias=bias)
+            return z
+
+        z = fusion_tail(4, rn_raw[3], rn_relu[3])
+        if taps is not None:
+            taps["path_4"] = self._debug_upsample(z)
+        for n in (3, 2, 1):
+            l_raw, l_relu = rn_raw[n - 1], rn_relu[n - 1]
+            res = buf(f"ff{n}_res", l_raw.shape)
+            rcu(n, 1, l_raw, l_relu, res)
+            s_raw, s_relu = buf(f"ff{n}_s", l_raw.shape), buf(f"ff{n}_s_relu", l_raw.shape)
+            ops.upsample2x_add(z, s_raw, res=res, out_relu=s_relu)         # up(path) + RCU1(layer_rn)
+            z = fusion_tail(n, s_raw, s_relu)
+            if taps is not None and n > 1:
+                taps[f"path_{n}"] = self._debug_upsample(z)
+        path_1 = buf("path_1", (B, z.shape[1] * 2, z.shape[2] * 2, _FEATURES))
+        ops.upsample2x_add(z, path_1)
+
+        # ---------------- head (dpt_depth.py:91-99)
+        w0, b0 = pk["head0"]
+        h1 = buf("head_h1", (B, path_1.shape[1], path_1.shape[2], _FEATURES // 2))
+        ops.conv3x3(path_1, w0, h1, bias=b0)
+        h1u = buf("head_h1u", (B, H, W, _FEATURES // 2))
+        ops.upsample2x_add(h1, h1u)
+        out = buf("out", (B, self.num_channels, H, W), torch.float32)
+        w2, b2 = pk["head2"]
+        w4, b4 = pk["head4"]
+        ops.conv3x3(h1u, w2, None, bias=b2, head=(w4, b4, out, self.non_negative))
+
+        if taps is not None:
+            taps.update(layer_1=layer_1, layer_2=layer_2, layer_3=layer_3, layer_4=layer_4,
+                        tokens_8=tokens_8, tokens_11=tokens_11, path_1=path_1,
+                        layer_1_rn=rn_raw[0], layer_2_rn=rn_raw[1], layer_3_rn=rn_raw[2],
+                        layer_4_rn=rn_raw[3])
+            self.taps = {k: v.clone() for k, v in taps.items()}
+        return out if (self.use_cuda_graph and not self.keep_taps) else out.clone()
+
+    @staticmethod
+    def _debug_upsample(z: torch.Tensor) -> torch.Tensor:
+        o = torch.empty((z.shape[0], 2 * z.shape[1], 2 * z.shape[2], z.shape[3]), device=z.device,
+                        dtype=torch.bfloat16)
+        ops.upsample2x_add(z, o)
+        return o

@@ -25,6 +25,40 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class LaunchTimer:
+    """Optional per-launch device timing (bench.py roofline pass): every C-ABI call made while the
+    timer is active is bracketed by CUDA events on torch's current stream — the stream the kernel is
+    launched on.  Not used on the normal path."""
+
+    active: "Optional[LaunchTimer]" = None
+
+    def __init__(self):
+        self.records = []          # (name, info dict, start event, end event)
+
+    def __enter__(self):
+        LaunchTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        LaunchTimer.active = None
+
+    def results(self):
+        torch.cuda.synchronize()
+        return [(n, i, s.elapsed_time(e)) for n, i, s, e in self.records]
+
+
+def _call(name: str, info: dict, fn, *args):
+    t = LaunchTimer.active
+    if t is None:
+        check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    check(fn(*args), name)
+    e.record()
+    t.records.append((name, info, s, e))
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -94,7 +128,9 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
         d.head_relu = 1 if hrelu else 0
         b, _, h, w = hout.shape
         d.out = View(None, 32, w, h, b, 0, 0, 0)
-    check(lib().odb_conv_gemm(C.byref(d), _stream()), "odb_conv_gemm")
+    rows = d.out.w * d.out.h * d.out.b
+    info = {"m": rows, "n": d.n, "k": d.num_taps * d.views[0].c, "taps": d.num_taps, "w": d.out.w, "h": d.out.h}
+    _call("odb_conv_gemm", info, lib().odb_conv_gemm, C.byref(d), _stream())
 
 
 TAPS_1 = [(0, 0, 0)]
@@ -148,8 +184,8 @@ def layernorm(x, gamma, beta, out, eps: float = 1e-6):
     if not (x.is_contiguous() and out.is_contiguous()):
         raise _capi.OdbError("layernorm: contiguous tensors required")
     rows = x.numel() // x.shape[-1]
-    check(lib().odb_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows,
-                              x.shape[-1], eps, _stream()), "odb_layernorm")
+    _call("odb_layernorm", {"bytes": 4 * x.numel()}, lib().odb_layernorm, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows,
+                              x.shape[-1], eps, _stream())
 
 
 def attention(qkv, out, heads: int = 12, scale: float = 0.125):
@@ -157,33 +193,31 @@ def attention(qkv, out, heads: int = 12, scale: float = 0.125):
     b, n, c3 = qkv.shape
     if not (qkv.is_contiguous() and out.is_contiguous()) or c3 != 3 * heads * 64:
         raise _capi.OdbError("attention: qkv must be contiguous [B, tokens, 3*heads*64]")
-    check(lib().odb_attention(qkv.data_ptr(), out.data_ptr(), b, n, heads, scale, _stream()), "odb_attention")
+    _call("odb_attention", {"flops": 4.0 * b * heads * n * n * 64, "bytes": 2 * (qkv.numel() + out.numel())}, lib().odb_attention, qkv.data_ptr(), out.data_ptr(), b, n, heads, scale, _stream())
 
 
-def groupnorm_stats(x, stats, groups: int = 32):
+def groupnorm_stats(x, stats, groups: int = 32, zero: bool = True):
     _need(x, torch.bfloat16, "x"); _need(stats, torch.float32, "stats")
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
-    check(lib().odb_fill_zero(stats.data_ptr(), stats.numel() * 4, _stream()), "odb_fill_zero")
-    check(lib().odb_groupnorm_stats(x.data_ptr(), stats.data_ptr(), b, hw, c, groups, _stream()),
-          "odb_groupnorm_stats")
+    if zero:
+        check(lib().odb_fill_zero(stats.data_ptr(), stats.numel() * 4, _stream()), "odb_fill_zero")
+    _call("odb_groupnorm_stats", {"bytes": 2 * x.numel()}, lib().odb_groupnorm_stats, x.data_ptr(), stats.data_ptr(), b, hw, c, groups, _stream())
 
 
 def groupnorm_apply(x, stats, gamma, beta, out, *, relu: bool, res=None, res_stats=None, res_gamma=None,
                     res_beta=None, groups: int = 32, eps: float = 1e-5):
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
-    check(lib().odb_groupnorm_apply(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+    _call("odb_groupnorm_apply", {"bytes": 2 * x.numel() * (2 + (res is not None))}, lib().odb_groupnorm_apply, x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                     _ptr(res), _ptr(res_stats), _ptr(res_gamma), _ptr(res_beta),
-                                    out.data_ptr(), b, hw, c, groups, eps, 1 if relu else 0, _stream()),
-          "odb_groupnorm_apply")
+                                    out.data_ptr(), b, hw, c, groups, eps, 1 if relu else 0, _stream())
 
 
 def stem_gn_relu_maxpool(x, stats, gamma, beta, out, groups: int = 32, eps: float = 1e-5):
     b, h, w, c = x.shape
-    check(lib().odb_stem_gn_relu_maxpool(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                         out.data_ptr(), b, h, w, c, groups, eps, _stream()),
-          "odb_stem_gn_relu_maxpool")
+    _call("odb_stem_gn_relu_maxpool", {}, lib().odb_stem_gn_relu_maxpool, x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                         out.data_ptr(), b, h, w, c, groups, eps, _stream())
 
 
 def stem_im2col(x, cols):
@@ -191,23 +225,23 @@ def stem_im2col(x, cols):
     b, ch, h, w = x.shape
     if ch != 3 or not x.is_contiguous():
         raise _capi.OdbError("stem_im2col: contiguous [B,3,H,W] fp32 input required")
-    check(lib().odb_stem_im2col(x.data_ptr(), cols.data_ptr(), b, h, w, cols.shape[-1], _stream()),
-          "odb_stem_im2col")
+    _call("odb_stem_im2col", {}, lib().odb_stem_im2col, x.data_ptr(), cols.data_ptr(), b, h, w, cols.shape[-1], _stream())
 
 
 def upsample2x_add(z, out, res=None, out_relu=None):
     b, h, w, c = z.shape
-    check(lib().odb_upsample2x_add(z.data_ptr(), _ptr(res), out.data_ptr(), _ptr(out_relu), b, h, w, c,
-                                   _stream()), "odb_upsample2x_add")
+    n_in = b * h * w * c * 2
+    info = {"bytes": n_in + 4 * n_in * (1 + (res is not None) + (out_relu is not None)), "h": h, "c": c}
+    _call("odb_upsample2x_add", info, lib().odb_upsample2x_add, z.data_ptr(), _ptr(res), out.data_ptr(), _ptr(out_relu), b, h, w, c,
+                                   _stream())
 
 
 def write_cls_row(tokens, cls, pos0):
     b, n, c = tokens.shape
-    check(lib().odb_write_cls_row(tokens.data_ptr(), cls.data_ptr(), pos0.data_ptr(), b, n, c, _stream()),
-          "odb_write_cls_row")
+    _call("odb_write_cls_row", {}, lib().odb_write_cls_row, tokens.data_ptr(), cls.data_ptr(), pos0.data_ptr(), b, n, c, _stream())
 
 
 def readout_cls_bias(w, bias, tokens, out):
     b, n, c = tokens.shape
-    check(lib().odb_readout_cls_bias(w.data_ptr(), bias.data_ptr(), tokens.data_ptr(), out.data_ptr(), b, n,
-                                     c, _stream()), "odb_readout_cls_bias")
+    _call("odb_readout_cls_bias", {}, lib().odb_readout_cls_bias, w.data_ptr(), bias.data_ptr(), tokens.data_ptr(), out.data_ptr(), b, n,
+                                     c, _stream())

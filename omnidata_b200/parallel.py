@@ -1,0 +1,91 @@
+"""Data-parallel plumbing for batched inference: one process per GPU (torch.distributed, NCCL on
+GPUs / gloo in CPU tests).  Images are independent units, so the data path has NO collective:
+the batch is split into contiguous per-rank slices, weights are broadcast once from rank 0, and
+only scalars (timings, counts) are reduced.  The reference has no multi-GPU inference at all
+(demo.py:41-42 uses cuda:0); its training path is PL DDP (train_depth.py:424-426).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None) -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank); initialises the default process group when WORLD_SIZE > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [start, end) slice of `n_items` for `rank` (first ranks take the remainder)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def broadcast_state_dict(module: torch.nn.Module, src: int = 0, bucket_bytes: int = 64 << 20) -> int:
+    """Broadcast every parameter / buffer of `module` from `src` in flat buckets; returns bytes sent."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    tensors = [t for t in module.state_dict().values() if torch.is_tensor(t)]
+    total = 0
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size, total
+        if not bucket:
+            return
+        flat = torch.cat([t.reshape(-1).to(torch.float32) for t in bucket])
+        dist.broadcast(flat, src=src)
+        off = 0
+        for t in bucket:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t).to(t.dtype))
+            off += n
+        total += flat.numel() * 4
+        bucket, size = [], 0
+
+    with torch.no_grad():
+        for t in tensors:
+            bucket.append(t)
+            size += t.numel() * 4
+            if size >= bucket_bytes:
+                flush()
+        flush()
+    return total
+
+
+def reduce_max(value: float, device) -> float:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(value: float, device) -> float:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

@@ -1,0 +1,99 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt|json from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+What it pins:
+  * state_dict_keys.json — key/shape/order of the reference DPTDepthModel.state_dict()
+    (instantiated from the reference class; timm half from oracle/timm_shim);
+  * dpt_fp32_seed0_c{1,3}.pt — for seeded weights (oracle/weights.py) and a seeded input, the
+    reference module's forward output (8x-subsampled) and, per tap, mean / rms / 256 sampled values
+    at fixed indices.  Taps come from the reference's own `pretrained.activations` hooks
+    (modules/midas/vit.py:158-165) and from forward hooks on scratch.* modules.
+  * losses_seed0.pt — reference MidasLoss / VNL_Loss values on seeded inputs (config 5 inputs).
+The fixtures are small (< 300 KiB in total) so that they can be committed.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import reference_loader as rl
+from . import weights
+
+GOLDEN = Path(__file__).resolve().parents[1] / "tests" / "golden"
+N_SAMPLES = 256
+
+
+def sample_indices(numel: int, name: str) -> torch.Tensor:
+    seed = sum(ord(c) for c in name) * 7919 + numel
+    g = torch.Generator().manual_seed(seed % (2 ** 31))
+    return torch.randint(0, numel, (N_SAMPLES,), generator=g)
+
+
+def summarize(name: str, t: torch.Tensor) -> dict:
+    flat = t.detach().float().reshape(-1)
+    idx = sample_indices(flat.numel(), name)
+    return {"shape": list(t.shape), "mean": float(flat.mean()), "rms": float(flat.pow(2).mean().sqrt()),
+            "samples": flat[idx].clone()}
+
+
+def golden_input(batch: int, seed: int = 0, size: int = 384) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+
+
+def run_reference(num_channels: int):
+    model = rl.load_reference_dpt(num_channels).eval()
+    sd = weights.make_state_dict(0, num_channels)
+    model.load_state_dict(sd, strict=True)
+    taps = {}
+
+    def grab(name):
+        def hook(mod, inp, out):
+            taps[name] = out.detach().clone()
+        return hook
+    for n in (1, 2, 3, 4):
+        getattr(model.scratch, f"layer{n}_rn").register_forward_hook(grab(f"layer_{n}_rn"))
+        getattr(model.scratch, f"refinenet{n}").register_forward_hook(grab(f"path_{n}"))
+    model.scratch.output_conv[4].register_forward_hook(grab("head_pre_relu"))
+    model.pretrained.act_postprocess3.register_forward_hook(grab("layer_3"))
+    model.pretrained.act_postprocess4.register_forward_hook(grab("layer_4"))
+    x = golden_input(1)
+    with torch.no_grad():
+        y = model(x)
+    acts = model.pretrained.activations
+    taps["layer_1"], taps["layer_2"] = acts["1"].detach(), acts["2"].detach()
+    taps["tokens_8"], taps["tokens_11"] = acts["3"].detach(), acts["4"].detach()
+    return y, taps
+
+
+def main():
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    ref = rl.load_reference_dpt(1)
+    keys = [[k, list(v.shape)] for k, v in ref.state_dict().items()]
+    (GOLDEN / "state_dict_keys.json").write_text(json.dumps(keys, indent=0))
+    for c in (1, 3):
+        y, taps = run_reference(c)
+        # layer_3/4 hooks fire on the Sequential slices too; keep the full-module outputs only
+        rec = {"output_sub8": y[..., ::8, ::8].clone(), "output_mean": float(y.mean()),
+               "taps": {k: summarize(k, v) for k, v in sorted(taps.items())}}
+        torch.save(rec, GOLDEN / f"dpt_fp32_seed0_c{c}.pt")
+        print(f"c={c}: output mean {rec['output_mean']:.6f}, taps {sorted(taps)}")
+    # ---- losses (reference modules, unmodified)
+    MidasLoss, VNL_Loss = rl.load_reference_losses()
+    g = torch.Generator().manual_seed(0)
+    pred = torch.rand(2, 1, 384, 384, generator=g)
+    gt = torch.rand(2, 1, 384, 384, generator=g)
+    mask = torch.rand(2, 1, 384, 384, generator=g) > 0.1
+    total, ssi, reg = MidasLoss(alpha=0.1, scales=4, reduction="image-based")(pred, gt, mask)
+    np.random.seed(0)
+    vnl = VNL_Loss(1.0, 1.0, (384, 384))(pred, gt)
+    torch.save({"midas_total": float(total), "midas_ssi": float(ssi), "midas_reg": float(reg), "vnl": float(vnl)},
+               GOLDEN / "losses_seed0.pt")
+    print("losses", float(total), float(ssi), float(reg), float(vnl))
+
+
+if __name__ == "__main__":
+    main()

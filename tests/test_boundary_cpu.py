@@ -1,0 +1,85 @@
+"""Drop-in boundary without a GPU: state_dict layout, constructor / error behaviour, the C-ABI
+library loads and exports every symbol that include/omnidata_b200.h declares."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def test_c_abi_exports_every_declared_symbol(lib_built):
+    header = (ROOT / "include" / "omnidata_b200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(odb_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(str(lib_built))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    from omnidata_b200 import _capi
+    assert sorted(_capi.exported_symbols()) == declared
+    assert _capi.lib().odb_abi_version() == 1
+    assert _capi.launch_count() == 0
+
+
+def test_compute_entry_fails_loudly_without_gpu(lib_built):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from omnidata_b200 import _capi, ops
+    with pytest.raises(_capi.OdbError):
+        ops.layernorm(torch.zeros(2, 768, dtype=torch.bfloat16), torch.ones(768), torch.zeros(768),
+                      torch.zeros(2, 768, dtype=torch.bfloat16))
+    # a raw C call on host pointers must return an error code, not crash or silently compute
+    d = _capi.ConvGemmDesc()
+    rc = _capi.lib().odb_conv_gemm(ctypes.byref(d), None)
+    assert rc != 0 and len(_capi.lib().odb_last_error()) > 0
+
+
+@pytest.mark.parametrize("c", [1, 3])
+def test_state_dict_layout_is_the_reference_layout(c):
+    from omnidata_b200.model import DPTDepthModel, state_dict_spec
+    keys = json.loads((GOLDEN / "state_dict_keys.json").read_text())
+    if c == 3:
+        keys = [[k, ([3] + s[1:] if k.startswith("scratch.output_conv.4.") else s)] for k, s in keys]
+    model = DPTDepthModel(backbone="vitb_rn50_384", num_channels=c)
+    got = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+    assert got == keys
+    assert [[k, list(s)] for k, s in state_dict_spec(c)] == keys
+    # strict load of a reference-layout checkpoint, incl. the PL 'model.' prefix handling of demo.py:65-68
+    from oracle import weights
+    sd = weights.make_state_dict(0, c)
+    model.load_state_dict(sd, strict=True)
+    assert torch.equal(model.state_dict()["scratch.refinenet4.resConfUnit1.conv1.weight"],
+                       sd["scratch.refinenet4.resConfUnit1.conv1.weight"])
+    with pytest.raises(RuntimeError):
+        bad = dict(sd)
+        bad.pop("pretrained.model.norm.weight")
+        model.load_state_dict(bad, strict=True)
+
+
+def test_constructor_and_forward_errors():
+    from omnidata_b200._capi import OdbError
+    from omnidata_b200.model import DPTDepthModel
+    with pytest.raises(AssertionError):
+        DPTDepthModel(backbone="vitl16_384")
+    m = DPTDepthModel()
+    assert m.num_channels == 1 and m.non_negative
+    if not torch.cuda.is_available():
+        with pytest.raises(OdbError):
+            m(torch.zeros(1, 3, 384, 384))
+
+
+def test_hub_entry_points_exist():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("hubconf", ROOT / "hubconf.py")
+    hub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(hub)
+    for name in ("depth_dpt_hybrid_384", "surface_normal_dpt_hybrid_384", "dpt_hybrid_384"):
+        assert callable(getattr(hub, name))
+    m = hub.dpt_hybrid_384(pretrained=False, task="normal")
+    assert m.num_channels == 3
+    m = hub.dpt_hybrid_384(pretrained=False, task="depth")
+    assert m.num_channels == 1
