@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""CLI with the reference's flags and outputs (omnidata_tools/torch/demo.py:23-36,125-163):
+
+    python demo.py --task {normal,depth} --img_path FILE-or-DIR --output_path DIR
+
+writes <name>_<task>.png and <name>_rgb.png.  Weights: ./pretrained_models/omnidata_dpt_{normal,depth}_v2.ckpt
+(reference checkpoint names, demo.py:62,80); `--synthetic_weights` substitutes seeded random weights
+when no checkpoint is available (offline).  Inference runs on cuda:0 through the sm_100a kernels —
+there is no CPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from PIL import Image
+
+_VIRIDIS = np.array([[68, 1, 84], [72, 40, 120], [62, 74, 137], [49, 104, 142], [38, 130, 142], [31, 158, 137],
+                     [53, 183, 121], [109, 205, 89], [180, 222, 44], [253, 231, 37]], dtype=np.float32)
+
+
+def viridis(a: np.ndarray) -> np.ndarray:
+    """plt.imsave(cmap='viridis') behaviour: normalise to the data range, map through the colormap."""
+    lo, hi = float(a.min()), float(a.max())
+    t = (a - lo) / (hi - lo) if hi > lo else np.zeros_like(a)
+    pos = t * (len(_VIRIDIS) - 1)
+    i0 = np.clip(np.floor(pos).astype(int), 0, len(_VIRIDIS) - 2)
+    w = (pos - i0)[..., None]
+    rgb = _VIRIDIS[i0] * (1 - w) + _VIRIDIS[i0 + 1] * w
+    return rgb.round().astype(np.uint8)
+
+
+def resize_center_crop(img: Image.Image, size: int) -> Image.Image:
+    """transforms.Resize(size, BILINEAR) + CenterCrop(size) on a PIL image (demo.py:74-76)."""
+    w, h = img.size
+    if w <= h:
+        nw, nh = size, int(size * h / w)
+    else:
+        nw, nh = int(size * w / h), size
+    img = img.resize((nw, nh), Image.BILINEAR)
+    left, top = int(round((nw - size) / 2.0)), int(round((nh - size) / 2.0))
+    return img.crop((left, top, left + size, top + size))
+
+
+def to_tensor(img: Image.Image) -> torch.Tensor:
+    a = np.asarray(img, dtype=np.float32) / 255.0
+    if a.ndim == 2:
+        a = a[..., None]
+    return torch.from_numpy(a).permute(2, 0, 1).contiguous()
+
+
+def build_model(task: str, root_dir: str, synthetic: bool, device):
+    import hubconf
+    model = hubconf.dpt_hybrid_384(pretrained=False, task=task)
+    ckpt = os.path.join(root_dir, hubconf._CKPT[task])
+    if os.path.exists(ckpt):
+        hubconf._load_checkpoint(model, ckpt)
+    elif synthetic:
+        from omnidata_b200 import synthetic as syn
+        model.load_state_dict(syn.make_state_dict(0, model.num_channels))
+        print(f"[demo] {ckpt} not found: using seeded synthetic weights")
+    else:
+        raise FileNotFoundError(f"{ckpt} not found (pass --synthetic_weights to run without a checkpoint)")
+    return model.to(device).eval()
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="Visualize output for depth or surface normals")
+    parser.add_argument("--task", dest="task", default="NONE", help="normal or depth")
+    parser.add_argument("--img_path", dest="img_path", help="path to rgb image")
+    parser.add_argument("--output_path", dest="output_path", help="path to where output image should be stored")
+    parser.add_argument("--synthetic_weights", action="store_true")
+    parser.add_argument("--weights_dir", default="./pretrained_models/")
+    args = parser.parse_args(argv)
+    if args.task not in ("normal", "depth"):
+        print("task should be one of the following: normal, depth")
+        sys.exit()
+    if not torch.cuda.is_available():
+        print("demo.py: a CUDA (sm_100a) device is required; this implementation has no CPU path")
+        sys.exit(1)
+    device = torch.device("cuda:0")
+    os.makedirs(args.output_path, exist_ok=True)
+    model = build_model(args.task, args.weights_dir, args.synthetic_weights, device)
+    image_size = 384
+
+    def save_outputs(img_path, name):
+        with torch.no_grad():
+            save_path = os.path.join(args.output_path, f"{name}_{args.task}.png")
+            print(f"Reading input {img_path} ...")
+            img = Image.open(img_path)
+            t = to_tensor(resize_center_crop(img, image_size))[:3]
+            if args.task == "depth":
+                t = (t - 0.5) / 0.5                                   # Normalize(0.5, 0.5), demo.py:92-95
+            t = t.unsqueeze(0).to(device)
+            resize_center_crop(img, 512).save(os.path.join(args.output_path, f"{name}_rgb.png"))
+            if t.shape[1] == 1:
+                t = t.repeat_interleave(3, 1)
+            output = model(t).clamp(min=0, max=1)
+            if args.task == "depth":
+                output = F.interpolate(output.unsqueeze(0), (512, 512), mode="bicubic").squeeze(0)
+                output = 1 - output.clamp(0, 1)
+                Image.fromarray(viridis(output.detach().cpu().squeeze().numpy())).save(save_path)
+            else:
+                arr = (output[0].detach().cpu().permute(1, 2, 0).numpy() * 255.0).round().astype(np.uint8)
+                Image.fromarray(arr).save(save_path)
+            print(f"Writing output {save_path} ...")
+
+    p = Path(args.img_path)
+    if p.is_file():
+        save_outputs(args.img_path, os.path.splitext(os.path.basename(args.img_path))[0])
+    elif p.is_dir():
+        for f in sorted(glob.glob(args.img_path + "/*")):
+            save_outputs(f, os.path.splitext(os.path.basename(f))[0])
+    else:
+        print("invalid file path!")
+        sys.exit()
+
+
+if __name__ == "__main__":
+    main()

@@ -355,6 +355,8 @@ class DPTDepthModel(nn.Module):
         st = gn_stats(s0)
         t = buf("stem_pool", (B, h2 // 2, w2 // 2, 64))
         ops.stem_gn_relu_maxpool(s0, st, pk["stem_g"], pk["stem_b"], t)
+        if taps is not None:
+            taps["stem_conv"], taps["stem_pool"] = s0, t
         feats = []
         hh, ww = h2 // 2, w2 // 2
         for s, b, e in pk["rn_blocks"]:
@@ -390,6 +392,8 @@ class DPTDepthModel(nn.Module):
             else:
                 ops.groupnorm_apply(y3, st3, e["g3"], e["b3"], out, relu=True, res=shortcut)
             t, hh, ww = out, ho, wo
+            if taps is not None:
+                taps[f"{tag}_out"] = out
             if b == _STAGES[s][1] - 1:
                 feats.append(t)
         layer_1, layer_2, f3 = feats
@@ -404,6 +408,8 @@ class DPTDepthModel(nn.Module):
         ops.linear(f3.view(B, 1, gh * gw, 1024), pk["proj_w"], tok[:, 1:, :].unsqueeze(1), bias=pk["proj_b"],
                    residual=pos_grid)
 
+        if taps is not None:
+            taps["tokens_in"] = tok.clone()
         # ---------------- 12 ViT blocks (vit.py:150-151); final norm is dead compute and skipped
         hbuf = buf("vit_h", (B, ntok, _EMBED))
         qkv = buf("vit_qkv", (B, ntok, 3 * _EMBED))
@@ -424,6 +430,8 @@ class DPTDepthModel(nn.Module):
                        act=ops.ACT_GELU)
             ops.linear(mlp.view(rows, -1), blk["fc2"][0], cur.view(rows, -1), bias=blk["fc2"][1],
                        residual=cur.view(rows, -1))
+            if taps is not None:
+                taps[f"tokens_{i}"] = cur.clone()
         tokens_8, tokens_11 = tok, tok_b
 
         # ---------------- reassemble (vit.py:66-97, 431-462)

@@ -184,8 +184,10 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
 
     xin = r(x.float())                                    # im2col stores the image as bf16
     s0 = sconv(xin, BB + "stem.conv.weight", 2)
+    taps["stem_conv"] = s0
     t = F.relu(gn_raw(s0, BB + "stem.norm"))
     t = r(F.max_pool2d(same_pad(t, 3, 2, float("-inf")), 3, 2))
+    taps["stem_pool"] = t
     feats = []
     for s, depth in enumerate((3, 4, 9)):
         for b in range(depth):
@@ -198,6 +200,7 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
             y = r(F.relu(gn_raw(sconv(y, p + "conv2.weight", stride), p + "norm2")))
             y = gn_raw(sconv(y, p + "conv3.weight"), p + "norm3")
             t = r(F.relu(y + sc))
+            taps[f"s{s}b{b}_out"] = t
         feats.append(t)
 
     gh, gw = feats[2].shape[-2:]
@@ -206,6 +209,7 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
     tok = tok.flatten(2).transpose(1, 2) + r(pos[:, 1:])
     cls = (g(P + "cls_token") + pos[:, :1]).expand(B, -1, -1)
     tok = r(torch.cat((cls, tok), dim=1))
+    taps["tokens_in"] = tok
     hooked = {}
     for i in range(12):
         p = f"{P}blocks.{i}."
@@ -221,9 +225,9 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
         h = r(F.layer_norm(tok, (768,), g(p + "norm2.weight"), g(p + "norm2.bias"), 1e-6))
         h = r(F.gelu(F.linear(h, wq(g(p + "mlp.fc1.weight")), g(p + "mlp.fc1.bias"))))
         tok = r(tok + F.linear(h, wq(g(p + "mlp.fc2.weight")), g(p + "mlp.fc2.bias")))
+        taps[f"tokens_{i}"] = tok
         if i in (8, 11):
             hooked[i] = tok
-    taps["tokens_8"], taps["tokens_11"] = hooked[8], hooked[11]
 
     def readout(tk, n):
         pp = f"pretrained.act_postprocess{n}."
