@@ -105,10 +105,14 @@ int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y,
 int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
                   void* stream);
 
-/* GroupNorm statistics (timm GroupNormAct, 32 groups): stats fp32 [b][groups][2] += (sum, sum of
- * squares) over x bf16 [b][hw][c].  The caller zeroes `stats` first (odb_fill_zero). */
-int odb_groupnorm_stats(const void* x, float* stats, int32_t b, int32_t hw, int32_t c,
-                        int32_t groups, void* stream);
+/* GroupNorm statistics (timm GroupNormAct, 32 groups), deterministic (no floating-point atomics):
+ * stats fp32 [b][groups][2] = (mean, 1/sqrt(var + eps)) over x bf16 [b][hw][c], biased variance,
+ * reduced in a fixed order with fp64 combination.  `scratch` is caller-owned device memory of at
+ * least odb_groupnorm_scratch_bytes(...) bytes, 256-byte aligned, ZEROED ONCE at allocation (the
+ * kernel leaves it zeroed); it may be shared by successive calls on one stream. */
+int64_t odb_groupnorm_scratch_bytes(int32_t b, int32_t hw, int32_t c, int32_t groups);
+int odb_groupnorm_stats(const void* x, float* stats, void* scratch, int64_t scratch_bytes, int32_t b,
+                        int32_t hw, int32_t c, int32_t groups, float eps, void* stream);
 
 /* GroupNorm apply (+ optional shortcut, + optional ReLU), timm Bottleneck.forward:
  *   y = relu?( gn(x; stats, gamma, beta) + shortcut )
@@ -116,13 +120,13 @@ int odb_groupnorm_stats(const void* x, float* stats, int32_t b, int32_t hw, int3
 int odb_groupnorm_apply(const void* x, const float* stats, const float* gamma, const float* beta,
                         const void* res, const float* res_stats, const float* res_gamma,
                         const float* res_beta, void* y, int32_t b, int32_t hw, int32_t c,
-                        int32_t groups, float eps, int32_t relu, void* stream);
+                        int32_t groups, int32_t relu, void* stream);
 
 /* Stem tail (timm ResNetV2 stem.norm + stem.pool): GroupNorm+ReLU then MaxPool 3x3 stride 2 with
  * TF-SAME padding (0,1).  x bf16 [b][h][w][c] -> y bf16 [b][h/2][w/2][c]. */
 int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const float* gamma,
                              const float* beta, void* y, int32_t b, int32_t h, int32_t w, int32_t c,
-                             int32_t groups, float eps, void* stream);
+                             int32_t groups, void* stream);
 
 /* im2col for the 7x7 stride-2 TF-SAME stem conv (timm StdConv2dSame 3->64): x fp32 NCHW
  * [b][3][h][w] -> cols bf16 [b*(h/2)*(w/2)][kpad], column (ky*7+kx)*3+ch, zero padded. */

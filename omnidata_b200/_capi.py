@@ -60,11 +60,11 @@ _SIGNATURES = {
                                 C.c_float, C.c_void_p]),
     "odb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p]),
-    "odb_groupnorm_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                      C.c_int32, C.c_void_p]),
-    "odb_groupnorm_apply": (C.c_int, [C.c_void_p] * 9 + [C.c_int32] * 4 + [C.c_float, C.c_int32,
-                                                                           C.c_void_p]),
-    "odb_stem_gn_relu_maxpool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
+    "odb_groupnorm_scratch_bytes": (C.c_int64, [C.c_int32] * 4),
+    "odb_groupnorm_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "odb_groupnorm_apply": (C.c_int, [C.c_void_p] * 9 + [C.c_int32] * 5 + [C.c_void_p]),
+    "odb_stem_gn_relu_maxpool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]),
     "odb_stem_im2col": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_void_p]),
     "odb_upsample2x_add": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),

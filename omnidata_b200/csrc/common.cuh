@@ -172,7 +172,19 @@ ODB_DEVINL constexpr uint32_t umma_idesc_bf16(int m, int n) {
 }
 
 // ---------------------------------------------------------------- small numerics helpers
-ODB_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below one bf16 ulp of the GELU output):
+// 1 MUFU.RCP + 1 MUFU.EX2 + 9 FMA-class ops instead of the ~30-instruction libdevice erff.
+ODB_DEVINL float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  return copysignf(fmaf(-p * t, e, 1.0f), x);
+}
+ODB_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 
 ODB_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

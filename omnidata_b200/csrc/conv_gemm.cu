@@ -2,7 +2,9 @@
 // -> fused epilogue -> TMA store.  One persistent CTA per SM, warp-specialised:
 //   warp 0    TMA producer (one elected lane)
 //   warp 1    TMEM allocation + tcgen05.mma issue (one elected lane)
-//   warps 2-5 epilogue: tcgen05.ld -> bias/act/residual -> bf16 -> swizzled smem -> TMA store
+//   warps 2-9 epilogue: tcgen05.ld -> bias/act/residual -> bf16 -> swizzled smem -> TMA store
+//             (two warps per TMEM lane quadrant, each owning 32 of the 64 columns of a chunk, so
+//              that every SM sub-partition has two epilogue warps to hide ALU/MUFU latency)
 //
 // The A operand of the GEMM (rows = output pixels, K = taps x input channels) is never
 // materialised: each K block is a 4-D TMA box {64 ch, tile_w, tile_h, 1} of the channels-last
@@ -21,8 +23,8 @@ constexpr int kTileRows = 128;                 // UMMA M
 constexpr int kKBlock = 64;                    // bf16 elements per K block = one 128B swizzle row
 constexpr int kABytes = kTileRows * 128;       // 16 KiB per stage
 constexpr int kStagingBytes = kTileRows * 128; // one 128 x 64 bf16 output chunk
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kNumThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kEpiThreads = 256;
 
 struct ConvGemmParams {
   CUtensorMap a_map[ODB_MAX_VIEWS];
@@ -93,7 +95,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), HEAD ? 4 : 8);  // one arrive per participating epilogue warp
     }
     mbar_fence_init();
     for (int v = 0; v < ODB_MAX_VIEWS; ++v) tma_prefetch_desc(&p.a_map[v]);
@@ -169,9 +171,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         umma_commit(tfull_bar(acc));  // accumulator complete
       }
     }
-  } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+  } else if (!HEAD || warp < 6) {
+    // ------------------------------------------------------------ epilogue (warps 2..9)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;      // which 32 of the 64 chunk columns this warp owns
     const int row = quad * 32 + lane;      // accumulator row == pixel within the tile
     const bool store_leader = (warp == 2 && lane == 0);
     const int tw = p.tile_w;
@@ -208,40 +211,61 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         if (lane == 0) mbar_arrive(tempty_bar(acc));
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float f = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + j) : 0.f);
-          v[j] = fmaxf(f, 0.f);
+        for (int j = 0; j < 8; ++j) {
+          float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + j)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * j + 0] = fmaxf(__uint_as_float(r[4 * j + 0]) + b4.x, 0.f);
+          v[4 * j + 1] = fmaxf(__uint_as_float(r[4 * j + 1]) + b4.y, 0.f);
+          v[4 * j + 2] = fmaxf(__uint_as_float(r[4 * j + 2]) + b4.z, 0.f);
+          v[4 * j + 3] = fmaxf(__uint_as_float(r[4 * j + 3]) + b4.w, 0.f);
         }
         if (valid) {
           for (int k = 0; k < p.head_c; ++k) {
             float o = __ldg(p.head_b + k);
+            const float4* wk = reinterpret_cast<const float4*>(p.head_w + k * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o = fmaf(v[j], __ldg(p.head_w + k * 32 + j), o);
+            for (int j = 0; j < 8; ++j) {
+              const float4 w4 = __ldg(wk + j);
+              o = fmaf(v[4 * j + 0], w4.x, o);
+              o = fmaf(v[4 * j + 1], w4.y, o);
+              o = fmaf(v[4 * j + 2], w4.z, o);
+              o = fmaf(v[4 * j + 3], w4.w, o);
+            }
             if (p.head_relu) o = fmaxf(o, 0.f);
             p.head_out[((static_cast<long long>(tb) * p.head_c + k) * p.out_h + y) * p.out_w + x] = o;
           }
         }
       } else {
         const int n0 = tn * BLOCK_N;
-        const float* bias = p.bias ? p.bias + static_cast<long long>(tb) * p.bias_sb + n0 : nullptr;
-        const bf16* res = p.residual
-                              ? p.residual + tb * p.res_sb + y * p.res_sy + x * p.res_sx + n0
+        const int cofs = half * 32;
+        const float* bias =
+            p.bias ? p.bias + static_cast<long long>(tb) * p.bias_sb + n0 + cofs : nullptr;
+        const bf16* res = (p.residual && valid)
+                              ? p.residual + tb * p.res_sb + y * p.res_sy + x * p.res_sx + n0 + cofs
                               : nullptr;
         constexpr int kChunks = BLOCK_N / 64;
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c, ++chunk_counter) {
-          uint32_t r[64];
-          tmem_ld_32x32(t_row + c * 64, r);
-          tmem_ld_32x32(t_row + c * 64 + 32, r + 32);
-          // residual loads overlap the TMEM read
-          uint4 rv[8];
-          if (res != nullptr && valid) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * 64 + cofs, r);
+          // residual / bias loads overlap the TMEM read
+          uint4 rv[4];
+          if (res != nullptr) {
             const uint4* rp = reinterpret_cast<const uint4*>(res + c * 64);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = rp[j];  // plain ld.global: out may alias residual
+            for (int j = 0; j < 4; ++j) rv[j] = rp[j];  // plain ld.global: out may alias residual
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 4; ++j) rv[j] = make_uint4(0, 0, 0, 0);
+          }
+          float4 bv[8];
+          if (bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(bias + c * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           tmem_ld_wait();
           if (c == kChunks - 1) {
@@ -250,14 +274,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
-          uint32_t packed[32], packed_relu[32];
+          uint32_t packed[16], packed_relu[16];
+          const float* bf = reinterpret_cast<const float*>(bv);
+          const uint32_t* ru = reinterpret_cast<const uint32_t*>(rv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
-            if (bias) {
-              f0 += __ldg(bias + c * 64 + 2 * j);
-              f1 += __ldg(bias + c * 64 + 2 * j + 1);
-            }
+          for (int j = 0; j < 16; ++j) {
+            float f0 = __uint_as_float(r[2 * j]) + bf[2 * j];
+            float f1 = __uint_as_float(r[2 * j + 1]) + bf[2 * j + 1];
             if (p.act == ODB_ACT_RELU) {
               f0 = fmaxf(f0, 0.f);
               f1 = fmaxf(f1, 0.f);
@@ -265,8 +288,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               f0 = gelu_erf(f0);
               f1 = gelu_erf(f1);
             }
-            const uint32_t ru = reinterpret_cast<const uint32_t*>(rv)[j];
-            const float2 rr = unpack_bf16x2(ru);
+            const float2 rr = unpack_bf16x2(ru[j]);
             f0 += rr.x;
             f1 += rr.y;
             packed[j] = pack_bf16x2(f0, f1);
@@ -283,17 +305,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint32_t buf0 = smem_base + Plan::kCOff + (slot * bufs_per_chunk) * kStagingBytes;
           const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t addr = buf0 + rowoff + (static_cast<uint32_t>(j ^ (row & 7)) << 4);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr =
+                buf0 + rowoff + (static_cast<uint32_t>((half * 4 + j) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j]),
                          "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
                          : "memory");
           }
           if (p.has_out2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t addr =
-                  buf0 + kStagingBytes + rowoff + (static_cast<uint32_t>(j ^ (row & 7)) << 4);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t addr = buf0 + kStagingBytes + rowoff +
+                                    (static_cast<uint32_t>((half * 4 + j) ^ (row & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
                            "r"(packed_relu[4 * j]), "r"(packed_relu[4 * j + 1]),
                            "r"(packed_relu[4 * j + 2]), "r"(packed_relu[4 * j + 3])

@@ -71,20 +71,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// GroupNorm statistics.  Block = (image, pixel slab); thread = (channel octet, pixel lane).
-// Per-channel partial sums are combined per group in shared memory, one atomicAdd pair per
-// (block, group).
-__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const bf16* __restrict__ x,
-                                                              float* __restrict__ stats, int hw,
-                                                              int c, int groups,
-                                                              int pixels_per_block) {
-  __shared__ float s_sum[64], s_sq[64];
-  const int b = blockIdx.y;
+// GroupNorm statistics, deterministic: block = (image, pixel slab); thread = (channel octet, pixel
+// lane) accumulates fp32 partial sums over a short strided run; the block combines them in a FIXED
+// order in fp64 and writes one (sum, sum of squares) pair per group to a partials buffer.  The last
+// block of an image to finish (ticket counter) reduces the slabs in slab order, in fp64, and
+// writes (mean, rstd) — no floating-point atomics anywhere, so results are bit-reproducible
+// run to run and independent of the batch size.
+constexpr int kGnMaxC = 1024;
+
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(
+    const bf16* __restrict__ x, float* __restrict__ stats, double* __restrict__ partial,
+    unsigned int* __restrict__ counters, int hw, int c, int groups, int pixels_per_block,
+    float eps) {
+  __shared__ float s_thr[2][256 * 8];     // per-thread channel partials, [plane][channel]
+  __shared__ double s_ch[2][kGnMaxC];     // per-channel block sums
+  __shared__ int s_last;
+  const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
   const int octets = c >> 3;
   const int cpg = c / groups;
-  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
-  const int p0 = blockIdx.x * pixels_per_block;
+  const int p0 = slab * pixels_per_block;
   const int p1 = min(hw, p0 + pixels_per_block);
   const int oct = threadIdx.x % octets;
   const int plane = threadIdx.x / octets;
@@ -96,29 +101,58 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const bf16* __rest
       float v[8];
       load8(base + (long long)p * c, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] += v[j] * v[j]; }
+      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
     }
-  }
-  if (cpg >= 8) {
-    float ts = 0.f, tq = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ts += s[j]; tq += q[j]; }
-    const int g = (oct * 8) / cpg;
-    atomicAdd(&s_sum[g], ts);
-    atomicAdd(&s_sq[g], tq);
-  } else {
-    for (int j0 = 0; j0 < 8; j0 += cpg) {
-      float ts = 0.f, tq = 0.f;
-      for (int j = j0; j < j0 + cpg; ++j) { ts += s[j]; tq += q[j]; }
-      const int g = (oct * 8 + j0) / cpg;
-      atomicAdd(&s_sum[g], ts);
-      atomicAdd(&s_sq[g], tq);
+    for (int j = 0; j < 8; ++j) {
+      s_thr[0][plane * c + oct * 8 + j] = s[j];
+      s_thr[1][plane * c + oct * 8 + j] = q[j];
     }
   }
   __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double ts = 0.0, tq = 0.0;
+    for (int pl = 0; pl < planes; ++pl) {
+      ts += (double)s_thr[0][pl * c + ch];
+      tq += (double)s_thr[1][pl * c + ch];
+    }
+    s_ch[0][ch] = ts;
+    s_ch[1][ch] = tq;
+  }
+  __syncthreads();
   if (threadIdx.x < groups) {
-    atomicAdd(&stats[((long long)b * groups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-    atomicAdd(&stats[((long long)b * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    const int g = threadIdx.x;
+    double ts = 0.0, tq = 0.0;
+    for (int j = 0; j < cpg; ++j) { ts += s_ch[0][g * cpg + j]; tq += s_ch[1][g * cpg + j]; }
+    double* dst = partial + (((long long)b * slabs + slab) * groups + g) * 2;
+    dst[0] = ts;
+    dst[1] = tq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&counters[b], 1u);
+    s_last = (ticket == (unsigned int)(slabs - 1));
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < groups) {
+      const int g = threadIdx.x;
+      double ts = 0.0, tq = 0.0;
+      for (int sl = 0; sl < slabs; ++sl) {
+        const double* src = partial + (((long long)b * slabs + sl) * groups + g) * 2;
+        ts += src[0];
+        tq += src[1];
+      }
+      const double n = (double)hw * (double)cpg;
+      const double mean = ts / n;
+      double var = tq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[((long long)b * groups + g) * 2 + 0] = (float)mean;
+      stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    if (threadIdx.x == 0) counters[b] = 0u;   // self-reset for the next launch on this stream
   }
 }
 
@@ -126,30 +160,40 @@ struct GnCoef {  // per-channel scale/shift of one image: y = x * a + b
   float a, b;
 };
 ODB_DEVINL GnCoef gn_coef(const float* stats, const float* gamma, const float* beta, int b,
-                          int groups, int cpg, int ch, float inv_n, float eps) {
+                          int groups, int cpg, int ch) {
   const int g = ch / cpg;
-  const float s = __ldg(&stats[((long long)b * groups + g) * 2 + 0]);
-  const float q = __ldg(&stats[((long long)b * groups + g) * 2 + 1]);
-  const float mean = s * inv_n;
-  const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + eps);
+  const float mean = __ldg(&stats[((long long)b * groups + g) * 2 + 0]);
+  const float rstd = __ldg(&stats[((long long)b * groups + g) * 2 + 1]);
   GnCoef k;
   k.a = rstd * __ldg(gamma + ch);
   k.b = __ldg(beta + ch) - mean * k.a;
   return k;
 }
 
-// y = relu?( gn(x) + shortcut ); thread = (pixel, channel octet).
+// y = relu?( gn(x) + shortcut ).  Each block first folds the statistics and the affine parameters
+// of its image into a per-channel (scale, shift) table in shared memory, so the streaming loop is
+// one FMA per element; thread = (pixel, channel octet), 16-byte accesses.
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
     const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, const bf16* __restrict__ res,
     const float* __restrict__ res_stats, const float* __restrict__ res_gamma,
-    const float* __restrict__ res_beta, bf16* __restrict__ y, int hw, int c, int groups, float eps,
-    int relu) {
+    const float* __restrict__ res_beta, bf16* __restrict__ y, int hw, int c, int groups, int relu) {
+  extern __shared__ float coef[];  // [c] scale, [c] shift, then [c] shortcut scale (shift is folded)
   const int b = blockIdx.y;
   const int octets = c >> 3;
   const int cpg = c / groups;
-  const float inv_n = 1.0f / ((float)hw * (float)cpg);
+  const bool res_norm = (res != nullptr) && (res_stats != nullptr);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    GnCoef k = gn_coef(stats, gamma, beta, b, groups, cpg, ch);
+    if (res_norm) {
+      const GnCoef kr = gn_coef(res_stats, res_gamma, res_beta, b, groups, cpg, ch);
+      coef[2 * c + ch] = kr.a;
+      k.b += kr.b;
+    }
+    coef[ch] = k.a;
+    coef[c + ch] = k.b;
+  }
+  __syncthreads();
   const long long total = (long long)hw * octets;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -157,24 +201,27 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
     const long long off = ((long long)b * hw) * c + i * 8;
     float v[8], o[8];
     load8(x + off, v);
+    const float4 a0 = *reinterpret_cast<const float4*>(coef + oct * 8);
+    const float4 a1 = *reinterpret_cast<const float4*>(coef + oct * 8 + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(coef + c + oct * 8);
+    const float4 s1 = *reinterpret_cast<const float4*>(coef + c + oct * 8 + 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const GnCoef k = gn_coef(stats, gamma, beta, b, groups, cpg, oct * 8 + j, inv_n, eps);
-      o[j] = v[j] * k.a + k.b;
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], a[j], sh[j]);
     if (res != nullptr) {
       float r[8];
       load8(res + off, r);
-      if (res_stats != nullptr) {
+      if (res_norm) {
+        const float4 r0 = *reinterpret_cast<const float4*>(coef + 2 * c + oct * 8);
+        const float4 r1 = *reinterpret_cast<const float4*>(coef + 2 * c + oct * 8 + 4);
+        const float ra[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const GnCoef k =
-              gn_coef(res_stats, res_gamma, res_beta, b, groups, cpg, oct * 8 + j, inv_n, eps);
-          r[j] = r[j] * k.a + k.b;
-        }
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(r[j], ra[j], o[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += r[j];
     }
     if (relu) {
 #pragma unroll
@@ -187,23 +234,27 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
 // Stem: GroupNorm + ReLU + MaxPool 3x3 s2, TF-SAME pad (0,1): window rows/cols 2o..2o+2, clipped.
 __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
     const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-    const float* __restrict__ beta, bf16* __restrict__ y, int h, int w, int c, int groups,
-    float eps) {
+    const float* __restrict__ beta, bf16* __restrict__ y, int h, int w, int c, int groups) {
+  extern __shared__ float coef[];  // [c] scale, [c] shift
   const int b = blockIdx.y;
   const int octets = c >> 3;
   const int cpg = c / groups;
   const int oh = h / 2, ow = w / 2;
-  const float inv_n = 1.0f / ((float)h * (float)w * (float)cpg);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const GnCoef k = gn_coef(stats, gamma, beta, b, groups, cpg, ch);
+    coef[ch] = k.a;
+    coef[c + ch] = k.b;
+  }
+  __syncthreads();
   const long long total = (long long)oh * ow * octets;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int oct = (int)(i % octets);
     const long long pix = i / octets;
     const int ox = (int)(pix % ow), oy = (int)(pix / ow);
-    GnCoef k[8];
+    float a[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      k[j] = gn_coef(stats, gamma, beta, b, groups, cpg, oct * 8 + j, inv_n, eps);
+    for (int j = 0; j < 8; ++j) { a[j] = coef[oct * 8 + j]; sh[j] = coef[c + oct * 8 + j]; }
     float m[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = 0.f;  // relu output is >= 0, so 0 is the identity of max
@@ -216,9 +267,7 @@ __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
         float v[8];
         load8(x + (((long long)b * h + iy) * w + ix) * c + oct * 8, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          m[j] = fmaxf(m[j], v[j] * k[j].a + k[j].b);  // relu folded into the 0-initialised max
-        }
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(v[j], a[j], sh[j]));  // relu folded into max(0,.)
       }
     }
     store8(y + (((long long)b * oh + oy) * ow + ox) * c + oct * 8, m);
@@ -376,20 +425,39 @@ static int gn_args_ok(int b, int hw, int c, int groups) {
          (c / 8) <= 256 && ((c / groups) >= 8 ? (c / groups) % 8 == 0 : 8 % (c / groups) == 0);
 }
 
-extern "C" int odb_groupnorm_stats(const void* x, float* stats, int32_t b, int32_t hw, int32_t c,
-                                   int32_t groups, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!x || !stats || !gn_args_ok(b, hw, c, groups))
-    return fail(ODB_ERR_INVALID, "groupnorm_stats: bad argument");
-  // ~4 slabs per SM across the batch keeps every SM busy without drowning in atomics
-  int slabs = (num_sms() * 4 + b - 1) / b;
-  if (slabs < 1) slabs = 1;
-  int ppb = (hw + slabs - 1) / slabs;
+static void gn_stats_plan(int b, int hw, int c, int* slabs, int* ppb) {
+  // The slab size depends on the layer shape only (never on the batch), so that the order of every
+  // floating-point sum — and therefore the result — is identical whatever batch an image sits in.
+  (void)b;
   const int planes = 256 / (c / 8);
-  if (ppb < planes * 4) ppb = planes * 4;
-  dim3 grid((hw + ppb - 1) / ppb, b);
-  groupnorm_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), stats, hw, c,
-                                                   groups, ppb);
+  *ppb = planes * 8;                      // 8 pixels per thread
+  *slabs = (hw + *ppb - 1) / *ppb;
+}
+
+extern "C" int64_t odb_groupnorm_scratch_bytes(int32_t b, int32_t hw, int32_t c, int32_t groups) {
+  if (!gn_args_ok(b, hw, c, groups)) return -1;
+  int slabs, ppb;
+  gn_stats_plan(b, hw, c, &slabs, &ppb);
+  return 256 + (int64_t)b * 4 + (int64_t)b * slabs * groups * 2 * 8;
+}
+
+extern "C" int odb_groupnorm_stats(const void* x, float* stats, void* scratch, int64_t scratch_bytes,
+                                   int32_t b, int32_t hw, int32_t c, int32_t groups, float eps,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !stats || !scratch || !gn_args_ok(b, hw, c, groups) || c > kGnMaxC)
+    return fail(ODB_ERR_INVALID, "groupnorm_stats: bad argument");
+  if (scratch_bytes < odb_groupnorm_scratch_bytes(b, hw, c, groups) ||
+      (reinterpret_cast<uintptr_t>(scratch) & 255u))
+    return fail(ODB_ERR_INVALID, "groupnorm_stats: scratch too small or not 256-byte aligned");
+  int slabs, ppb;
+  gn_stats_plan(b, hw, c, &slabs, &ppb);
+  unsigned int* counters = static_cast<unsigned int*>(scratch);
+  const size_t part_off = (((size_t)b * 4) + 255) & ~(size_t)255;
+  double* partial = reinterpret_cast<double*>(static_cast<char*>(scratch) + part_off);
+  dim3 grid(slabs, b);
+  groupnorm_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), stats, partial,
+                                                   counters, hw, c, groups, ppb, eps);
   count_launch();
   return check_launch("groupnorm_stats");
 }
@@ -397,7 +465,7 @@ extern "C" int odb_groupnorm_stats(const void* x, float* stats, int32_t b, int32
 extern "C" int odb_groupnorm_apply(const void* x, const float* stats, const float* gamma,
                                    const float* beta, const void* res, const float* res_stats,
                                    const float* res_gamma, const float* res_beta, void* y, int32_t b,
-                                   int32_t hw, int32_t c, int32_t groups, float eps, int32_t relu,
+                                   int32_t hw, int32_t c, int32_t groups, int32_t relu,
                                    void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !stats || !gamma || !beta || !y || !gn_args_ok(b, hw, c, groups))
@@ -407,16 +475,16 @@ extern "C" int odb_groupnorm_apply(const void* x, const float* stats, const floa
   int gx = grid_for((long long)hw * (c / 8), 256) / b;
   if (gx < 1) gx = 1;
   dim3 grid(gx, b);
-  groupnorm_apply_kernel<<<grid, 256, 0, stream>>>(
+  groupnorm_apply_kernel<<<grid, 256, 3 * c * sizeof(float), stream>>>(
       static_cast<const bf16*>(x), stats, gamma, beta, static_cast<const bf16*>(res), res_stats,
-      res_gamma, res_beta, static_cast<bf16*>(y), hw, c, groups, eps, relu);
+      res_gamma, res_beta, static_cast<bf16*>(y), hw, c, groups, relu);
   count_launch();
   return check_launch("groupnorm_apply");
 }
 
 extern "C" int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const float* gamma,
                                         const float* beta, void* y, int32_t b, int32_t h, int32_t w,
-                                        int32_t c, int32_t groups, float eps, void* stream_) {
+                                        int32_t c, int32_t groups, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !stats || !gamma || !beta || !y || h < 2 || w < 2 || (h & 1) || (w & 1) ||
       !gn_args_ok(b, h * w, c, groups))
@@ -424,9 +492,8 @@ extern "C" int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const
   int gx = grid_for((long long)(h / 2) * (w / 2) * (c / 8), 256) / b;
   if (gx < 1) gx = 1;
   dim3 grid(gx, b);
-  stem_gn_relu_maxpool_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), stats, gamma,
-                                                        beta, static_cast<bf16*>(y), h, w, c,
-                                                        groups, eps);
+  stem_gn_relu_maxpool_kernel<<<grid, 256, 2 * c * sizeof(float), stream>>>(
+      static_cast<const bf16*>(x), stats, gamma, beta, static_cast<bf16*>(y), h, w, c, groups);
   count_launch();
   return check_launch("stem_gn_relu_maxpool");
 }

@@ -340,12 +340,14 @@ class DPTDepthModel(nn.Module):
         h2, w2 = H // 2, W // 2
         n_gn = 1 + sum(3 * d + 1 for _, d in _STAGES)
         stats_pool = buf("gn_stats", (n_gn, B, 32, 2), torch.float32)
-        stats_pool.zero_()
+        gn_scratch = ws.bufs.get("gn_scratch")
+        if gn_scratch is None:                         # zeroed once; the kernel leaves it zeroed
+            gn_scratch = ws.bufs["gn_scratch"] = torch.zeros(4 << 20, dtype=torch.uint8, device=x.device)
         stat_i = iter(range(n_gn))
 
         def gn_stats(t):
             st = stats_pool[next(stat_i)]
-            ops.groupnorm_stats(t, st, zero=False)
+            ops.groupnorm_stats(t, st, scratch=gn_scratch)
             return st
 
         cols = buf("stem_cols", (B * h2 * w2, 160))

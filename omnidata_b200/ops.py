@@ -196,28 +196,46 @@ def attention(qkv, out, heads: int = 12, scale: float = 0.125):
     _call("odb_attention", {"flops": 4.0 * b * heads * n * n * 64, "bytes": 2 * (qkv.numel() + out.numel())}, lib().odb_attention, qkv.data_ptr(), out.data_ptr(), b, n, heads, scale, _stream())
 
 
-def groupnorm_stats(x, stats, groups: int = 32, zero: bool = True):
+_GN_SCRATCH = {}
+
+
+def groupnorm_scratch(device, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch shared by all GroupNorm statistics launches of one device/stream."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _GN_SCRATCH.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _GN_SCRATCH[key] = t
+    return t
+
+
+def groupnorm_stats(x, stats, groups: int = 32, eps: float = 1e-5, scratch: Optional[torch.Tensor] = None):
+    """stats[b, g] = (mean, rstd).  Deterministic; `scratch` must stay zeroed between calls (it does)."""
     _need(x, torch.bfloat16, "x"); _need(stats, torch.float32, "stats")
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
-    if zero:
-        check(lib().odb_fill_zero(stats.data_ptr(), stats.numel() * 4, _stream()), "odb_fill_zero")
-    _call("odb_groupnorm_stats", {"bytes": 2 * x.numel()}, lib().odb_groupnorm_stats, x.data_ptr(), stats.data_ptr(), b, hw, c, groups, _stream())
+    need = int(lib().odb_groupnorm_scratch_bytes(b, hw, c, groups))
+    if need < 0:
+        raise _capi.OdbError("groupnorm_stats: unsupported shape")
+    if scratch is None:
+        scratch = groupnorm_scratch(x.device, need)
+    _call("odb_groupnorm_stats", {"bytes": 2 * x.numel()}, lib().odb_groupnorm_stats, x.data_ptr(), stats.data_ptr(),
+          scratch.data_ptr(), scratch.numel(), b, hw, c, groups, eps, _stream())
 
 
 def groupnorm_apply(x, stats, gamma, beta, out, *, relu: bool, res=None, res_stats=None, res_gamma=None,
-                    res_beta=None, groups: int = 32, eps: float = 1e-5):
+                    res_beta=None, groups: int = 32):
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
-    _call("odb_groupnorm_apply", {"bytes": 2 * x.numel() * (2 + (res is not None))}, lib().odb_groupnorm_apply, x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                    _ptr(res), _ptr(res_stats), _ptr(res_gamma), _ptr(res_beta),
-                                    out.data_ptr(), b, hw, c, groups, eps, 1 if relu else 0, _stream())
+    _call("odb_groupnorm_apply", {"bytes": 2 * x.numel() * (2 + (res is not None))}, lib().odb_groupnorm_apply,
+          x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(res), _ptr(res_stats),
+          _ptr(res_gamma), _ptr(res_beta), out.data_ptr(), b, hw, c, groups, 1 if relu else 0, _stream())
 
 
-def stem_gn_relu_maxpool(x, stats, gamma, beta, out, groups: int = 32, eps: float = 1e-5):
+def stem_gn_relu_maxpool(x, stats, gamma, beta, out, groups: int = 32):
     b, h, w, c = x.shape
-    _call("odb_stem_gn_relu_maxpool", {}, lib().odb_stem_gn_relu_maxpool, x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                         out.data_ptr(), b, h, w, c, groups, eps, _stream())
+    _call("odb_stem_gn_relu_maxpool", {"bytes": int(2.5 * x.numel())}, lib().odb_stem_gn_relu_maxpool, x.data_ptr(),
+          stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), b, h, w, c, groups, _stream())
 
 
 def stem_im2col(x, cols):

@@ -165,6 +165,27 @@ def forward_fp32(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
 
 
 # ----------------------------------------------------------------------------- product rounding points
+def _attention_online_bf16(q, k, v, chunk: int = 64):
+    """The attention kernel's arithmetic (omnidata_b200/csrc/attention.cu): flash-style online softmax
+    over 64-key chunks in the log2 domain; the probabilities of a chunk are rounded to bf16 for the PV
+    product while the running row sum uses the unrounded fp32 values.  Equal to softmax(qk^T/8)v in
+    real arithmetic."""
+    scale_log2e = float(torch.tensor(0.125, dtype=torch.float32) * torch.tensor(1.4426950408889634, dtype=torch.float32))
+    n = q.shape[-2]
+    o = torch.zeros_like(q)
+    m = torch.full(q.shape[:-1], float("-inf"), dtype=q.dtype)
+    l = torch.zeros(q.shape[:-1], dtype=q.dtype)
+    for c0 in range(0, n, chunk):
+        s_ = (q @ k[..., c0:c0 + chunk, :].transpose(-2, -1)) * scale_log2e
+        m_new = torch.maximum(m, s_.amax(dim=-1))
+        alpha = torch.exp2(m - m_new)
+        p = torch.exp2(s_ - m_new[..., None])
+        l = l * alpha + p.sum(dim=-1)
+        o = o * alpha[..., None] + _bf16(p) @ v[..., c0:c0 + chunk, :]
+        m = m_new
+    return o / l[..., None]
+
+
 def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[dict] = None,
                  non_negative: bool = True) -> torch.Tensor:
     """Same network with bf16 operands / fp32 accumulation and a bf16 rounding wherever the CUDA
@@ -217,9 +238,7 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
         qkv = r(F.linear(h, wq(g(p + "attn.qkv.weight")), g(p + "attn.qkv.bias")))
         N = qkv.shape[1]
         q, k, v = qkv.reshape(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4)
-        s_ = (q @ k.transpose(-2, -1)) * 0.125
-        pr = torch.exp(s_ - s_.amax(dim=-1, keepdim=True))
-        a = (r(pr) @ v) / pr.sum(dim=-1, keepdim=True)    # P rounded to bf16 for the PV product
+        a = _attention_online_bf16(q, k, v)
         a = r(a.transpose(1, 2).reshape(B, N, 768))
         tok = r(tok + F.linear(a, wq(g(p + "attn.proj.weight")), g(p + "attn.proj.bias")))
         h = r(F.layer_norm(tok, (768,), g(p + "norm2.weight"), g(p + "norm2.bias"), 1e-6))

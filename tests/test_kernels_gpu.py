@@ -213,12 +213,12 @@ def test_attention(b, tokens):
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(b, tokens, 3, 12, 64).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2) * 0.125
-    p = torch.exp(s - s.amax(dim=-1, keepdim=True))
-    # the kernel's definition: P rounded to bf16 for the PV product, fp32 row sum of the unrounded P
-    ref = (p.to(torch.bfloat16).float() @ v) / p.sum(dim=-1, keepdim=True)
-    check(out, ref.transpose(1, 2).reshape(b, tokens, 768), f"attention b{b} n{tokens}", tol=2e-3)
+    # the kernel's definition (online softmax over 64-key chunks, P rounded to bf16 for PV)
+    from oracle.dpt_oracle import _attention_online_bf16
+    ref = _attention_online_bf16(q.cpu(), k.cpu(), v.cpu()).to(dev())
+    check(out, ref.transpose(1, 2).reshape(b, tokens, 768), f"attention b{b} n{tokens}", tol=1e-3)
     exact = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(b, tokens, 768)
-    assert rel_l2(out.float(), exact) < 6e-3
+    assert rel_l2(out.float(), exact) < 4e-3
 
 
 @pytest.mark.parametrize("c,hw", [(64, 96 * 96), (256, 96 * 96), (128, 48 * 48), (1024, 24 * 24), (512, 100)])

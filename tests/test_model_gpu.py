@@ -16,7 +16,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = Path(__file__).parent / "golden"
-BF16_TOL = 5e-3
+BF16_TOL = 4e-3
 DRIFT_FACTOR = 1.5
 TAPS = ["layer_1", "layer_2", "tokens_8", "tokens_11", "layer_3", "layer_4", "layer_1_rn", "layer_2_rn",
         "layer_3_rn", "layer_4_rn", "path_4", "path_3", "path_2", "path_1"]
@@ -117,7 +117,7 @@ def test_cuda_graph_replay_equals_eager_and_outputs_are_fresh(setup):
     torch.cuda.synchronize()
     model.use_cuda_graph = False
     model.keep_taps = True
-    assert torch.equal(y0, y1) and torch.equal(y1, y3)
+    assert torch.equal(y0, y1) and torch.equal(y1, y3)      # bit-reproducible: no fp atomics anywhere
     assert torch.equal(y2, y1.flip(0))
     assert y1.data_ptr() != y3.data_ptr()
 
@@ -132,4 +132,4 @@ def test_batch_independence(setup):
         y1 = model(x[1:])
     torch.cuda.synchronize()
     model.keep_taps = True
-    assert rel(y1.float().cpu(), y2[1:].float().cpu()) < 2e-3
+    assert torch.equal(y1, y2[1:])                          # bit-identical regardless of batch size
