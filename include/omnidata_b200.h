@@ -83,6 +83,7 @@ typedef struct odb_conv_gemm_desc {
   int32_t act;        /* odb_act */
   int32_t tile_w, tile_h; /* spatial tile of the 128-row MMA tile, tile_w*tile_h <= 128; 0 = auto */
   int32_t block_n;        /* N tile: 256, 128, 64 (32 with the head tail); 0 = auto */
+  int32_t cta_pair;       /* tcgen05 cta_group::2 (two SMs per 256-row tile): 0 = auto, 1 = on, -1 = off */
   /* Fused DPT head tail (M/dpt_depth.py:93-97): only with n == 32.  When head_out != NULL the
    * 32-channel result relu(v + bias) is not stored; instead
    *   head_out[b][k][y][x] = relu?(head_b[k] + sum_j head_w[k][j] * relu(v_j + bias_j))  (fp32, NCHW) */

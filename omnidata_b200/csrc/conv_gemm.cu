@@ -52,9 +52,10 @@ struct ConvGemmParams {
   float* head_out;
 };
 
-template <int BLOCK_N, int STAGES, int NSTAGING>
+template <int BLOCK_N, int STAGES, int NSTAGING, bool PAIR>
 struct SmemPlan {
-  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // a CTA pair splits B along N
+  static constexpr int kBBytes = kBRows * 128;
   static constexpr int kAOff = 0;
   static constexpr int kBOff = STAGES * kABytes;
   static constexpr int kCOff = kBOff + STAGES * kBBytes;
@@ -70,10 +71,15 @@ struct TmemCols {
       2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128 : 2 * BLOCK_N <= 256 ? 256 : 512;
 };
 
-template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD>
+// PAIR = true: two CTAs of a cluster form one tcgen05 cta_group::2 unit.  The pair computes two
+// vertically adjacent 128-row M tiles against the same N tile as ONE UMMA (M = 256): each CTA
+// TMA-loads its own A rows and HALF of the B rows, the leader CTA issues the MMAs for both, and each
+// CTA drains its own 128 TMEM lanes.  Per-SM smem fill and L2 read traffic per MMA drop by a third.
+template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING>;
+  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR>;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Plan::kBarOff;
@@ -90,12 +96,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), PAIR ? 2 : 1);  // pair: leader's expect_tx arrive + the peer's arrive
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), HEAD ? 4 : 8);  // one arrive per participating epilogue warp
+      // one arrive per participating epilogue warp (of both CTAs for a pair)
+      mbar_init(tempty_bar(a), (HEAD ? 4 : 8) * (PAIR ? 2 : 1));
     }
     mbar_fence_init();
     for (int v = 0; v < ODB_MAX_VIEWS; ++v) tma_prefetch_desc(&p.a_map[v]);
@@ -103,40 +110,69 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (!HEAD) tma_prefetch_desc(&p.out_map);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TmemCols<BLOCK_N>::value);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_cg2(tmem_slot, TmemCols<BLOCK_N>::value);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, TmemCols<BLOCK_N>::value);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int total_tiles = p.tiles_n * p.tiles_x * p.tiles_y * p.tiles_b;
+  // work units: (n tile, m tile) for a single CTA, (n tile, pair of m tiles) for a CTA pair
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+  const int total_tiles = p.tiles_n * m_units;
+  const int unit0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_kb = p.num_taps * p.kb_per_tap;
   const uint32_t a_bytes = static_cast<uint32_t>(p.tile_w * p.tile_h) * 128u;
+  // unit -> (tn, tx, ty, tb); an M tile past the end (odd tile count, peer CTA) maps to batch
+  // index tiles_b: every TMA box is then out of bounds (zero fill on load, nothing stored)
+  auto decode = [&](int unit, int& tn, int& tx, int& ty, int& tb) {
+    tn = unit % p.tiles_n;
+    int m = unit / p.tiles_n;
+    if (PAIR) m = 2 * m + static_cast<int>(cta_rank);
+    if (m >= m_tiles) { tx = 0; ty = 0; tb = p.tiles_b; return; }
+    tx = m % p.tiles_x; m /= p.tiles_x;
+    ty = m % p.tiles_y;
+    tb = m / p.tiles_y;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int tn = t % p.tiles_n; t /= p.tiles_n;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y;
-        const int tb = t / p.tiles_y;
+      for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+        int tn, tx, ty, tb;
+        decode(tile, tn, tx, ty, tb);
         const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const CUtensorMap* amap = &p.a_map[p.tap_view[tap]];
           const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), a_bytes + Plan::kBBytes);
-            tma_load_4d(smem_base + Plan::kAOff + stage * kABytes, amap, full_bar(stage),
-                        kb * kKBlock, ax, ay, tb);
-            tma_load_2d(smem_base + Plan::kBOff + stage * Plan::kBBytes, &p.b_map, full_bar(stage),
-                        (tap * p.kb_per_tap + kb) * kKBlock, tn * BLOCK_N);
+            const uint32_t sa = smem_base + Plan::kAOff + stage * kABytes;
+            const uint32_t sb = smem_base + Plan::kBOff + stage * Plan::kBBytes;
+            const int kcoord = (tap * p.kb_per_tap + kb) * kKBlock;
+            if constexpr (PAIR) {
+              // both CTAs credit the LEADER's full barrier; the leader arms it for both CTAs' bytes
+              const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+              if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * (a_bytes + Plan::kBBytes));
+              tma_load_4d_cg2(sa, amap, lead_full, kb * kKBlock, ax, ay, tb);
+              tma_load_2d_cg2(sb, &p.b_map, lead_full, kcoord,
+                              tn * BLOCK_N + static_cast<int>(cta_rank) * Plan::kBRows);
+              if (cta_rank != 0) mbar_arrive_cluster(lead_full);
+            } else {
+              mbar_expect_tx(full_bar(stage), a_bytes + Plan::kBBytes);
+              tma_load_4d(sa, amap, full_bar(stage), kb * kKBlock, ax, ay, tb);
+              tma_load_2d(sb, &p.b_map, full_bar(stage), kcoord, tn * BLOCK_N);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -144,12 +180,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileRows, BLOCK_N);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kTileRows : kTileRows, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
         const uint32_t acc = iter & 1u;
         const uint32_t acc_phase = (iter >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -163,12 +199,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
           for (int k = 0; k < kKBlock / 16; ++k) {
             // +32 bytes (= 2 in 16-byte units) per UMMA_K=16 inside the 128B swizzle row
-            umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR)
+              umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if constexpr (PAIR) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete
+        // accumulator complete
+        if constexpr (PAIR) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
       }
     }
   } else if (!HEAD || warp < 6) {
@@ -185,15 +226,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int bufs_per_chunk = p.has_out2 ? 2 : 1;
     const int slots = NSTAGING > 0 ? NSTAGING / bufs_per_chunk : 1;
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      int t = tile;
-      const int tn = t % p.tiles_n; t /= p.tiles_n;
-      const int tx = t % p.tiles_x; t /= p.tiles_x;
-      const int ty = t % p.tiles_y;
-      const int tb = t / p.tiles_y;
+    const uint32_t tempty0 = PAIR ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    const uint32_t tempty1 = PAIR ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
+    for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
+      int tn, tx, ty, tb;
+      decode(tile, tn, tx, ty, tb);
       const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
       const int x = x0 + lx, y = y0 + ly;
-      const bool valid = row_in_tile && x < p.out_w && y < p.out_h;
+      const bool valid = row_in_tile && x < p.out_w && y < p.out_h && tb < p.out_b;
       const uint32_t acc = iter & 1u;
       const uint32_t acc_phase = (iter >> 1) & 1u;
 
@@ -208,7 +248,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(acc ? tempty1 : tempty0);
+          else mbar_arrive(tempty_bar(acc));
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -238,8 +281,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       } else {
         const int n0 = tn * BLOCK_N;
         const int cofs = half * 32;
-        const float* bias =
-            p.bias ? p.bias + static_cast<long long>(tb) * p.bias_sb + n0 + cofs : nullptr;
+        const float* bias =   // (a pair's padding tile has tb == tiles_b: keep the address in range)
+            p.bias ? p.bias + static_cast<long long>(tb < p.out_b ? tb : 0) * p.bias_sb + n0 + cofs
+                   : nullptr;
         const bf16* res = (p.residual && valid)
                               ? p.residual + tb * p.res_sb + y * p.res_sy + x * p.res_sx + n0 + cofs
                               : nullptr;
@@ -272,36 +316,42 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(acc ? tempty1 : tempty0);
+              else mbar_arrive(tempty_bar(acc));
+            }
           }
-          uint32_t packed[16], packed_relu[16];
+          // ---- bias + activation (specialised per activation: a straight-line block keeps the 32
+          //      independent elements of a thread in flight), residual, bf16 packing
+          float v[32];
           const float* bf = reinterpret_cast<const float*>(bv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bf[j];
+          if (p.act == ODB_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == ODB_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          uint32_t packed[16];
           const uint32_t* ru = reinterpret_cast<const uint32_t*>(rv);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float f0 = __uint_as_float(r[2 * j]) + bf[2 * j];
-            float f1 = __uint_as_float(r[2 * j + 1]) + bf[2 * j + 1];
-            if (p.act == ODB_ACT_RELU) {
-              f0 = fmaxf(f0, 0.f);
-              f1 = fmaxf(f1, 0.f);
-            } else if (p.act == ODB_ACT_GELU) {
-              f0 = gelu_erf(f0);
-              f1 = gelu_erf(f1);
-            }
             const float2 rr = unpack_bf16x2(ru[j]);
-            f0 += rr.x;
-            f1 += rr.y;
-            packed[j] = pack_bf16x2(f0, f1);
-            packed_relu[j] = pack_bf16x2(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
+            v[2 * j] += rr.x;
+            v[2 * j + 1] += rr.y;
+            packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
-          // ---- staging slot handshake
-          const int slot = static_cast<int>(chunk_counter % static_cast<uint32_t>(slots));
-          if (store_leader) {
-            if (slots >= 4) tma_store_wait_read<3>();
-            else if (slots == 2) tma_store_wait_read<1>();
-            else tma_store_wait_read<0>();
+          // ---- staging: two slots alternate.  Slot (c & 1) was last read by the TMA store of chunk
+          //      c-2, whose completion the store leader awaited before the barrier of chunk c-1, so
+          //      one block barrier per chunk suffices.  (With a relu copy and only two staging
+          //      buffers there is a single slot: wait for the previous store first.)
+          const int slot = slots >= 2 ? static_cast<int>(chunk_counter & 1u) : 0;
+          if (slots < 2) {
+            if (store_leader) tma_store_wait_read<0>();
+            named_bar_sync(1, kEpiThreads);
           }
-          named_bar_sync(1, kEpiThreads);
           const uint32_t buf0 = smem_base + Plan::kCOff + (slot * bufs_per_chunk) * kStagingBytes;
           const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
 #pragma unroll
@@ -318,12 +368,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               const uint32_t addr = buf0 + kStagingBytes + rowoff +
                                     (static_cast<uint32_t>((half * 4 + j) ^ (row & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                           "r"(packed_relu[4 * j]), "r"(packed_relu[4 * j + 1]),
-                           "r"(packed_relu[4 * j + 2]), "r"(packed_relu[4 * j + 3])
+                           "r"(pack_bf16x2(fmaxf(v[8 * j + 0], 0.f), fmaxf(v[8 * j + 1], 0.f))),
+                           "r"(pack_bf16x2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f))),
+                           "r"(pack_bf16x2(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f))),
+                           "r"(pack_bf16x2(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f)))
                            : "memory");
             }
           }
           fence_proxy_async_smem();
+          if (slots >= 2 && store_leader) tma_store_wait_read<0>();  // store of chunk c-1 has read its slot
           named_bar_sync(1, kEpiThreads);
           if (store_leader) {
             tma_store_4d(&p.out_map, buf0, n0 + c * 64, x0, y0, tb);
@@ -337,10 +390,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TmemCols<BLOCK_N>::value);
+    if constexpr (PAIR) tmem_dealloc_cg2(tmem_base, TmemCols<BLOCK_N>::value);
+    else tmem_dealloc(tmem_base, TmemCols<BLOCK_N>::value);
   }
 }
 
@@ -367,10 +421,10 @@ static int encode_view_map(CUtensorMap* map, const odb_view& v, int box_c, int b
                       strides, box, estr, swz);
 }
 
-template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD>
-static int launch_instance(const ConvGemmParams& p, int grid, cudaStream_t stream) {
-  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, STAGES, NSTAGING, HEAD>;
+template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR>
+static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_t stream) {
+  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, STAGES, NSTAGING, HEAD, PAIR>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -378,8 +432,28 @@ static int launch_instance(const ConvGemmParams& p, int grid, cudaStream_t strea
     if (e != cudaSuccess) return fail_cuda(e, "conv_gemm: cudaFuncSetAttribute");
     configured = true;
   }
-  kernel<<<grid, kNumThreads, Plan::kTotal, stream>>>(p);
+  const int sms = num_sms();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    const long long pairs = units < sms / 2 ? units : sms / 2;
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3((unsigned)(units < sms ? units : sms));
+  }
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Plan::kTotal;
+  cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
   count_launch();
+  if (e != cudaSuccess) return fail_cuda(e, "conv_gemm: launch");
   return check_launch("conv_gemm");
 }
 
@@ -444,6 +518,12 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
     return fail(ODB_ERR_INVALID, "conv_gemm: unsupported block_n");
   p.tiles_n = N / block_n;
   if (m_tiles * p.tiles_n > 0x7fffffffLL) return fail(ODB_ERR_INVALID, "conv_gemm: too many tiles");
+  // CTA pairs (cta_group::2): explicit request, or automatically when the problem fills the chip
+  bool pair = false;
+  if (d->cta_pair == 1) pair = true;
+  else if (d->cta_pair == 0) pair = (block_n == 256 && !head && m_tiles * p.tiles_n >= 2LL * num_sms());
+  if (pair && (block_n != 256 || head))
+    return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: cta_pair needs block_n == 256 and no head tail");
 
   p.num_taps = d->num_taps;
   p.kb_per_tap = (C + kKBlock - 1) / kKBlock;
@@ -463,7 +543,7 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     if ((K * 2) % 16 != 0) return fail(ODB_ERR_INVALID, "conv_gemm: K must be a multiple of 8");
-    cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)block_n};
+    cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)(pair ? block_n / 2 : block_n)};
     cuuint32_t estr[2] = {1, 1};
     rc = encode_tiled(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->weight),
                       dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -501,14 +581,14 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   p.head_out = d->head_out;
 
   const long long total = m_tiles * p.tiles_n;
-  const int grid = (int)(total < num_sms() ? total : num_sms());
+  if (pair) return launch_instance<256, 6, 2, false, true>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
   switch (block_n) {
-    case 256: return launch_instance<256, 4, 2, false>(p, grid, stream);
-    case 128: return launch_instance<128, 5, 4, false>(p, grid, stream);
-    case 64: return launch_instance<64, 6, 4, false>(p, grid, stream);
+    case 256: return launch_instance<256, 4, 2, false, false>(p, total, stream);
+    case 128: return launch_instance<128, 5, 4, false, false>(p, total, stream);
+    case 64: return launch_instance<64, 6, 4, false, false>(p, total, stream);
     case 32:
       if (!head) return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: block_n 32 only with the head tail");
-      return launch_instance<32, 8, 0, true>(p, grid, stream);
+      return launch_instance<32, 8, 0, true, false>(p, total, stream);
   }
   return fail(ODB_ERR_INVALID, "conv_gemm: unreachable");
 }

@@ -85,6 +85,7 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
               out: Optional[torch.Tensor], *, bias: Optional[torch.Tensor] = None,
               bias_per_image: bool = False, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None, block_n: int = 0,
+              cta_pair: int = 0,
               head: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, bool]] = None,
               out_extent: Optional[Tuple[int, int, int]] = None) -> None:
     """taps: (view index, dx, dy).  head = (w[head_c,32] f32, b[head_c] f32, out[B,head_c,H,W] f32, relu)."""
@@ -120,6 +121,7 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
     if tile is not None:
         d.tile_w, d.tile_h = tile
     d.block_n = block_n
+    d.cta_pair = cta_pair
     if head is not None:
         hw, hb, hout, hrelu = head
         _need(hw, torch.float32, "head_w"); _need(hb, torch.float32, "head_b"); _need(hout, torch.float32, "head_out")

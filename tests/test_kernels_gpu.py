@@ -59,6 +59,42 @@ def test_linear_plain(m, k, n, block_n):
     check(out, x.float() @ w.float().t(), f"linear {m}x{k}x{n} bn{block_n}")
 
 
+@pytest.mark.parametrize("m,k,n", [(300, 64, 256), (1000, 768, 768), (577 * 32, 768, 2304), (5000, 3072, 768),
+                                   (128 * 3, 256, 512)])
+def test_linear_cta_pair(m, k, n):
+    """tcgen05 cta_group::2: two CTAs share one 256-row UMMA tile (odd tile counts included)."""
+    o = ops()
+    x = rnd(m, k).to(torch.bfloat16)
+    w = rnd(n, k, scale=k ** -0.5).to(torch.bfloat16)
+    bias = rnd(n)
+    res = rnd(m, n, seed=11).to(torch.bfloat16)
+    out = torch.full((m, n), float("nan"), device=dev(), dtype=torch.bfloat16)
+    o.linear(x, w, out, bias=bias, residual=res, act=o.ACT_GELU, block_n=256, cta_pair=1)
+    torch.cuda.synchronize()
+    check(out, F.gelu(x.float() @ w.float().t() + bias) + res.float(), f"pair linear {m}x{k}x{n}")
+    single = torch.empty_like(out)
+    o.linear(x, w, single, bias=bias, residual=res, act=o.ACT_GELU, block_n=256, cta_pair=-1)
+    torch.cuda.synchronize()
+    assert torch.equal(out, single)          # same accumulation order => bit-identical to the 1-CTA kernel
+
+
+@pytest.mark.parametrize("b,h,w_", [(2, 48, 48), (3, 24, 24), (1, 96, 96)])
+def test_conv3x3_cta_pair(b, h, w_):
+    o = ops()
+    c = 256
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    skip = rnd(b, h, w_, c, seed=5).to(torch.bfloat16)
+    w = rnd(c, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    bias = rnd(c)
+    out = torch.full((b, h, w_, c), float("nan"), device=dev(), dtype=torch.bfloat16)
+    out2 = torch.empty_like(out)
+    o.conv3x3(x, o.pack_conv_weight(w), out, bias=bias, residual=skip, out2=out2, block_n=256, cta_pair=1)
+    torch.cuda.synchronize()
+    ref = conv_ref(x, w) + bias + skip.float()
+    check(out, ref, "pair conv3x3 residual")
+    check(out2, F.relu(ref), "pair conv3x3 relu copy")
+
+
 @pytest.mark.parametrize("act", [0, 1, 2])
 def test_linear_epilogue(act):
     o = ops()

@@ -3,10 +3,14 @@
 /root/reference does not exist there; the checker is the oracle (pinned against the unmodified
 reference in the build container) plus the committed golden vectors.
 
-Tolerances (rel-L2 = ||a-b|| / ||b||):
-  * vs the bf16-rounding oracle (same rounding points as the kernels)  : <= BF16_TOL per tap
-  * vs the fp32 oracle / reference golden                               : <= DRIFT_FACTOR x the drift the
-    bf16-rounding oracle itself shows against fp32 (stock bf16 drifts 2-3e-2 on this net)
+Tolerances (rel-L2 = ||a-b|| / ||b||), see DESIGN.md §4:
+  * first kernels of the chain (stem conv, stem pool) vs the bf16-rounding oracle: <= 2e-4 — the kernels are
+    exact up to rounding flips (tests/test_kernels_gpu.py shows the same for every kernel in isolation);
+  * deeper taps: two bf16 pipelines that differ by ANY fp32 summation order de-correlate: a perturbation e
+    before a bf16 rounding (ulp u) becomes sqrt(e*u) after it, so the mismatch converges towards the size of
+    independent rounding noise within a few layers.  The meaningful bounds are therefore relative to the
+    drift D the bf16-rounding oracle itself shows against fp32:  mismatch(kernel, bf16-oracle) <= D and
+    drift(kernel, fp32 oracle / reference golden) <= DRIFT_FACTOR x D.
 """
 from pathlib import Path
 
@@ -16,7 +20,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = Path(__file__).parent / "golden"
-BF16_TOL = 4e-3
+FIRST_KERNELS_TOL = 2e-4
 DRIFT_FACTOR = 1.5
 TAPS = ["layer_1", "layer_2", "tokens_8", "tokens_11", "layer_3", "layer_4", "layer_1_rn", "layer_2_rn",
         "layer_3_rn", "layer_4_rn", "path_4", "path_3", "path_2", "path_1"]
@@ -66,11 +70,13 @@ def test_taps_match_bf16_rounding_oracle(setup, c):
     report = []
     for k in TAPS:
         e16 = rel(r["taps"][k], r["t16"][k])
-        report.append(f"{k}: vs bf16-oracle {e16:.2e}")
+        report.append(f"{k}: vs bf16-oracle {e16:.2e} (oracle drift vs fp32 {rel(r['t16'][k], r['t32'][k]):.2e})")
     print("\n".join(report))
+    for k in ("stem_conv", "stem_pool"):
+        assert rel(r["taps"][k], r["t16"][k]) <= FIRST_KERNELS_TOL, (k, rel(r["taps"][k], r["t16"][k]))
     for k in TAPS:
-        assert rel(r["taps"][k], r["t16"][k]) <= BF16_TOL, (k, report)
-    assert rel(r["y"], r["y16"]) <= 2 * BF16_TOL, ("output", rel(r["y"], r["y16"]))
+        assert rel(r["taps"][k], r["t16"][k]) <= rel(r["t16"][k], r["t32"][k]), (k, report)
+    assert rel(r["y"], r["y16"]) <= rel(r["y16"], r["y32"]), ("output", rel(r["y"], r["y16"]))
 
 
 @pytest.mark.parametrize("c", [1, 3])
