@@ -194,13 +194,20 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
     coef[c + ch] = k.b;
   }
   __syncthreads();
-  const long long total = (long long)hw * octets;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int oct = (int)(i % octets);
-    const long long off = ((long long)b * hw) * c + i * 8;
+  // 32-bit indexing inside one image (hw * c < 2^31); c is a power of two on this path
+  const unsigned total = (unsigned)hw * (unsigned)octets;
+  const unsigned omask = (unsigned)octets - 1u;
+  const bool pow2 = (octets & (octets - 1)) == 0;
+  const bf16* xb = x + ((long long)b * hw) * c;
+  const bf16* rb = res ? res + ((long long)b * hw) * c : nullptr;
+  bf16* yb = y + ((long long)b * hw) * c;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned oct = pow2 ? (i & omask) : (i % (unsigned)octets);
+    const unsigned off = i * 8u;
     float v[8], o[8];
-    load8(x + off, v);
+    load8(xb + off, v);
+    float r[8];
+    if (rb != nullptr) load8(rb + off, r);
     const float4 a0 = *reinterpret_cast<const float4*>(coef + oct * 8);
     const float4 a1 = *reinterpret_cast<const float4*>(coef + oct * 8 + 4);
     const float4 s0 = *reinterpret_cast<const float4*>(coef + c + oct * 8);
@@ -209,9 +216,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
     const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], a[j], sh[j]);
-    if (res != nullptr) {
-      float r[8];
-      load8(res + off, r);
+    if (rb != nullptr) {
       if (res_norm) {
         const float4 r0 = *reinterpret_cast<const float4*>(coef + 2 * c + oct * 8);
         const float4 r1 = *reinterpret_cast<const float4*>(coef + 2 * c + oct * 8 + 4);
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
     }
-    store8(y + off, o);
+    store8(yb + off, o);
   }
 }
 
@@ -246,31 +251,34 @@ __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
     coef[c + ch] = k.b;
   }
   __syncthreads();
-  const long long total = (long long)oh * ow * octets;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int oct = (int)(i % octets);
-    const long long pix = i / octets;
-    const int ox = (int)(pix % ow), oy = (int)(pix / ow);
+  const unsigned total = (unsigned)oh * (unsigned)ow * (unsigned)octets;
+  const bf16* xb = x + (long long)b * h * w * c;
+  bf16* yb = y + (long long)b * oh * ow * c;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned oct = i % (unsigned)octets;
+    const unsigned pix = i / (unsigned)octets;
+    const int ox = (int)(pix % (unsigned)ow), oy = (int)(pix / (unsigned)ow);
     float a[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] = coef[oct * 8 + j]; sh[j] = coef[c + oct * 8 + j]; }
     float m[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = 0.f;  // relu output is >= 0, so 0 is the identity of max
+#pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int iy = 2 * oy + dy;
       if (iy >= h) continue;
+#pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const int ix = 2 * ox + dx;
         if (ix >= w) continue;
         float v[8];
-        load8(x + (((long long)b * h + iy) * w + ix) * c + oct * 8, v);
+        load8(xb + ((unsigned)iy * (unsigned)w + (unsigned)ix) * (unsigned)c + oct * 8, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(v[j], a[j], sh[j]));  // relu folded into max(0,.)
       }
     }
-    store8(y + (((long long)b * oh + oy) * ow + ox) * c + oct * 8, m);
+    store8(yb + pix * (unsigned)c + oct * 8, m);
   }
 }
 
@@ -281,14 +289,13 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
                                                           int w, int kpad) {
   const int oh = h / 2, ow = w / 2;
   const int groups8 = kpad >> 3;
-  const long long total = (long long)b * oh * ow * groups8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups8);
-    const long long pix = i / groups8;
-    const int ox = (int)(pix % ow);
-    const int oy = (int)((pix / ow) % oh);
-    const int bi = (int)(pix / ((long long)ow * oh));
+  const int oy = blockIdx.x % oh, bi = blockIdx.x / oh;   // one block per output row
+  const float* xb = x + (long long)bi * 3 * h * w;
+  bf16* crow = cols + ((long long)bi * oh + oy) * ow * kpad;
+  const int total = ow * groups8;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int g = i % groups8;
+    const int ox = i / groups8;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -299,12 +306,11 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
         const int kx = (col / 3) % 7;
         const int ky = col / 21;
         const int iy = 2 * oy + ky - 2, ix = 2 * ox + kx - 2;
-        if (iy >= 0 && iy < h && ix >= 0 && ix < w)
-          val = __ldg(x + (((long long)bi * 3 + ch) * h + iy) * w + ix);
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = __ldg(xb + (ch * h + iy) * w + ix);
       }
       v[j] = val;
     }
-    store8(cols + pix * kpad + g * 8, v);
+    store8(crow + i * 8, v);
   }
 }
 
@@ -314,37 +320,40 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
                                                              bf16* __restrict__ out,
                                                              bf16* __restrict__ out_relu, int b,
                                                              int h, int w, int c) {
+  // grid: (column chunks, output row, image) — all index math is 32-bit and row-uniform
   const int octets = c >> 3;
   const int oh = 2 * h, ow = 2 * w;
+  const int oy = blockIdx.y, bi = blockIdx.z;
   const float sy = (float)(h - 1) / (float)(oh - 1), sx = (float)(w - 1) / (float)(ow - 1);
-  const long long total = (long long)b * oh * ow * octets;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int oct = (int)(i % octets);
-    const long long pix = i / octets;
-    const int ox = (int)(pix % ow);
-    const int oy = (int)((pix / ow) % oh);
-    const int bi = (int)(pix / ((long long)ow * oh));
-    const float fy = oy * sy, fx = ox * sx;
-    const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float wy = fy - (float)y0, wx = fx - (float)x0;
-    const bf16* zb = z + (long long)bi * h * w * c + oct * 8;
-    float a[8], bq[8], cc[8], d[8], o[8];
-    load8(zb + ((long long)y0 * w + x0) * c, a);
-    load8(zb + ((long long)y0 * w + x1) * c, bq);
-    load8(zb + ((long long)y1 * w + x0) * c, cc);
-    load8(zb + ((long long)y1 * w + x1) * c, d);
+  const float fy = oy * sy;
+  const int y0 = min((int)fy, h - 1);
+  const int y1 = min(y0 + 1, h - 1);
+  const float wy = fy - (float)y0;
+  const bf16* z0 = z + ((long long)bi * h + y0) * w * c;
+  const bf16* z1 = z + ((long long)bi * h + y1) * w * c;
+  const long long orow = ((long long)bi * oh + oy) * ow * c;
+  const int total = ow * octets;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int oct = i % octets;
+    const int ox = i / octets;
+    const float fx = ox * sx;
+    const int x0 = min((int)fx, w - 1);
+    const int x1 = min(x0 + 1, w - 1);
+    const float wx = fx - (float)x0;
+    float a[8], bq[8], cc[8], d[8], o[8], r[8];
+    load8(z0 + x0 * c + oct * 8, a);
+    load8(z0 + x1 * c + oct * 8, bq);
+    load8(z1 + x0 * c + oct * 8, cc);
+    load8(z1 + x1 * c + oct * 8, d);
+    const long long off = orow + i * 8;
+    if (res != nullptr) load8(res + off, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float top = a[j] + (bq[j] - a[j]) * wx;
       const float bot = cc[j] + (d[j] - cc[j]) * wx;
       o[j] = top + (bot - top) * wy;
     }
-    const long long off = pix * c + oct * 8;
     if (res != nullptr) {
-      float r[8];
-      load8(res + off, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += r[j];
     }
@@ -503,9 +512,7 @@ extern "C" int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !cols || b < 1 || h < 2 || w < 2 || (h & 1) || (w & 1) || kpad < 152 || kpad % 8)
     return fail(ODB_ERR_INVALID, "stem_im2col: bad argument");
-  const long long total = (long long)b * (h / 2) * (w / 2) * (kpad / 8);
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, static_cast<bf16*>(cols), b, h, w,
-                                                               kpad);
+  stem_im2col_kernel<<<b * (h / 2), 256, 0, stream>>>(x, static_cast<bf16*>(cols), b, h, w, kpad);
   count_launch();
   return check_launch("stem_im2col");
 }
@@ -515,8 +522,10 @@ extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, voi
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!z || !out || b < 1 || h < 1 || w < 1 || c < 8 || c % 8)
     return fail(ODB_ERR_INVALID, "upsample2x_add: bad argument");
-  const long long total = (long long)b * 4 * h * w * (c / 8);
-  upsample2x_add_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
+  if (2 * h > 65535 || b > 65535) return fail(ODB_ERR_INVALID, "upsample2x_add: extent too large");
+  const int per_row = 2 * w * (c / 8);
+  dim3 grid((per_row + 255) / 256, 2 * h, b);
+  upsample2x_add_kernel<<<grid, 256, 0, stream>>>(
       static_cast<const bf16*>(z), static_cast<const bf16*>(res), static_cast<bf16*>(out),
       static_cast<bf16*>(out_relu), b, h, w, c);
   count_launch();
