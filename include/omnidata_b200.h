@@ -92,9 +92,17 @@ typedef struct odb_conv_gemm_desc {
   int32_t head_c;
   int32_t head_relu;
   float* head_out;
+  /* Fused GroupNorm statistics (timm GroupNormAct after every StdConv2dSame): when gn_partial != NULL
+   * each epilogue warp also writes, for the bf16 values it stores, the per-group (sum, sum of squares)
+   * of its 32 rows to  gn_partial[b][ty*tiles_x+tx][quadrant 0..3][group][2]  (fp32, every entry is
+   * written exactly once: no atomics, deterministic).  odb_groupnorm_finalize reduces them. */
+  float* gn_partial;
+  int32_t gn_groups;
 } odb_conv_gemm_desc;
 
 int odb_conv_gemm(const odb_conv_gemm_desc* desc, void* stream);
+/* The tiling odb_conv_gemm will use for `desc`: out4 = {tiles_x, tiles_y, block_n, cta_pair}. */
+int odb_conv_gemm_plan(const odb_conv_gemm_desc* desc, int32_t* out4);
 
 /* LayerNorm over the last dim (timm Block.norm1/norm2, eps 1e-6): y = (x-mean)/sqrt(var+eps)*g + b.
  * x, y bf16 [rows][cols] (cols multiple of 256, <= 1024); gamma/beta fp32. */
@@ -114,6 +122,12 @@ int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t
 int64_t odb_groupnorm_scratch_bytes(int32_t b, int32_t hw, int32_t c, int32_t groups);
 int odb_groupnorm_stats(const void* x, float* stats, void* scratch, int64_t scratch_bytes, int32_t b,
                         int32_t hw, int32_t c, int32_t groups, float eps, void* stream);
+
+/* Reduce the partial sums written by odb_conv_gemm (gn_partial) in a fixed order with fp64
+ * combination: stats[b][g] = (mean, 1/sqrt(var + eps)); rows_per_image = tiles_x * tiles_y * 4,
+ * count = pixels * channels_per_group of one group. */
+int odb_groupnorm_finalize(const float* partial, float* stats, int32_t b, int32_t rows_per_image,
+                           int32_t groups, double count, float eps, void* stream);
 
 /* GroupNorm apply (+ optional shortcut, + optional ReLU), timm Bottleneck.forward:
  *   y = relu?( gn(x; stats, gamma, beta) + shortcut )

@@ -52,11 +52,16 @@ class ConvGemmDesc(C.Structure):
         ("head_c", C.c_int32),
         ("head_relu", C.c_int32),
         ("head_out", C.c_void_p),
+        ("gn_partial", C.c_void_p),
+        ("gn_groups", C.c_int32),
     ]
 
 
 _SIGNATURES = {
     "odb_conv_gemm": (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p]),
+    "odb_conv_gemm_plan": (C.c_int, [C.POINTER(ConvGemmDesc), C.POINTER(C.c_int32)]),
+    "odb_groupnorm_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                         C.c_float, C.c_void_p]),
     "odb_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                 C.c_float, C.c_void_p]),
     "odb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,

@@ -50,7 +50,62 @@ struct ConvGemmParams {
   int head_c;
   int head_relu;
   float* head_out;
+  float* gn_partial;   // optional GroupNorm partial sums, [b][tiles_y*tiles_x][4 quadrants][groups][2]
+  int gn_cpg;          // channels per group (2..32, power of two)
+  int gn_groups;
 };
+
+// ---- GroupNorm partial statistics of one epilogue warp (32 rows x 32 columns of a tile):
+// per-thread group sums over its row, then a transposing butterfly over the 32 lanes: V values are
+// reduced with V-1 + (5 - log2 V) shuffles in a FIXED order (deterministic), value i ending on the
+// lanes whose top log2(V) bits equal i.
+template <int CPG>
+ODB_DEVINL void gn_row_group_sums(const float* v, float* vals) {
+  constexpr int NG = 32 / CPG;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      const float x = v[g * CPG + j];
+      sm += x;
+      sq = fmaf(x, x, sq);
+    }
+    vals[2 * g] = sm;
+    vals[2 * g + 1] = sq;
+  }
+}
+template <int V>
+ODB_DEVINL void gn_lane_butterfly(float* vals, int lane) {
+  int n = V;
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    if (n > 1) {
+      const int half = n >> 1;
+      const bool upper = (lane & sft) != 0;
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        if (i < half) {
+          const float send = upper ? vals[i] : vals[i + half];
+          const float keep = upper ? vals[i + half] : vals[i];
+          vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+        }
+      }
+      n = half;
+    } else {
+      vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], sft);
+    }
+  }
+}
+template <int CPG>
+ODB_DEVINL void gn_warp_partials(const float* v, int lane, float* dst /* [groups*2] at group gidx0 */) {
+  constexpr int V = 2 * (32 / CPG);
+  constexpr int LOGV = V == 32 ? 5 : V == 16 ? 4 : V == 8 ? 3 : V == 4 ? 2 : 1;
+  float vals[V];
+  gn_row_group_sums<CPG>(v, vals);
+  gn_lane_butterfly<V>(vals, lane);
+  if ((lane & ((1 << (5 - LOGV)) - 1)) == 0) dst[lane >> (5 - LOGV)] = vals[0];
+}
 
 template <int BLOCK_N, int STAGES, int NSTAGING, bool PAIR>
 struct SmemPlan {
@@ -343,6 +398,27 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             v[2 * j + 1] += rr.y;
             packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
+          // ---- fused GroupNorm statistics over the bf16-rounded values this warp is about to store
+          if (p.gn_partial != nullptr) {
+            float rq[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 t2 = unpack_bf16x2(packed[j]);
+              rq[2 * j] = valid ? t2.x : 0.f;
+              rq[2 * j + 1] = valid ? t2.y : 0.f;
+            }
+            if (tb < p.out_b) {
+              const int cpg = p.gn_cpg;
+              float* dst = p.gn_partial +
+                           ((((long long)tb * (p.tiles_x * p.tiles_y) + (ty * p.tiles_x + tx)) * 4 + quad) *
+                                p.gn_groups + (n0 + c * 64 + cofs) / cpg) * 2;
+              if (cpg == 2) gn_warp_partials<2>(rq, lane, dst);
+              else if (cpg == 4) gn_warp_partials<4>(rq, lane, dst);
+              else if (cpg == 8) gn_warp_partials<8>(rq, lane, dst);
+              else if (cpg == 16) gn_warp_partials<16>(rq, lane, dst);
+              else gn_warp_partials<32>(rq, lane, dst);
+            }
+          }
           // ---- staging: two slots alternate.  Slot (c & 1) was last read by the TMA store of chunk
           //      c-2, whose completion the store leader awaited before the barrier of chunk c-1, so
           //      one block barrier per chunk suffices.  (With a relu copy and only two staging
@@ -461,8 +537,13 @@ static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_
 
 using namespace odb;
 
-extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+struct HostPlan {
+  int tw, th, tiles_x, tiles_y, block_n;
+  bool pair, head;
+  long long m_tiles;
+};
+
+static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
   if (d == nullptr) return fail(ODB_ERR_INVALID, "conv_gemm: null descriptor");
   if (d->num_views < 1 || d->num_views > ODB_MAX_VIEWS || d->num_taps < 1 ||
       d->num_taps > ODB_MAX_TAPS)
@@ -480,14 +561,7 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
       return fail(ODB_ERR_INVALID, "conv_gemm: head tail needs n == 32, head_w, head_b");
   } else {
     if (N % 64 != 0) return fail(ODB_ERR_INVALID, "conv_gemm: n must be a multiple of 64");
-    if (d->out.ptr == nullptr) return fail(ODB_ERR_INVALID, "conv_gemm: null output");
   }
-  if (d->weight == nullptr || (reinterpret_cast<uintptr_t>(d->weight) & 15u) != 0)
-    return fail(ODB_ERR_INVALID, "conv_gemm: weight must be non-null and 16-byte aligned");
-  const long long K = (long long)d->num_taps * C;
-
-  ConvGemmParams p;
-  memset(&p, 0, sizeof(p));
   const int ow = d->out.w, oh = d->out.h, ob = d->out.b;
   if (ow < 1 || oh < 1 || ob < 1) return fail(ODB_ERR_INVALID, "conv_gemm: empty output extent");
   int tw = d->tile_w, th = d->tile_h;
@@ -500,30 +574,64 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   }
   if (tw * th > kTileRows || tw > 256 || th > 256)
     return fail(ODB_ERR_INVALID, "conv_gemm: tile_w * tile_h must be <= 128");
-  p.tile_w = tw; p.tile_h = th;
-  p.tiles_x = (ow + tw - 1) / tw;
-  p.tiles_y = (oh + th - 1) / th;
-  p.tiles_b = ob;
-  p.out_w = ow; p.out_h = oh; p.out_b = ob; p.n_total = N;
-
+  hp->tw = tw; hp->th = th;
+  hp->tiles_x = (ow + tw - 1) / tw;
+  hp->tiles_y = (oh + th - 1) / th;
+  hp->m_tiles = (long long)hp->tiles_x * hp->tiles_y * ob;
   int block_n = d->block_n;
   if (head) block_n = 32;
-  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_b;
   if (block_n == 0) {
     block_n = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
     const int sms = num_sms();
-    while (block_n > 64 && m_tiles * (N / block_n) < sms) block_n /= 2;
+    while (block_n > 64 && hp->m_tiles * (N / block_n) < sms) block_n /= 2;
   }
   if (!(block_n == 256 || block_n == 128 || block_n == 64 || block_n == 32) || N % block_n != 0)
     return fail(ODB_ERR_INVALID, "conv_gemm: unsupported block_n");
-  p.tiles_n = N / block_n;
-  if (m_tiles * p.tiles_n > 0x7fffffffLL) return fail(ODB_ERR_INVALID, "conv_gemm: too many tiles");
+  if (hp->m_tiles * (N / block_n) > 0x7fffffffLL)
+    return fail(ODB_ERR_INVALID, "conv_gemm: too many tiles");
   // CTA pairs (cta_group::2): explicit request, or automatically when the problem fills the chip
   bool pair = false;
   if (d->cta_pair == 1) pair = true;
-  else if (d->cta_pair == 0) pair = (block_n == 256 && !head && m_tiles * p.tiles_n >= 2LL * num_sms());
+  else if (d->cta_pair == 0)
+    pair = (block_n == 256 && !head && hp->m_tiles * (N / block_n) >= 2LL * num_sms());
   if (pair && (block_n != 256 || head))
     return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: cta_pair needs block_n == 256 and no head tail");
+  hp->block_n = block_n; hp->pair = pair; hp->head = head;
+  return ODB_OK;
+}
+
+extern "C" int odb_conv_gemm_plan(const odb_conv_gemm_desc* d, int32_t* out4) {
+  HostPlan hp;
+  int rc = make_plan(d, &hp);
+  if (rc) return rc;
+  if (out4) { out4[0] = hp.tiles_x; out4[1] = hp.tiles_y; out4[2] = hp.block_n; out4[3] = hp.pair ? 1 : 0; }
+  return ODB_OK;
+}
+
+extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  HostPlan hp;
+  int rc = make_plan(d, &hp);
+  if (rc) return rc;
+  const bool head = hp.head, pair = hp.pair;
+  const int block_n = hp.block_n, tw = hp.tw, th = hp.th;
+  const int C = d->views[0].c;
+  const int N = d->n;
+  if (!head && d->out.ptr == nullptr) return fail(ODB_ERR_INVALID, "conv_gemm: null output");
+  if (d->weight == nullptr || (reinterpret_cast<uintptr_t>(d->weight) & 15u) != 0)
+    return fail(ODB_ERR_INVALID, "conv_gemm: weight must be non-null and 16-byte aligned");
+  const long long K = (long long)d->num_taps * C;
+
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int ow = d->out.w, oh = d->out.h, ob = d->out.b;
+  p.tile_w = tw; p.tile_h = th;
+  p.tiles_x = hp.tiles_x;
+  p.tiles_y = hp.tiles_y;
+  p.tiles_b = ob;
+  p.out_w = ow; p.out_h = oh; p.out_b = ob; p.n_total = N;
+  const long long m_tiles = hp.m_tiles;
+  p.tiles_n = N / block_n;
 
   p.num_taps = d->num_taps;
   p.kb_per_tap = (C + kKBlock - 1) / kKBlock;
@@ -532,7 +640,6 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
     p.tap_dx[t] = d->tap_dx[t];
     p.tap_dy[t] = d->tap_dy[t];
   }
-  int rc;
   for (int v = 0; v < ODB_MAX_VIEWS; ++v) {
     // unused slots alias view 0 so that prefetch.tensormap always sees a valid descriptor
     const odb_view& src = d->views[v < d->num_views ? v : 0];
@@ -579,6 +686,15 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   p.act = d->act;
   p.head_w = d->head_w; p.head_b = d->head_b; p.head_c = d->head_c; p.head_relu = d->head_relu;
   p.head_out = d->head_out;
+  if (d->gn_partial != nullptr) {
+    const int g = d->gn_groups;
+    const int cpg = g > 0 ? N / g : 0;
+    if (head || g < 1 || N % g != 0 || !(cpg == 2 || cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32))
+      return fail(ODB_ERR_INVALID, "conv_gemm: gn_partial needs n / gn_groups in {2,4,8,16,32}");
+    p.gn_partial = d->gn_partial;
+    p.gn_cpg = cpg;
+    p.gn_groups = g;
+  }
 
   const long long total = m_tiles * p.tiles_n;
   if (pair) return launch_instance<256, 6, 2, false, true>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);

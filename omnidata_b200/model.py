@@ -345,16 +345,24 @@ class DPTDepthModel(nn.Module):
             gn_scratch = ws.bufs["gn_scratch"] = torch.zeros(4 << 20, dtype=torch.uint8, device=x.device)
         stat_i = iter(range(n_gn))
 
-        def gn_stats(t):
+        def gn_stats(t):                                  # standalone statistics pass (stem only)
             st = stats_pool[next(stat_i)]
             ops.groupnorm_stats(t, st, scratch=gn_scratch)
             return st
 
+        # fused statistics: the conv epilogue writes per-warp partial sums here (largest layer:
+        # stage 0 at 96x96 -> 72 tiles x 4 quadrants x 32 groups x 2 per image)
+        gn_part = buf("gn_partial", (B * ((H // 4) * (W // 4) // 32 + 64) * 4 * 32 * 2,), torch.float32)
+
+        def gn_fused():
+            return (gn_part, stats_pool[next(stat_i)])
+
         cols = buf("stem_cols", (B * h2 * w2, 160))
         ops.stem_im2col(x, cols)
         s0 = buf("stem_conv", (B, h2, w2, 64))
-        ops.linear(cols, pk["stem_w"], s0.view(-1, 64))
-        st = gn_stats(s0)
+        gs = gn_fused()
+        ops.conv1x1(cols.view(B, h2, w2, 160), pk["stem_w"], s0, gn_stats=gs)
+        st = gs[1]
         t = buf("stem_pool", (B, h2 // 2, w2 // 2, 64))
         ops.stem_gn_relu_maxpool(s0, st, pk["stem_g"], pk["stem_b"], t)
         if taps is not None:
@@ -368,25 +376,29 @@ class DPTDepthModel(nn.Module):
             shortcut, sc_stats = t, None
             if b == 0:
                 d = buf(tag + "_ds", (B, ho, wo, cout))
-                ops.conv1x1(t[:, ::stride, ::stride, :] if stride > 1 else t, e["wd"], d)
-                sc_stats = gn_stats(d)
+                gs = gn_fused()
+                ops.conv1x1(t[:, ::stride, ::stride, :] if stride > 1 else t, e["wd"], d, gn_stats=gs)
+                sc_stats = gs[1]
                 shortcut = d
             y1 = buf(tag + "_y1", (B, hh, ww, mid))
-            ops.conv1x1(t, e["w1"], y1)
-            st1 = gn_stats(y1)
+            gs = gn_fused()
+            ops.conv1x1(t, e["w1"], y1, gn_stats=gs)
+            st1 = gs[1]
             a1 = buf(tag + "_a1", (B, hh, ww, mid))
             ops.groupnorm_apply(y1, st1, e["g1"], e["b1"], a1, relu=True)
             y2 = buf(tag + "_y2", (B, ho, wo, mid))
+            gs = gn_fused()
             if stride == 1:
-                ops.conv3x3(a1, e["w2"], y2)
+                ops.conv3x3(a1, e["w2"], y2, gn_stats=gs)
             else:
-                ops.conv3x3_s2(a1, e["w2"], y2, "same")
-            st2 = gn_stats(y2)
+                ops.conv3x3_s2(a1, e["w2"], y2, "same", gn_stats=gs)
+            st2 = gs[1]
             a2 = buf(tag + "_a2", (B, ho, wo, mid))
             ops.groupnorm_apply(y2, st2, e["g2"], e["b2"], a2, relu=True)
             y3 = buf(tag + "_y3", (B, ho, wo, cout))
-            ops.conv1x1(a2, e["w3"], y3)
-            st3 = gn_stats(y3)
+            gs = gn_fused()
+            ops.conv1x1(a2, e["w3"], y3, gn_stats=gs)
+            st3 = gs[1]
             out = buf(tag + "_out", (B, ho, wo, cout))
             if b == 0:
                 ops.groupnorm_apply(y3, st3, e["g3"], e["b3"], out, relu=True, res=shortcut,

@@ -85,7 +85,8 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
               out: Optional[torch.Tensor], *, bias: Optional[torch.Tensor] = None,
               bias_per_image: bool = False, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None, block_n: int = 0,
-              cta_pair: int = 0,
+              cta_pair: int = 0, gn_stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+              gn_groups: int = 32, gn_eps: float = 1e-5,
               head: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, bool]] = None,
               out_extent: Optional[Tuple[int, int, int]] = None) -> None:
     """taps: (view index, dx, dy).  head = (w[head_c,32] f32, b[head_c] f32, out[B,head_c,H,W] f32, relu)."""
@@ -132,7 +133,23 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
         d.out = View(None, 32, w, h, b, 0, 0, 0)
     rows = d.out.w * d.out.h * d.out.b
     info = {"m": rows, "n": d.n, "k": d.num_taps * d.views[0].c, "taps": d.num_taps, "w": d.out.w, "h": d.out.h}
+    if gn_stats is None:
+        _call("odb_conv_gemm", info, lib().odb_conv_gemm, C.byref(d), _stream())
+        return
+    # fused GroupNorm statistics: the epilogue writes per-warp partial sums, a tiny kernel reduces them
+    partial, stats = gn_stats
+    _need(partial, torch.float32, "gn partial"); _need(stats, torch.float32, "gn stats")
+    plan = (C.c_int32 * 4)()
+    check(lib().odb_conv_gemm_plan(C.byref(d), plan), "odb_conv_gemm_plan")
+    part_rows = plan[0] * plan[1] * 4
+    if partial.numel() < d.out.b * part_rows * gn_groups * 2:
+        raise _capi.OdbError("conv_gemm: gn partial buffer too small")
+    d.gn_partial = partial.data_ptr()
+    d.gn_groups = gn_groups
     _call("odb_conv_gemm", info, lib().odb_conv_gemm, C.byref(d), _stream())
+    count = float(d.out.w) * float(d.out.h) * (d.n // gn_groups)
+    _call("odb_groupnorm_finalize", {}, lib().odb_groupnorm_finalize, partial.data_ptr(), stats.data_ptr(),
+          d.out.b, part_rows, gn_groups, count, gn_eps, _stream())
 
 
 TAPS_1 = [(0, 0, 0)]

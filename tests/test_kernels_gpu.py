@@ -286,6 +286,36 @@ def test_groupnorm(c, hw):
     check(out, ref.transpose(1, 2), f"groupnorm+identity shortcut c{c}")
 
 
+@pytest.mark.parametrize("b,h,w_,c,n,pair", [(2, 96, 96, 64, 64, 0), (3, 48, 48, 128, 512, 0), (2, 24, 24, 256, 1024, 0),
+                                              (2, 48, 48, 256, 256, 1), (3, 24, 24, 1024, 256, 0)])
+def test_conv_fused_groupnorm_stats(b, h, w_, c, n, pair):
+    """GroupNorm statistics produced by the conv epilogue (+ finalize) == statistics of the stored output."""
+    o = ops()
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    w = rnd(n, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    out = torch.empty((b, h, w_, n), device=dev(), dtype=torch.bfloat16)
+    partial = torch.full((b * 128 * 4 * 32 * 2,), float("nan"), device=dev())
+    stats = torch.full((b, 32, 2), float("nan"), device=dev())
+    o.conv3x3(x, o.pack_conv_weight(w), out, gn_stats=(partial, stats), cta_pair=pair,
+              block_n=256 if pair else 0)
+    torch.cuda.synchronize()
+    check(out, conv_ref(x, w, padding=1), "conv with fused stats")
+    y = out.double().view(b, h * w_, 32, n // 32)
+    mean = y.mean(dim=(1, 3))
+    var = y.var(dim=(1, 3), unbiased=False)
+    assert rel_l2(stats[..., 0], mean) < 1e-5 or float((stats[..., 0].double() - mean).abs().max()) < 1e-6
+    assert rel_l2(stats[..., 1], 1.0 / torch.sqrt(var + 1e-5)) < 1e-5
+    stats2 = torch.empty_like(stats)
+    o.conv3x3(x, o.pack_conv_weight(w), out, gn_stats=(partial, stats2), cta_pair=pair, block_n=256 if pair else 0)
+    torch.cuda.synchronize()
+    assert torch.equal(stats, stats2)                      # deterministic
+    # and it agrees with the standalone statistics kernel
+    stats3 = torch.empty_like(stats)
+    o.groupnorm_stats(out, stats3)
+    torch.cuda.synchronize()
+    assert rel_l2(stats3, stats) < 1e-6
+
+
 def test_stem_path():
     o = ops()
     b, h, w_ = 2, 64, 96
