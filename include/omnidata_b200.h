@@ -110,9 +110,15 @@ int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y,
                   int32_t cols, float eps, void* stream);
 
 /* Fused multi-head attention (timm Attention.forward): qkv bf16 [b][tokens][3][heads][64] as written
- * by the qkv linear; out bf16 [b][tokens][heads*64]; softmax(q k^T * scale) v, fp32 softmax. */
+ * by the qkv linear; out bf16 [b][tokens][heads*64]; softmax(q k^T * scale) v.  tcgen05 kernel:
+ * S and O accumulate in TMEM, exact two-pass fp32 softmax (global row maximum), P rounded to bf16
+ * for the PV product, fp32 row sum of the unrounded P.  tokens <= 640. */
 int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
                   void* stream);
+/* Same contract on the legacy mma.sync path (flash-style online softmax over 64-key chunks); kept
+ * for A/B comparison only. */
+int odb_attention_mma(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
+                      void* stream);
 
 /* GroupNorm statistics (timm GroupNormAct, 32 groups), deterministic (no floating-point atomics):
  * stats fp32 [b][groups][2] = (mean, 1/sqrt(var + eps)) over x bf16 [b][hw][c], biased variance,

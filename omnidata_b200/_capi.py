@@ -66,6 +66,8 @@ _SIGNATURES = {
                                 C.c_float, C.c_void_p]),
     "odb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p]),
+    "odb_attention_mma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                    C.c_void_p]),
     "odb_groupnorm_scratch_bytes": (C.c_int64, [C.c_int32] * 4),
     "odb_groupnorm_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_float, C.c_void_p]),

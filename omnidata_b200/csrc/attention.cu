@@ -101,24 +101,19 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int token
 
     for (int ck = 0; ck < nchunks; ++ck) {
       const int key0 = ck * 64;
-      const int rem = tokens - key0;                  // valid keys in this chunk (>= 1)
-      const int nj = rem >= 64 ? 8 : (rem + 7) >> 3;  // 8-key S tiles that hold a valid key
-      const int nt = rem >= 64 ? 4 : (rem + 15) >> 4; // 16-key PV steps that hold a valid key
       float s[8][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
       // ---- S = Q K^T for 64 keys
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (j < nj) {   // the last chunk of a 577-token sequence holds a single valid key
-          const int key = key0 + j * 8 + lrow;
-          const uint32_t rowaddr = sK + key * 128;
-          uint32_t kb[8];
-          ldmatrix_x4(rowaddr + (((lmat) ^ (key & 7)) << 4), kb[0], kb[1], kb[2], kb[3]);
-          ldmatrix_x4(rowaddr + (((4 + lmat) ^ (key & 7)) << 4), kb[4], kb[5], kb[6], kb[7]);
+        const int key = key0 + j * 8 + lrow;
+        const uint32_t rowaddr = sK + key * 128;
+        uint32_t kb[8];
+        ldmatrix_x4(rowaddr + (((lmat) ^ (key & 7)) << 4), kb[0], kb[1], kb[2], kb[3]);
+        ldmatrix_x4(rowaddr + (((4 + lmat) ^ (key & 7)) << 4), kb[4], kb[5], kb[6], kb[7]);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_bf16_16816(s[j], qa[kk], kb[2 * kk], kb[2 * kk + 1]);
-        }
+        for (int kk = 0; kk < 4; ++kk) mma_bf16_16816(s[j], qa[kk], kb[2 * kk], kb[2 * kk + 1]);
       }
       // ---- scale, mask, online softmax
       float cmax0 = -INFINITY, cmax1 = -INFINITY;
@@ -161,16 +156,14 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int token
       // ---- O += P V
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        if (t < nt) {
-          const int key = key0 + t * 16 + (lmat & 1) * 8 + lrow;
-          const uint32_t rowaddr = sV + key * 128;
+        const int key = key0 + t * 16 + (lmat & 1) * 8 + lrow;
+        const uint32_t rowaddr = sV + key * 128;
 #pragma unroll
-          for (int jp = 0; jp < 4; ++jp) {
-            uint32_t v0, v1, v2, v3;
-            ldmatrix_x4_trans(rowaddr + (((2 * jp + (lmat >> 1)) ^ (key & 7)) << 4), v0, v1, v2, v3);
-            mma_bf16_16816(o[2 * jp], pa[t], v0, v1);
-            mma_bf16_16816(o[2 * jp + 1], pa[t], v2, v3);
-          }
+        for (int jp = 0; jp < 4; ++jp) {
+          uint32_t v0, v1, v2, v3;
+          ldmatrix_x4_trans(rowaddr + (((2 * jp + (lmat >> 1)) ^ (key & 7)) << 4), v0, v1, v2, v3);
+          mma_bf16_16816(o[2 * jp], pa[t], v0, v1);
+          mma_bf16_16816(o[2 * jp + 1], pa[t], v2, v3);
         }
       }
     }
@@ -197,7 +190,7 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int token
 
 using namespace odb;
 
-extern "C" int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads,
+extern "C" int odb_attention_mma(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads,
                              float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!qkv || !out || b < 1 || heads < 1 || tokens < 1)

@@ -238,20 +238,21 @@ def test_layernorm():
     check(out, F.layer_norm(x.float(), (768,), g, bta, 1e-6), "layernorm")
 
 
-@pytest.mark.parametrize("b,tokens", [(2, 577), (1, 64), (1, 100)])
-def test_attention(b, tokens):
+@pytest.mark.parametrize("impl", ["tc", "mma"])
+@pytest.mark.parametrize("b,tokens", [(2, 577), (1, 64), (1, 100), (13, 257), (40, 577)])
+def test_attention(b, tokens, impl):
     o = ops()
     qkv = rnd(b, tokens, 2304)
     qkv[..., :1536] *= 2.0            # peaky softmax, as in a trained ViT
     qkv = qkv.to(torch.bfloat16)
     out = torch.full((b, tokens, 768), float("nan"), device=dev(), dtype=torch.bfloat16)
-    o.attention(qkv, out)
+    o.attention(qkv, out, impl=impl)
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(b, tokens, 3, 12, 64).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2) * 0.125
-    # the kernel's definition (online softmax over 64-key chunks, P rounded to bf16 for PV)
-    from oracle.dpt_oracle import _attention_online_bf16
-    ref = _attention_online_bf16(q.cpu(), k.cpu(), v.cpu()).to(dev())
+    # each kernel's own definition of where P is rounded to bf16 (see oracle/dpt_oracle.py)
+    from oracle.dpt_oracle import _attention_bf16, _attention_online_bf16
+    ref = (_attention_bf16 if impl == "tc" else _attention_online_bf16)(q.cpu(), k.cpu(), v.cpu()).to(dev())
     check(out, ref.transpose(1, 2).reshape(b, tokens, 768), f"attention b{b} n{tokens}", tol=1e-3)
     exact = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(b, tokens, 768)
     assert rel_l2(out.float(), exact) < 4e-3
