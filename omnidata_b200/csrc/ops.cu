@@ -156,29 +156,30 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(
   }
 }
 
-// Finalize the per-warp partial sums written by the conv epilogue: block = image, 8 threads per
-// group sum a fixed strided subset of the rows in fp64, then combine in a fixed shuffle order.
-__global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const float* __restrict__ partial,
-                                                                 float* __restrict__ stats,
-                                                                 int rows, int groups, double count,
-                                                                 float eps) {
+// Finalize the per-warp partial sums written by the conv epilogue: block = image, one warp per
+// group; lane l sums rows l, l+32, ... in fp64 (independent loads, fixed order), then a fixed
+// shuffle tree combines the 32 lanes.
+__global__ void __launch_bounds__(1024) groupnorm_finalize_kernel(const float* __restrict__ partial,
+                                                                  float* __restrict__ stats,
+                                                                  int rows, int groups, double count,
+                                                                  float eps) {
   const int b = blockIdx.x;
-  const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (g >= groups) return;
+  const float* base = partial + ((long long)b * rows) * groups * 2 + g * 2;
   double ts = 0.0, tq = 0.0;
-  if (g < groups) {
-    const float* base = partial + ((long long)b * rows) * groups * 2 + g * 2;
-    for (int r = sub; r < rows; r += 8) {
-      const float2 v = *reinterpret_cast<const float2*>(base + (long long)r * groups * 2);
-      ts += (double)v.x;
-      tq += (double)v.y;
-    }
+#pragma unroll 4
+  for (int r = lane; r < rows; r += 32) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(base + (long long)r * groups * 2));
+    ts += (double)v.x;
+    tq += (double)v.y;
   }
 #pragma unroll
-  for (int o = 4; o >= 1; o >>= 1) {
-    ts += __shfl_down_sync(0xffffffffu, ts, o, 8);
-    tq += __shfl_down_sync(0xffffffffu, tq, o, 8);
+  for (int o = 16; o >= 1; o >>= 1) {
+    ts += __shfl_down_sync(0xffffffffu, ts, o);
+    tq += __shfl_down_sync(0xffffffffu, tq, o);
   }
-  if (g < groups && sub == 0) {
+  if (lane == 0) {
     const double mean = ts / count;
     double var = tq / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -508,8 +509,8 @@ extern "C" int odb_groupnorm_finalize(const float* partial, float* stats, int32_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!partial || !stats || b < 1 || rows_per_image < 1 || groups < 1 || groups > 32 || count <= 0)
     return fail(ODB_ERR_INVALID, "groupnorm_finalize: bad argument");
-  groupnorm_finalize_kernel<<<b, 256, 0, stream>>>(partial, stats, rows_per_image, groups, count,
-                                                   eps);
+  groupnorm_finalize_kernel<<<b, 32 * groups, 0, stream>>>(partial, stats, rows_per_image, groups,
+                                                           count, eps);
   count_launch();
   return check_launch("groupnorm_finalize");
 }
