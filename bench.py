@@ -196,7 +196,7 @@ def classify_gemm(info: dict, batch: int, ntok: int) -> str:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (configs[1]: 32)")
@@ -212,6 +212,8 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+    os.environ["NCCL_DEBUG"] = os.environ.get("ODB_NCCL_DEBUG", "WARN")
     import torch
     from omnidata_b200 import _capi, ops, parallel
     from omnidata_b200.model import DPTDepthModel

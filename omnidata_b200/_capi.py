@@ -47,6 +47,7 @@ class ConvGemmDesc(C.Structure):
         ("tile_w", C.c_int32), ("tile_h", C.c_int32),
         ("block_n", C.c_int32),
         ("cta_pair", C.c_int32),
+        ("halo", C.c_int32),
         ("head_w", C.c_void_p),
         ("head_b", C.c_void_p),
         ("head_c", C.c_int32),

@@ -50,6 +50,7 @@ struct ConvGemmParams {
   int head_c;
   int head_relu;
   float* head_out;
+  int halo_w;          // HALO mode: tile_w + 2 (row pitch of the halo tile), else 0
   float* gn_partial;   // optional GroupNorm partial sums, [b][tiles_y*tiles_x][4 quadrants][groups][2]
   int gn_cpg;          // channels per group (2..32, power of two)
   int gn_groups;
@@ -107,17 +108,29 @@ ODB_DEVINL void gn_warp_partials(const float* v, int lane, float* dst /* [groups
   if ((lane & ((1 << (5 - LOGV)) - 1)) == 0) dst[lane >> (5 - LOGV)] = vals[0];
 }
 
-template <int BLOCK_N, int STAGES, int NSTAGING, bool PAIR>
+// HALO = true (3x3 stride-1 convolutions): instead of nine shifted 128-row boxes per K block, ONE
+// halo box {64 ch, tile_w + 2, tile_h + 2} is loaded per K block into its own ring and the nine taps
+// are nine UMMA descriptors into it (start address shifted by whole 128-byte rows, swizzle phase
+// carried by the descriptor's base-offset field).  Accumulator row r is halo position
+// (r / (tile_w+2), r % (tile_w+2)); the two junk columns per halo row are masked in the epilogue.
+// L2 -> smem traffic for A drops from 9 x 16 KiB to <= 49 KiB per K block.  The weights keep their
+// own (tap, K block) ring.
+constexpr int kHaloStageBytes = 49 * 1024;   // >= 390 rows x 128 B (tile_w = 128, tile_h = 1)
+
+template <int BLOCK_N, int STAGES, int NSTAGING, bool PAIR, bool HALO, bool HEAD>
 struct SmemPlan {
   static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // a CTA pair splits B along N
   static constexpr int kBBytes = kBRows * 128;
+  static constexpr int kAStages = HALO ? (HEAD ? 3 : 2) : STAGES;
+  static constexpr int kAStageBytes = HALO ? kHaloStageBytes : kABytes;
   static constexpr int kAOff = 0;
-  static constexpr int kBOff = STAGES * kABytes;
+  static constexpr int kBOff = kAStages * kAStageBytes;
   static constexpr int kCOff = kBOff + STAGES * kBBytes;
   static constexpr int kBarOff = kCOff + NSTAGING * kStagingBytes;
-  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base pointer
-  static constexpr int kBarBytes = (2 * STAGES + 4) * 8 + 16;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], a_full[3], a_empty[3], tmem base pointer
+  static constexpr int kBarBytes = (2 * STAGES + 4 + 6) * 8 + 16;
   static constexpr int kTotal = kBarOff + kBarBytes + 1024;  // +1024: manual 1 KiB alignment
+  static_assert(kTotal <= 232448, "shared memory plan exceeds 227 KiB");
 };
 
 template <int BLOCK_N>
@@ -130,10 +143,10 @@ struct TmemCols {
 // vertically adjacent 128-row M tiles against the same N tile as ONE UMMA (M = 256): each CTA
 // TMA-loads its own A rows and HALF of the B rows, the leader CTA issues the MMAs for both, and each
 // CTA drains its own 128 TMEM lanes.  Per-SM smem fill and L2 read traffic per MMA drop by a third.
-template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR>
+template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR>;
+  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR, HALO, HEAD>;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -142,7 +155,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto afull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + a); };
+  auto aempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 7 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 10);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -158,6 +173,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(tfull_bar(a), 1);
       // one arrive per participating epilogue warp (of both CTAs for a pair)
       mbar_init(tempty_bar(a), (HEAD ? 4 : 8) * (PAIR ? 2 : 1));
+    }
+    for (int a = 0; a < 3; ++a) {
+      mbar_init(afull_bar(a), PAIR ? 2 : 1);
+      mbar_init(aempty_bar(a), 1);
     }
     mbar_fence_init();
     for (int v = 0; v < ODB_MAX_VIEWS; ++v) tma_prefetch_desc(&p.a_map[v]);
@@ -185,7 +204,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int unit0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int unit_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_kb = p.num_taps * p.kb_per_tap;
-  const uint32_t a_bytes = static_cast<uint32_t>(p.tile_w * p.tile_h) * 128u;
+  const uint32_t a_bytes =
+      HALO ? static_cast<uint32_t>(p.halo_w * (p.tile_h + 2)) * 128u
+           : static_cast<uint32_t>(p.tile_w * p.tile_h) * 128u;
   // unit -> (tn, tx, ty, tb); an M tile past the end (odd tile count, peer CTA) maps to batch
   // index tiles_b: every TMA box is then out of bounds (zero fill on load, nothing stored)
   auto decode = [&](int unit, int& tn, int& tx, int& ty, int& tb) {
@@ -201,34 +222,69 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, astage = 0;
+      uint32_t phase = 0, aphase = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
         int tn, tx, ty, tb;
         decode(tile, tn, tx, ty, tb);
         const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          const CUtensorMap* amap = &p.a_map[p.tap_view[tap]];
-          const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
+        if constexpr (HALO) {
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + Plan::kAOff + stage * kABytes;
-            const uint32_t sb = smem_base + Plan::kBOff + stage * Plan::kBBytes;
-            const int kcoord = (tap * p.kb_per_tap + kb) * kKBlock;
+            // ---- one halo box of the input per K block ...
+            mbar_wait(aempty_bar(astage), aphase ^ 1u);
+            const uint32_t sa = smem_base + Plan::kAOff + astage * Plan::kAStageBytes;
             if constexpr (PAIR) {
-              // both CTAs credit the LEADER's full barrier; the leader arms it for both CTAs' bytes
-              const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
-              if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * (a_bytes + Plan::kBBytes));
-              tma_load_4d_cg2(sa, amap, lead_full, kb * kKBlock, ax, ay, tb);
-              tma_load_2d_cg2(sb, &p.b_map, lead_full, kcoord,
-                              tn * BLOCK_N + static_cast<int>(cta_rank) * Plan::kBRows);
-              if (cta_rank != 0) mbar_arrive_cluster(lead_full);
+              const uint32_t lead = mapa_shared(afull_bar(astage), 0);
+              if (cta_rank == 0) mbar_expect_tx(afull_bar(astage), 2u * a_bytes);
+              tma_load_4d_cg2(sa, &p.a_map[0], lead, kb * kKBlock, x0 - 1, y0 - 1, tb);
+              if (cta_rank != 0) mbar_arrive_cluster(lead);
             } else {
-              mbar_expect_tx(full_bar(stage), a_bytes + Plan::kBBytes);
-              tma_load_4d(sa, amap, full_bar(stage), kb * kKBlock, ax, ay, tb);
-              tma_load_2d(sb, &p.b_map, full_bar(stage), kcoord, tn * BLOCK_N);
+              mbar_expect_tx(afull_bar(astage), a_bytes);
+              tma_load_4d(sa, &p.a_map[0], afull_bar(astage), kb * kKBlock, x0 - 1, y0 - 1, tb);
             }
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (++astage == Plan::kAStages) { astage = 0; aphase ^= 1u; }
+            // ---- ... and the nine weight tiles of that K block
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sb = smem_base + Plan::kBOff + stage * Plan::kBBytes;
+              const int kcoord = (tap * p.kb_per_tap + kb) * kKBlock;
+              if constexpr (PAIR) {
+                const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * Plan::kBBytes);
+                tma_load_2d_cg2(sb, &p.b_map, lead_full, kcoord,
+                                tn * BLOCK_N + static_cast<int>(cta_rank) * Plan::kBRows);
+                if (cta_rank != 0) mbar_arrive_cluster(lead_full);
+              } else {
+                mbar_expect_tx(full_bar(stage), Plan::kBBytes);
+                tma_load_2d(sb, &p.b_map, full_bar(stage), kcoord, tn * BLOCK_N);
+              }
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        } else {
+          for (int tap = 0; tap < p.num_taps; ++tap) {
+            const CUtensorMap* amap = &p.a_map[p.tap_view[tap]];
+            const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap];
+            for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = smem_base + Plan::kAOff + stage * kABytes;
+              const uint32_t sb = smem_base + Plan::kBOff + stage * Plan::kBBytes;
+              const int kcoord = (tap * p.kb_per_tap + kb) * kKBlock;
+              if constexpr (PAIR) {
+                // both CTAs credit the LEADER's full barrier; the leader arms it for both CTAs' bytes
+                const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * (a_bytes + Plan::kBBytes));
+                tma_load_4d_cg2(sa, amap, lead_full, kb * kKBlock, ax, ay, tb);
+                tma_load_2d_cg2(sb, &p.b_map, lead_full, kcoord,
+                                tn * BLOCK_N + static_cast<int>(cta_rank) * Plan::kBRows);
+                if (cta_rank != 0) mbar_arrive_cluster(lead_full);
+              } else {
+                mbar_expect_tx(full_bar(stage), a_bytes + Plan::kBBytes);
+                tma_load_4d(sa, amap, full_bar(stage), kb * kKBlock, ax, ay, tb);
+                tma_load_2d(sb, &p.b_map, full_bar(stage), kcoord, tn * BLOCK_N);
+              }
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
@@ -237,8 +293,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kTileRows : kTileRows, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, astage = 0;
+      uint32_t phase = 0, aphase = 0;
       uint32_t iter = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
         const uint32_t acc = iter & 1u;
@@ -246,22 +302,51 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_base + Plan::kAOff + stage * kABytes);
-          const uint64_t bdesc = umma_desc_sw128(smem_base + Plan::kBOff + stage * Plan::kBBytes);
+        if constexpr (HALO) {
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(afull_bar(astage), aphase);
+            tc_fence_after();
+            const uint32_t a_base = smem_base + Plan::kAOff + astage * Plan::kAStageBytes;
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              // tap (dy, dx) = the halo tile shifted by whole 128-byte rows; the swizzle phase of the
+              // (no longer 1 KiB aligned) start address goes into the descriptor's base-offset field
+              const uint32_t a_addr =
+                  a_base + static_cast<uint32_t>((p.tap_dy[tap] + 1) * p.halo_w + (p.tap_dx[tap] + 1)) * 128u;
+              const uint64_t adesc =
+                  umma_desc_sw128(a_addr) | (static_cast<uint64_t>((a_addr >> 7) & 7u) << 49);
+              const uint64_t bdesc = umma_desc_sw128(smem_base + Plan::kBOff + stage * Plan::kBBytes);
 #pragma unroll
-          for (int k = 0; k < kKBlock / 16; ++k) {
-            // +32 bytes (= 2 in 16-byte units) per UMMA_K=16 inside the 128B swizzle row
-            if constexpr (PAIR)
-              umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else
-              umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kKBlock / 16; ++k) {
+                const uint32_t accum = (kb | tap | k) != 0 ? 1u : 0u;
+                if constexpr (PAIR) umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+                else umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+              }
+              if constexpr (PAIR) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            if constexpr (PAIR) umma_commit_cg2(aempty_bar(astage), 3); else umma_commit(aempty_bar(astage));
+            if (++astage == Plan::kAStages) { astage = 0; aphase ^= 1u; }
           }
-          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-          if constexpr (PAIR) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        } else {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_base + Plan::kAOff + stage * kABytes);
+            const uint64_t bdesc = umma_desc_sw128(smem_base + Plan::kBOff + stage * Plan::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kKBlock / 16; ++k) {
+              // +32 bytes (= 2 in 16-byte units) per UMMA_K=16 inside the 128B swizzle row
+              if constexpr (PAIR)
+                umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+            if constexpr (PAIR) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
         // accumulator complete
         if constexpr (PAIR) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
@@ -274,8 +359,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int row = quad * 32 + lane;      // accumulator row == pixel within the tile
     const bool store_leader = (warp == 2 && lane == 0);
     const int tw = p.tile_w;
-    const int ly = row / tw, lx = row - ly * tw;
-    const bool row_in_tile = row < p.tile_w * p.tile_h;
+    const int rpitch = HALO ? p.halo_w : tw;            // accumulator rows per tile row
+    const int ly = row / rpitch, lx = row - ly * rpitch;
+    const bool row_in_tile = HALO ? (lx < tw && ly < p.tile_h) : (row < p.tile_w * p.tile_h);
+    const int srow = HALO ? (row_in_tile ? ly * tw + lx : 0) : row;   // dense row in the store staging tile
     uint32_t iter = 0;
     uint32_t chunk_counter = 0;
     const int bufs_per_chunk = p.has_out2 ? 2 : 1;
@@ -429,20 +516,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             named_bar_sync(1, kEpiThreads);
           }
           const uint32_t buf0 = smem_base + Plan::kCOff + (slot * bufs_per_chunk) * kStagingBytes;
-          const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
+          const uint32_t rowoff = static_cast<uint32_t>(srow) * 128u;
+          const bool do_store = !HALO || row_in_tile;       // halo junk columns own no staging row
+          if (do_store) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t addr =
-                buf0 + rowoff + (static_cast<uint32_t>((half * 4 + j) ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j]),
-                         "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
-                         : "memory");
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t addr =
+                  buf0 + rowoff + (static_cast<uint32_t>((half * 4 + j) ^ (srow & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j]),
+                           "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                           : "memory");
+            }
           }
-          if (p.has_out2) {
+          if (p.has_out2 && do_store) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t addr = buf0 + kStagingBytes + rowoff +
-                                    (static_cast<uint32_t>((half * 4 + j) ^ (row & 7)) << 4);
+                                    (static_cast<uint32_t>((half * 4 + j) ^ (srow & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
                            "r"(pack_bf16x2(fmaxf(v[8 * j + 0], 0.f), fmaxf(v[8 * j + 1], 0.f))),
                            "r"(pack_bf16x2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f))),
@@ -497,10 +587,10 @@ static int encode_view_map(CUtensorMap* map, const odb_view& v, int box_c, int b
                       strides, box, estr, swz);
 }
 
-template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR>
+template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR, bool HALO>
 static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_t stream) {
-  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, STAGES, NSTAGING, HEAD, PAIR>;
+  using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR, HALO, HEAD>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, STAGES, NSTAGING, HEAD, PAIR, HALO>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -539,9 +629,17 @@ using namespace odb;
 
 struct HostPlan {
   int tw, th, tiles_x, tiles_y, block_n;
-  bool pair, head;
+  bool pair, head, halo;
   long long m_tiles;
 };
+
+// the canonical 3x3 / stride 1 / pad 1 pattern over a single view (tap t = (ky, kx) row-major)
+static bool is_canonical_3x3(const odb_conv_gemm_desc* d) {
+  if (d->num_views != 1 || d->num_taps != 9) return false;
+  for (int t = 0; t < 9; ++t)
+    if (d->tap_view[t] != 0 || d->tap_dx[t] != t % 3 - 1 || d->tap_dy[t] != t / 3 - 1) return false;
+  return d->views[0].w == d->out.w && d->views[0].h == d->out.h && d->views[0].b == d->out.b;
+}
 
 static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
   if (d == nullptr) return fail(ODB_ERR_INVALID, "conv_gemm: null descriptor");
@@ -565,6 +663,20 @@ static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
   const int ow = d->out.w, oh = d->out.h, ob = d->out.b;
   if (ow < 1 || oh < 1 || ob < 1) return fail(ODB_ERR_INVALID, "conv_gemm: empty output extent");
   int tw = d->tile_w, th = d->tile_h;
+  bool halo = false;
+  if (d->halo == 1) {
+    if (!is_canonical_3x3(d)) return fail(ODB_ERR_INVALID, "conv_gemm: halo mode needs a 3x3 stride-1 pad-1 conv");
+    halo = true;
+  } else if (d->halo == 0) {
+    halo = is_canonical_3x3(d) && (tw <= 0 || th <= 0);
+  }
+  if (halo && (tw <= 0 || th <= 0)) {
+    if (ow <= 126) { tw = ow; th = 130 / (ow + 2); if (th > oh) th = oh; }
+    else { const int segs = (ow + 127) / 128; tw = (ow + segs - 1) / segs; th = 1; }
+  }
+  if (halo && (th * (tw + 2) - 2 > kTileRows || (tw + 2) * (th + 2) * 128 > kHaloStageBytes))
+    return fail(ODB_ERR_INVALID, "conv_gemm: halo tile does not fit (tile_h * (tile_w + 2) - 2 <= 128)");
+  hp->halo = halo;
   if (tw <= 0 || th <= 0) {
     if (oh == 1) { tw = 128; th = 1; }
     else if (ow % 16 == 0 && oh % 8 == 0) { tw = 16; th = 8; }
@@ -604,7 +716,10 @@ extern "C" int odb_conv_gemm_plan(const odb_conv_gemm_desc* d, int32_t* out4) {
   HostPlan hp;
   int rc = make_plan(d, &hp);
   if (rc) return rc;
-  if (out4) { out4[0] = hp.tiles_x; out4[1] = hp.tiles_y; out4[2] = hp.block_n; out4[3] = hp.pair ? 1 : 0; }
+  if (out4) {
+    out4[0] = hp.tiles_x; out4[1] = hp.tiles_y; out4[2] = hp.block_n;
+    out4[3] = (hp.pair ? 1 : 0) | (hp.halo ? 2 : 0);
+  }
   return ODB_OK;
 }
 
@@ -643,7 +758,8 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   for (int v = 0; v < ODB_MAX_VIEWS; ++v) {
     // unused slots alias view 0 so that prefetch.tensormap always sees a valid descriptor
     const odb_view& src = d->views[v < d->num_views ? v : 0];
-    rc = encode_view_map(&p.a_map[v], src, kKBlock, tw, th, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_view_map(&p.a_map[v], src, kKBlock, hp.halo ? tw + 2 : tw, hp.halo ? th + 2 : th,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
@@ -697,14 +813,26 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   }
 
   const long long total = m_tiles * p.tiles_n;
-  if (pair) return launch_instance<256, 6, 2, false, true>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
+  if (hp.halo) {
+    p.halo_w = tw + 2;
+    if (pair) return launch_instance<256, 4, 2, false, true, true>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
+    switch (block_n) {
+      case 256: return launch_instance<256, 2, 2, false, false, true>(p, total, stream);
+      case 128: return launch_instance<128, 5, 2, false, false, true>(p, total, stream);
+      case 64: return launch_instance<64, 6, 2, false, false, true>(p, total, stream);
+      case 32:
+        if (!head) return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: block_n 32 only with the head tail");
+        return launch_instance<32, 8, 0, true, false, true>(p, total, stream);
+    }
+  }
+  if (pair) return launch_instance<256, 6, 2, false, true, false>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
   switch (block_n) {
-    case 256: return launch_instance<256, 4, 2, false, false>(p, total, stream);
-    case 128: return launch_instance<128, 5, 4, false, false>(p, total, stream);
-    case 64: return launch_instance<64, 6, 4, false, false>(p, total, stream);
+    case 256: return launch_instance<256, 4, 2, false, false, false>(p, total, stream);
+    case 128: return launch_instance<128, 5, 4, false, false, false>(p, total, stream);
+    case 64: return launch_instance<64, 6, 4, false, false, false>(p, total, stream);
     case 32:
       if (!head) return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: block_n 32 only with the head tail");
-      return launch_instance<32, 8, 0, true, false>(p, total, stream);
+      return launch_instance<32, 8, 0, true, false, false>(p, total, stream);
   }
   return fail(ODB_ERR_INVALID, "conv_gemm: unreachable");
 }

@@ -233,38 +233,50 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
   const bf16* xb = x + ((long long)b * hw) * c;
   const bf16* rb = res ? res + ((long long)b * hw) * c : nullptr;
   bf16* yb = y + ((long long)b * hw) * c;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const unsigned oct = pow2 ? (i & omask) : (i % (unsigned)octets);
-    const unsigned off = i * 8u;
-    float v[8], o[8];
-    load8(xb + off, v);
-    float r[8];
-    if (rb != nullptr) load8(rb + off, r);
-    const float4 a0 = *reinterpret_cast<const float4*>(coef + oct * 8);
-    const float4 a1 = *reinterpret_cast<const float4*>(coef + oct * 8 + 4);
-    const float4 s0 = *reinterpret_cast<const float4*>(coef + c + oct * 8);
-    const float4 s1 = *reinterpret_cast<const float4*>(coef + c + oct * 8 + 4);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], a[j], sh[j]);
+  // two independent items per iteration: all global loads are issued before any math
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    const unsigned i1 = i0 + stride;
+    const bool has1 = i1 < total;
+    float v[2][8], r[2][8];
+    load8(xb + i0 * 8u, v[0]);
+    if (has1) load8(xb + i1 * 8u, v[1]);
     if (rb != nullptr) {
-      if (res_norm) {
-        const float4 r0 = *reinterpret_cast<const float4*>(coef + 2 * c + oct * 8);
-        const float4 r1 = *reinterpret_cast<const float4*>(coef + 2 * c + oct * 8 + 4);
-        const float ra[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      load8(rb + i0 * 8u, r[0]);
+      if (has1) load8(rb + i1 * 8u, r[1]);
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(r[j], ra[j], o[j]);
-      } else {
+    for (int u = 0; u < 2; ++u) {
+      const unsigned i = u ? i1 : i0;
+      if (u && !has1) break;
+      const unsigned oct = pow2 ? (i & omask) : (i % (unsigned)octets);
+      float o[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(coef + oct * 8);
+      const float4 a1 = *reinterpret_cast<const float4*>(coef + oct * 8 + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(coef + c + oct * 8);
+      const float4 s1 = *reinterpret_cast<const float4*>(coef + c + oct * 8 + 4);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(v[u][j], a[j], sh[j]);
+      if (rb != nullptr) {
+        if (res_norm) {
+          const float4 r0 = *reinterpret_cast<const float4*>(coef + 2 * c + oct * 8);
+          const float4 r1 = *reinterpret_cast<const float4*>(coef + 2 * c + oct * 8 + 4);
+          const float ra[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(r[u][j], ra[j], o[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[u][j];
+        }
       }
-    }
-    if (relu) {
+      if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+      }
+      store8(yb + i * 8u, o);
     }
-    store8(yb + off, o);
   }
 }
 
@@ -352,18 +364,25 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
                                                              bf16* __restrict__ out,
                                                              bf16* __restrict__ out_relu, int b,
                                                              int h, int w, int c) {
-  // grid: (column chunks, output row, image) — all index math is 32-bit and row-uniform
+  // grid: (column chunks, output row PAIR, image); all index math is 32-bit and row-uniform.
+  // A thread produces the same (column, channel octet) of two adjacent output rows: 8 gathers and
+  // 2 skip loads are in flight before any arithmetic.
   const int octets = c >> 3;
   const int oh = 2 * h, ow = 2 * w;
-  const int oy = blockIdx.y, bi = blockIdx.z;
+  const int oy0 = 2 * blockIdx.y, bi = blockIdx.z;
   const float sy = (float)(h - 1) / (float)(oh - 1), sx = (float)(w - 1) / (float)(ow - 1);
-  const float fy = oy * sy;
-  const int y0 = min((int)fy, h - 1);
-  const int y1 = min(y0 + 1, h - 1);
-  const float wy = fy - (float)y0;
-  const bf16* z0 = z + ((long long)bi * h + y0) * w * c;
-  const bf16* z1 = z + ((long long)bi * h + y1) * w * c;
-  const long long orow = ((long long)bi * oh + oy) * ow * c;
+  const bf16* zrow[2][2];
+  float wy[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const float fy = (oy0 + u) * sy;
+    const int y0 = min((int)fy, h - 1);
+    const int y1 = min(y0 + 1, h - 1);
+    wy[u] = fy - (float)y0;
+    zrow[u][0] = z + ((long long)bi * h + y0) * w * c;
+    zrow[u][1] = z + ((long long)bi * h + y1) * w * c;
+  }
+  const long long orow = ((long long)bi * oh + oy0) * ow * c;
   const int total = ow * octets;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int oct = i % octets;
@@ -372,28 +391,38 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
     const int x0 = min((int)fx, w - 1);
     const int x1 = min(x0 + 1, w - 1);
     const float wx = fx - (float)x0;
-    float a[8], bq[8], cc[8], d[8], o[8], r[8];
-    load8(z0 + x0 * c + oct * 8, a);
-    load8(z0 + x1 * c + oct * 8, bq);
-    load8(z1 + x0 * c + oct * 8, cc);
-    load8(z1 + x1 * c + oct * 8, d);
-    const long long off = orow + i * 8;
-    if (res != nullptr) load8(res + off, r);
+    float g[2][4][8], r[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float top = a[j] + (bq[j] - a[j]) * wx;
-      const float bot = cc[j] + (d[j] - cc[j]) * wx;
-      o[j] = top + (bot - top) * wy;
+    for (int u = 0; u < 2; ++u) {
+      load8(zrow[u][0] + x0 * c + oct * 8, g[u][0]);
+      load8(zrow[u][0] + x1 * c + oct * 8, g[u][1]);
+      load8(zrow[u][1] + x0 * c + oct * 8, g[u][2]);
+      load8(zrow[u][1] + x1 * c + oct * 8, g[u][3]);
     }
     if (res != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += r[j];
+      load8(res + orow + i * 8, r[0]);
+      load8(res + orow + (long long)ow * c + i * 8, r[1]);
     }
-    store8(out + off, o);
-    if (out_relu != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-      store8(out_relu + off, o);
+    for (int u = 0; u < 2; ++u) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float top = g[u][0][j] + (g[u][1][j] - g[u][0][j]) * wx;
+        const float bot = g[u][2][j] + (g[u][3][j] - g[u][2][j]) * wx;
+        o[j] = top + (bot - top) * wy[u];
+      }
+      if (res != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[u][j];
+      }
+      const long long off = orow + (long long)u * ow * c + i * 8;
+      store8(out + off, o);
+      if (out_relu != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        store8(out_relu + off, o);
+      }
     }
   }
 }
@@ -568,7 +597,7 @@ extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, voi
     return fail(ODB_ERR_INVALID, "upsample2x_add: bad argument");
   if (2 * h > 65535 || b > 65535) return fail(ODB_ERR_INVALID, "upsample2x_add: extent too large");
   const int per_row = 2 * w * (c / 8);
-  dim3 grid((per_row + 255) / 256, 2 * h, b);
+  dim3 grid((per_row + 255) / 256, h, b);   // one block row per PAIR of output rows
   upsample2x_add_kernel<<<grid, 256, 0, stream>>>(
       static_cast<const bf16*>(z), static_cast<const bf16*>(res), static_cast<bf16*>(out),
       static_cast<bf16*>(out_relu), b, h, w, c);

@@ -134,6 +134,54 @@ def test_conv3x3(b, h, w_, c, n, tile):
     check(out, F.relu(conv_ref(x, w) + bias), f"conv3x3 {b}x{h}x{w_}x{c}->{n}")
 
 
+@pytest.mark.parametrize("b,h,w_,c,n,bn,pair", [
+    (2, 96, 96, 64, 64, 0, 0), (2, 48, 48, 256, 256, 0, 0), (3, 24, 24, 768, 256, 0, 0), (2, 12, 12, 256, 256, 0, 0),
+    (1, 192, 192, 128, 128, 0, 0), (1, 384, 384, 64, 64, 0, 0), (2, 96, 96, 256, 256, 256, 1), (3, 48, 48, 256, 256, 256, 1),
+    (2, 40, 56, 128, 128, 0, 0),
+])
+def test_conv3x3_halo_mode(b, h, w_, c, n, bn, pair):
+    """Halo tiles (one input box per K block, nine shifted UMMA descriptors) == per-tap boxes."""
+    o = ops()
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    skip = rnd(b, h, w_, n, seed=5).to(torch.bfloat16)
+    w = rnd(n, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    bias = rnd(n)
+    wp = o.pack_conv_weight(w)
+    out = torch.full((b, h, w_, n), float("nan"), device=dev(), dtype=torch.bfloat16)
+    out2 = torch.full((b, h, w_, n), float("nan"), device=dev(), dtype=torch.bfloat16)
+    partial = torch.empty((b * 512 * 4 * 32 * 2,), device=dev())
+    stats = torch.empty((b, 32, 2), device=dev())
+    o.conv3x3(x, wp, out, bias=bias, residual=skip, out2=out2, halo=1, block_n=bn, cta_pair=pair,
+              gn_stats=(partial, stats))
+    torch.cuda.synchronize()
+    ref = conv_ref(x, w) + bias + skip.float()
+    check(out, ref, f"halo conv3x3 {b}x{h}x{w_}x{c}->{n}")
+    check(out2, F.relu(ref), "halo conv3x3 relu copy")
+    base = torch.empty_like(out)
+    stats_b = torch.empty_like(stats)
+    o.conv3x3(x, wp, base, bias=bias, residual=skip, halo=-1, block_n=bn, cta_pair=pair, gn_stats=(partial, stats_b))
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), base.float()) < 3e-4        # same math, different K order (kb-major vs tap-major)
+    assert rel_l2(stats, stats_b) < 1e-4
+
+
+def test_head_tail_halo():
+    o = ops()
+    b, h, w_, c = 2, 64, 384, 128
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    w = rnd(32, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    bias, hw, hb = rnd(32), rnd(3, 32, scale=0.3), rnd(3, scale=0.1)
+    outs = []
+    for halo in (1, -1):
+        hout = torch.full((b, 3, h, w_), float("nan"), device=dev(), dtype=torch.float32)
+        o.conv3x3(x, o.pack_conv_weight(w), None, bias=bias, head=(hw, hb, hout, True), halo=halo)
+        torch.cuda.synchronize()
+        outs.append(hout)
+    v = F.relu(conv_ref(x, w) + bias)
+    ref = F.relu(torch.einsum("bhwj,kj->bkhw", v, hw) + hb[None, :, None, None])
+    assert rel_l2(outs[0], ref) < 1e-4 and rel_l2(outs[1], ref) < 1e-4
+
+
 def test_conv3x3_residual_dual():
     o = ops()
     b, h, w_, c = 2, 48, 48, 256
