@@ -110,11 +110,12 @@ ODB_DEVINL void gn_warp_partials(const float* v, int lane, float* dst /* [groups
 
 // HALO = true (3x3 stride-1 convolutions): instead of nine shifted 128-row boxes per K block, ONE
 // halo box {64 ch, tile_w + 2, tile_h + 2} is loaded per K block into its own ring and the nine taps
-// are nine UMMA descriptors into it (start address shifted by whole 128-byte rows, swizzle phase
-// carried by the descriptor's base-offset field).  Accumulator row r is halo position
+// are nine UMMA descriptors into it (start address shifted by whole 128-byte rows; the operand
+// swizzle is address-based, so no base-offset correction is needed — verified on hardware).  Accumulator row r is halo position
 // (r / (tile_w+2), r % (tile_w+2)); the two junk columns per halo row are masked in the epilogue.
 // L2 -> smem traffic for A drops from 9 x 16 KiB to <= 49 KiB per K block.  The weights keep their
 // own (tap, K block) ring.
+constexpr int kHaloAutoMaxN = 64;            // wider outputs are MMA / weight-traffic bound: per-tap boxes win
 constexpr int kHaloStageBytes = 49 * 1024;   // >= 390 rows x 128 B (tile_w = 128, tile_h = 1)
 
 template <int BLOCK_N, int STAGES, int NSTAGING, bool PAIR, bool HALO, bool HEAD>
@@ -310,12 +311,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int tap = 0; tap < p.num_taps; ++tap) {
               mbar_wait(full_bar(stage), phase);
               tc_fence_after();
-              // tap (dy, dx) = the halo tile shifted by whole 128-byte rows; the swizzle phase of the
-              // (no longer 1 KiB aligned) start address goes into the descriptor's base-offset field
+              // tap (dy, dx) = the halo tile shifted by whole 128-byte rows.  Measured on B200: the
+              // 128B swizzle of the UMMA operand fetch is a function of the shared-memory ADDRESS bits
+              // (like the TMA write), so a row-shifted start needs no base-offset correction.
               const uint32_t a_addr =
                   a_base + static_cast<uint32_t>((p.tap_dy[tap] + 1) * p.halo_w + (p.tap_dx[tap] + 1)) * 128u;
-              const uint64_t adesc =
-                  umma_desc_sw128(a_addr) | (static_cast<uint64_t>((a_addr >> 7) & 7u) << 49);
+              const uint64_t adesc = umma_desc_sw128(a_addr);
               const uint64_t bdesc = umma_desc_sw128(smem_base + Plan::kBOff + stage * Plan::kBBytes);
 #pragma unroll
               for (int k = 0; k < kKBlock / 16; ++k) {
@@ -668,7 +669,8 @@ static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
     if (!is_canonical_3x3(d)) return fail(ODB_ERR_INVALID, "conv_gemm: halo mode needs a 3x3 stride-1 pad-1 conv");
     halo = true;
   } else if (d->halo == 0) {
-    halo = is_canonical_3x3(d) && (tw <= 0 || th <= 0);
+    // automatic only where the per-tap scheme is bound by input re-reads: narrow outputs
+    halo = is_canonical_3x3(d) && (tw <= 0 || th <= 0) && d->n <= kHaloAutoMaxN;
   }
   if (halo && (tw <= 0 || th <= 0)) {
     if (ow <= 126) { tw = ow; th = 130 / (ow + 2); if (th > oh) th = oh; }

@@ -364,25 +364,18 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
                                                              bf16* __restrict__ out,
                                                              bf16* __restrict__ out_relu, int b,
                                                              int h, int w, int c) {
-  // grid: (column chunks, output row PAIR, image); all index math is 32-bit and row-uniform.
-  // A thread produces the same (column, channel octet) of two adjacent output rows: 8 gathers and
-  // 2 skip loads are in flight before any arithmetic.
+  // grid: (column chunks, output row, image) — all index math is 32-bit and row-uniform
   const int octets = c >> 3;
   const int oh = 2 * h, ow = 2 * w;
-  const int oy0 = 2 * blockIdx.y, bi = blockIdx.z;
+  const int oy = blockIdx.y, bi = blockIdx.z;
   const float sy = (float)(h - 1) / (float)(oh - 1), sx = (float)(w - 1) / (float)(ow - 1);
-  const bf16* zrow[2][2];
-  float wy[2];
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const float fy = (oy0 + u) * sy;
-    const int y0 = min((int)fy, h - 1);
-    const int y1 = min(y0 + 1, h - 1);
-    wy[u] = fy - (float)y0;
-    zrow[u][0] = z + ((long long)bi * h + y0) * w * c;
-    zrow[u][1] = z + ((long long)bi * h + y1) * w * c;
-  }
-  const long long orow = ((long long)bi * oh + oy0) * ow * c;
+  const float fy = oy * sy;
+  const int y0 = min((int)fy, h - 1);
+  const int y1 = min(y0 + 1, h - 1);
+  const float wy = fy - (float)y0;
+  const bf16* z0 = z + ((long long)bi * h + y0) * w * c;
+  const bf16* z1 = z + ((long long)bi * h + y1) * w * c;
+  const long long orow = ((long long)bi * oh + oy) * ow * c;
   const int total = ow * octets;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int oct = i % octets;
@@ -391,38 +384,28 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
     const int x0 = min((int)fx, w - 1);
     const int x1 = min(x0 + 1, w - 1);
     const float wx = fx - (float)x0;
-    float g[2][4][8], r[2][8];
+    float a[8], bq[8], cc[8], d[8], o[8], r[8];
+    load8(z0 + x0 * c + oct * 8, a);
+    load8(z0 + x1 * c + oct * 8, bq);
+    load8(z1 + x0 * c + oct * 8, cc);
+    load8(z1 + x1 * c + oct * 8, d);
+    const long long off = orow + i * 8;
+    if (res != nullptr) load8(res + off, r);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      load8(zrow[u][0] + x0 * c + oct * 8, g[u][0]);
-      load8(zrow[u][0] + x1 * c + oct * 8, g[u][1]);
-      load8(zrow[u][1] + x0 * c + oct * 8, g[u][2]);
-      load8(zrow[u][1] + x1 * c + oct * 8, g[u][3]);
+    for (int j = 0; j < 8; ++j) {
+      const float top = a[j] + (bq[j] - a[j]) * wx;
+      const float bot = cc[j] + (d[j] - cc[j]) * wx;
+      o[j] = top + (bot - top) * wy;
     }
     if (res != nullptr) {
-      load8(res + orow + i * 8, r[0]);
-      load8(res + orow + (long long)ow * c + i * 8, r[1]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += r[j];
     }
+    store8(out + off, o);
+    if (out_relu != nullptr) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float top = g[u][0][j] + (g[u][1][j] - g[u][0][j]) * wx;
-        const float bot = g[u][2][j] + (g[u][3][j] - g[u][2][j]) * wx;
-        o[j] = top + (bot - top) * wy[u];
-      }
-      if (res != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += r[u][j];
-      }
-      const long long off = orow + (long long)u * ow * c + i * 8;
-      store8(out + off, o);
-      if (out_relu != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-        store8(out_relu + off, o);
-      }
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+      store8(out_relu + off, o);
     }
   }
 }
@@ -597,7 +580,7 @@ extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, voi
     return fail(ODB_ERR_INVALID, "upsample2x_add: bad argument");
   if (2 * h > 65535 || b > 65535) return fail(ODB_ERR_INVALID, "upsample2x_add: extent too large");
   const int per_row = 2 * w * (c / 8);
-  dim3 grid((per_row + 255) / 256, h, b);   // one block row per PAIR of output rows
+  dim3 grid((per_row + 255) / 256, 2 * h, b);
   upsample2x_add_kernel<<<grid, 256, 0, stream>>>(
       static_cast<const bf16*>(z), static_cast<const bf16*>(res), static_cast<bf16*>(out),
       static_cast<bf16*>(out_relu), b, h, w, c);

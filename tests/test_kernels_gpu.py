@@ -139,7 +139,7 @@ def test_conv3x3(b, h, w_, c, n, tile):
     (1, 192, 192, 128, 128, 0, 0), (1, 384, 384, 64, 64, 0, 0), (2, 96, 96, 256, 256, 256, 1), (3, 48, 48, 256, 256, 256, 1),
     (2, 40, 56, 128, 128, 0, 0),
 ])
-def test_conv3x3_halo_mode(b, h, w_, c, n, bn, pair):
+def test_conv3x3_halo_mode(b, h, w_, c, n, bn, pair, hmode=1):
     """Halo tiles (one input box per K block, nine shifted UMMA descriptors) == per-tap boxes."""
     o = ops()
     x = rnd(b, h, w_, c).to(torch.bfloat16)
@@ -149,9 +149,9 @@ def test_conv3x3_halo_mode(b, h, w_, c, n, bn, pair):
     wp = o.pack_conv_weight(w)
     out = torch.full((b, h, w_, n), float("nan"), device=dev(), dtype=torch.bfloat16)
     out2 = torch.full((b, h, w_, n), float("nan"), device=dev(), dtype=torch.bfloat16)
-    partial = torch.empty((b * 512 * 4 * 32 * 2,), device=dev())
+    partial = torch.empty((b * 1280 * 4 * 32 * 2,), device=dev())
     stats = torch.empty((b, 32, 2), device=dev())
-    o.conv3x3(x, wp, out, bias=bias, residual=skip, out2=out2, halo=1, block_n=bn, cta_pair=pair,
+    o.conv3x3(x, wp, out, bias=bias, residual=skip, out2=out2, halo=hmode, block_n=bn, cta_pair=pair,
               gn_stats=(partial, stats))
     torch.cuda.synchronize()
     ref = conv_ref(x, w) + bias + skip.float()
