@@ -172,6 +172,28 @@ int odb_write_cls_row(void* tokens, const float* cls, const float* pos0, int32_t
 int odb_readout_cls_bias(const void* w, const float* bias, const void* tokens, float* out, int32_t b,
                          int32_t tokens_n, int32_t c, void* stream);
 
+/* ---- depth-training losses, FORWARD ONLY (train_depth.py:261-279); all tensors fp32 [b][h][w] ------- */
+
+/* make_valid_mask (train_depth.py:215-242): valid = nearest_upsample(max_pool2d(1 - mask, pool)) == 0. */
+int odb_make_valid_mask(const float* mask_float, uint8_t* mask_valid, int32_t b, int32_t h, int32_t w,
+                        int32_t pool, void* stream);
+
+/* MidasLoss(alpha, scales, reduction='image-based').forward (losses/midas_loss.py:137-157):
+ * out3 = (total, ssi, reg).  mask: uint8, 1 = valid.  Exact lower nanmedian by radix select,
+ * deterministic fp64-combined reductions.  workspace: >= odb_midas_loss_workspace_bytes(b), 256-B aligned. */
+int64_t odb_midas_loss_workspace_bytes(int32_t b);
+int odb_midas_loss_fwd(const float* prediction, const float* target, const uint8_t* mask, int32_t b,
+                       int32_t h, int32_t w, float alpha, int32_t scales, float* out3, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/* VNL_Loss.forward(first, second, select) (losses/virtual_normal_loss.py:151-194) for given point
+ * triplets p1/p2/p3 (device int32 [n_points], flat index y*w + x — the reference draws them with host
+ * NumPy RNG, :52-72).  `first` takes the reference's `gt_depth` slot (train_depth.py:272 passes the
+ * PREDICTION there).  group_loss: scratch fp32 [b * n_points]; out1: the scalar loss. */
+int odb_vnl_loss_fwd(const float* first, const float* second, const int32_t* p1, const int32_t* p2,
+                     const int32_t* p3, int32_t n_points, int32_t b, int32_t h, int32_t w, float fx, float fy,
+                     float delta_z, int32_t select, float* out1, float* group_loss, void* stream);
+
 int odb_fill_zero(void* ptr, int64_t bytes, void* stream);
 
 /* Introspection (no GPU needed). */

@@ -79,6 +79,12 @@ _SIGNATURES = {
     "odb_upsample2x_add": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
     "odb_write_cls_row": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p]),
     "odb_readout_cls_bias": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
+    "odb_make_valid_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "odb_midas_loss_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "odb_midas_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "odb_vnl_loss_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_float] * 3 + [C.c_int32, C.c_void_p,
+                                                                                        C.c_void_p, C.c_void_p]),
     "odb_fill_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "odb_abi_version": (C.c_int, []),
     "odb_last_error": (C.c_char_p, []),

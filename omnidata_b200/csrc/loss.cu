@@ -1,0 +1,422 @@
+// Forward kernels of the depth-training losses of omnidata_tools/torch:
+//   * make_valid_mask            train_depth.py:215-242
+//   * MidasLoss.forward          losses/midas_loss.py:137-157  (SSIMAE :33-56,104-111; scale/shift :10-30;
+//                                 4-scale gradient matching :59-100,114-134; masked_l1 losses/masked_losses.py:4-7)
+//   * VNL_Loss.forward           losses/virtual_normal_loss.py:29-194
+// All inputs are fp32 (the reference trains in fp32).  Reductions are deterministic: per-thread fp64
+// partials combined in a fixed shuffle/shared-memory order, medians / order statistics by an exact
+// 4-pass radix select with integer histograms.  Forward only — the backward pass of the train step
+// is the next row of the scope table, not built yet.
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/omnidata_b200.h"
+
+namespace odb {
+
+constexpr int kLossThreads = 1024;
+
+ODB_DEVINL double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// fixed-order block sum (result valid in thread 0)
+ODB_DEVINL double block_sum_d(double v, double* scratch /* [32] shared */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum_d(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0.0;
+    r = warp_sum_d(r);
+  }
+  return r;
+}
+ODB_DEVINL uint32_t sortable_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+ODB_DEVINL float key_to_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Exact k-th smallest (0-based rank) of the selected elements of `vals`; `pred(i)` says whether
+// element i takes part.  Whole block cooperates; returns the key in every thread.
+template <typename Pred>
+ODB_DEVINL uint32_t block_radix_select(const float* vals, long long n, unsigned long long rank, Pred pred,
+                                       uint32_t* hist /* [256] shared */, uint32_t* bcast /* [2] shared */) {
+  uint32_t prefix = 0, himask = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      if (!pred(i)) continue;
+      const uint32_t k = sortable_key(vals[i]);
+      if (((k ^ prefix) & himask) == 0) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long cum = 0;
+      uint32_t d = 0;
+      for (; d < 256; ++d) {
+        if (cum + hist[d] > rank) break;
+        cum += hist[d];
+      }
+      if (d > 255) d = 255;
+      bcast[0] = d;
+      bcast[1] = (uint32_t)cum;
+    }
+    __syncthreads();
+    prefix |= bcast[0] << shift;
+    himask |= 0xFFu << shift;
+    rank -= bcast[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// ------------------------------------------------------------------------------------------ make_valid_mask
+// valid = nearest_upsample(max_pool2d(1 - m, k)) == 0        (train_depth.py:234-238)
+__global__ void __launch_bounds__(256) make_valid_mask_kernel(const float* __restrict__ m,
+                                                              uint8_t* __restrict__ valid, int b, int h,
+                                                              int w, int k) {
+  const int hp = h / k, wp = w / k;
+  const float sy = (float)hp / (float)h, sx = (float)wp / (float)w;   // F.interpolate 'nearest' scale
+  const long long total = (long long)b * h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int bi = (int)(i / ((long long)w * h));
+    const int py = min((int)floorf(y * sy), hp - 1), px = min((int)floorf(x * sx), wp - 1);
+    float mx = -INFINITY;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx)
+        mx = fmaxf(mx, 1.0f - m[((long long)bi * h + py * k + dy) * w + px * k + dx]);
+    valid[i] = (mx == 0.0f) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ MiDaS loss
+struct MidasWs {
+  float* med;      // [2][b]  nanmedian of (pred, target) over valid pixels, 0 if none
+  float* scale;    // [2][b]  mean absolute deviation sum|x - med| / (n_mask + 1)
+  double* sums;    // [b][8]  ssi_abs, n_mask, a00, a01, a11, b0, b1
+  double* grad;    // [b][4][2] (gradient loss, mask count) per scale
+};
+
+// grid (2, b): tensor 0 = prediction, 1 = target.  masked_shift_and_scale (midas_loss.py:33-56)
+__global__ void __launch_bounds__(kLossThreads) midas_median_kernel(const float* __restrict__ pred,
+                                                                    const float* __restrict__ target,
+                                                                    const uint8_t* __restrict__ mask,
+                                                                    MidasWs ws, int b_n, int hw) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bc[2];
+  __shared__ double scratch[32];
+  __shared__ unsigned long long s_n;
+  __shared__ float s_med;
+  const int sel = blockIdx.x, b = blockIdx.y;
+  const float* v = (sel == 0 ? pred : target) + (long long)b * hw;
+  const uint8_t* mk = mask + (long long)b * hw;
+  auto take = [&](long long i) { return mk[i] != 0 && !isnan(v[i]); };
+  // count of non-NaN valid values (integer, deterministic)
+  double cnt = 0.0, nmask = 0.0;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    if (mk[i]) { nmask += 1.0; if (!isnan(v[i])) cnt += 1.0; }
+  }
+  const double tot = block_sum_d(cnt, scratch);
+  const double totm = block_sum_d(nmask, scratch);
+  if (threadIdx.x == 0) s_n = (unsigned long long)tot;
+  __syncthreads();
+  const unsigned long long n = s_n;
+  float med = 0.f;   // t[isnan(t)] = 0
+  if (n > 0) {
+    const uint32_t key = block_radix_select(v, hw, (n - 1) / 2, take, hist, bc);   // lower median
+    med = key_to_float(key);
+  }
+  // mean absolute deviation over the mask:  sum(|x - t| over mask) / (n_mask + 1)
+  double dev = 0.0;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x)
+    if (mk[i]) dev += (double)fabsf(v[i] - med);
+  const double devs = block_sum_d(dev, scratch);
+  if (threadIdx.x == 0) {
+    s_med = med;
+    ws.med[sel * b_n + b] = med;
+    // n_mask is a block_sum_d result valid in thread 0 only: recompute from the shared copy below
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ws.scale[sel * b_n + b] = (float)devs / ((float)totm + 1.0f);
+}
+
+// grid (b): SSIMAE numerator + the five sums of compute_scale_and_shift (midas_loss.py:10-30, :147-151)
+__global__ void __launch_bounds__(kLossThreads) midas_sums_kernel(const float* __restrict__ pred,
+                                                                  const float* __restrict__ target,
+                                                                  const uint8_t* __restrict__ mask,
+                                                                  MidasWs ws, int b_n, int hw) {
+  __shared__ double scratch[32];
+  const int b = blockIdx.x;
+  const float* p = pred + (long long)b * hw;
+  const float* g = target + (long long)b * hw;
+  const uint8_t* mk = mask + (long long)b * hw;
+  const float tp = ws.med[b], tg = ws.med[b_n + b];
+  const float sp = ws.scale[b] + 1e-6f, sg = ws.scale[b_n + b] + 1e-6f;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    if (!mk[i]) continue;
+    const float pv = p[i], gv = g[i];
+    const float pa = (pv - tp) / sp, ga = (gv - tg) / sg;
+    acc[0] += (double)fabsf(pa - ga);
+    acc[1] += 1.0;
+    const float pi = 1.0f / (pv + 1e-6f), ti = 1.0f / (gv + 1e-6f);
+    acc[2] += (double)(pi * pi);
+    acc[3] += (double)pi;
+    acc[4] += 1.0;
+    acc[5] += (double)(pi * ti);
+    acc[6] += (double)ti;
+  }
+  for (int k = 0; k < 7; ++k) {
+    const double r = block_sum_d(acc[k], scratch);
+    if (threadIdx.x == 0) ws.sums[b * 8 + k] = r;
+  }
+}
+
+// grid (scales, b): gradient_loss at stride 2^s on prediction_ssi = scale * 1/(p+eps) + shift
+// (midas_loss.py:83-100, 128-132, 151-153)
+__global__ void __launch_bounds__(kLossThreads) midas_grad_kernel(const float* __restrict__ pred,
+                                                                  const float* __restrict__ target,
+                                                                  const uint8_t* __restrict__ mask,
+                                                                  MidasWs ws, int h, int w) {
+  __shared__ double scratch[32];
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int step = 1 << s;
+  const int hs = (h + step - 1) / step, wsz = (w + step - 1) / step;
+  const long long img = (long long)b * h * w;
+  // closed-form 2x2 solve in fp32 exactly as the reference does it
+  const float a00 = (float)ws.sums[b * 8 + 2], a01 = (float)ws.sums[b * 8 + 3], a11 = (float)ws.sums[b * 8 + 4];
+  const float b0 = (float)ws.sums[b * 8 + 5], b1 = (float)ws.sums[b * 8 + 6];
+  const float det = a00 * a11 - a01 * a01;
+  float x0 = 0.f, x1 = 0.f;
+  if (det != 0.f) {
+    x0 = (a11 * b0 - a01 * b1) / (det + 1e-6f);
+    x1 = (-a01 * b0 + a00 * b1) / (det + 1e-6f);
+  }
+  auto dval = [&](int y, int x, float& m) {
+    const long long i = img + (long long)(y * step) * w + x * step;
+    m = mask[i] ? 1.f : 0.f;
+    const float pssi = x0 * (1.0f / (pred[i] + 1e-6f)) + x1;
+    return m * (pssi - 1.0f / (target[i] + 1e-6f));
+  };
+  double loss = 0.0, cnt = 0.0;
+  const int total = hs * wsz;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int y = i / wsz, x = i - y * wsz;
+    float m0;
+    const float d0 = dval(y, x, m0);
+    cnt += (double)m0;
+    if (x + 1 < wsz) {
+      float m1;
+      const float d1 = dval(y, x + 1, m1);
+      loss += (double)(m1 * m0 * fabsf(d1 - d0));
+    }
+    if (y + 1 < hs) {
+      float m1;
+      const float d1 = dval(y + 1, x, m1);
+      loss += (double)(m1 * m0 * fabsf(d1 - d0));
+    }
+  }
+  const double l = block_sum_d(loss, scratch);
+  const double c = block_sum_d(cnt, scratch);
+  if (threadIdx.x == 0) { ws.grad[(b * 4 + s) * 2] = l; ws.grad[(b * 4 + s) * 2 + 1] = c; }
+}
+
+__global__ void midas_finalize_kernel(MidasWs ws, int b_n, int scales, float alpha, float* __restrict__ out3) {
+  if (threadIdx.x != 0) return;
+  double num = 0.0, den = 0.0;
+  for (int b = 0; b < b_n; ++b) { num += ws.sums[b * 8 + 0]; den += ws.sums[b * 8 + 1]; }
+  const float ssi = (float)(num / den);               // masked_l1_loss: sum / mask.sum()
+  float reg = 0.f;
+  for (int s = 0; s < scales; ++s) {
+    double acc = 0.0;                                  // reduction_image_based: mean_b(loss_b / M_b)
+    for (int b = 0; b < b_n; ++b) {
+      const double l = ws.grad[(b * 4 + s) * 2], m = ws.grad[(b * 4 + s) * 2 + 1];
+      acc += (m != 0.0) ? l / m : l;
+    }
+    reg += (float)(acc / b_n);
+  }
+  out3[1] = ssi;
+  out3[2] = reg;
+  out3[0] = ssi + alpha * reg;
+}
+
+// ------------------------------------------------------------------------------------------ virtual normal loss
+struct Vec3 { float x, y, z; };
+ODB_DEVINL Vec3 sub3(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+ODB_DEVINL float dot3(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+ODB_DEVINL Vec3 cross3(Vec3 a, Vec3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+ODB_DEVINL float comp(Vec3 v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : v.z); }
+
+// thread = (image, point group).  transfer_xyz :44-50, filter_mask :95-128, select_points_groups
+// :130-149, per-group loss :169-188.  loss[i] = NaN for filtered-out groups.
+__global__ void __launch_bounds__(256) vnl_groups_kernel(const float* __restrict__ first,
+                                                         const float* __restrict__ second,
+                                                         const int* __restrict__ p1, const int* __restrict__ p2,
+                                                         const int* __restrict__ p3, float* __restrict__ loss,
+                                                         int b_n, int n_pts, int h, int w, float fx, float fy,
+                                                         float delta_z) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)b_n * n_pts) return;
+  const int b = (int)(gid / n_pts), n = (int)(gid % n_pts);
+  const int idx[3] = {p1[n], p2[n], p3[n]};
+  const float u0 = (float)(w / 2), v0 = (float)(h / 2);
+  Vec3 G[3], D[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int y = idx[j] / w, x = idx[j] - y * w;
+    const float gd = first[(long long)b * h * w + idx[j]];
+    const float dd = second[(long long)b * h * w + idx[j]];
+    G[j] = {((float)x - u0) * fabsf(gd) / fx, ((float)y - v0) * fabsf(gd) / fy, gd};
+    D[j] = {((float)x - u0) * fabsf(dd) / fx, ((float)y - v0) * fabsf(dd) / fy, dd};
+  }
+  // ---- filter_mask on the first argument's points
+  const Vec3 d12 = sub3(G[1], G[0]), d13 = sub3(G[2], G[0]), d23 = sub3(G[2], G[1]);
+  const Vec3 dv[3] = {d12, d13, d23};
+  float nrm[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) nrm[i] = sqrtf(dot3(dv[i], dv[i]));
+  int ncos = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float e = dot3(dv[i], dv[j]) / (nrm[i] * nrm[j] + 1e-8f);
+      ncos += (e > 0.867f || e < -0.867f) ? 1 : 0;
+    }
+  const bool mask_cos = ncos > 3;
+  const bool mask_pad = (G[0].z > delta_z) && (G[1].z > delta_z) && (G[2].z > delta_z);
+  bool near_[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    near_[c] = fabsf(comp(d12, c)) < 0.005f || fabsf(comp(d13, c)) < 0.005f || fabsf(comp(d23, c)) < 0.005f;
+  const bool ignore = (near_[0] && near_[1] && near_[2]) || mask_cos;
+  if (!(mask_pad && !ignore)) { loss[gid] = __int_as_float(0x7fc00000); return; }
+  // ---- reference quirk (:144): the boolean mask z_j == 0 of POINT j indexes the COORDINATE axis, so
+  // coordinate j of all three points of the second argument becomes 1e-4
+  const bool z0[3] = {D[0].z == 0.f, D[1].z == 0.f, D[2].z == 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (z0[0]) D[j].x = 0.0001f;
+    if (z0[1]) D[j].y = 0.0001f;
+    if (z0[2]) D[j].z = 0.0001f;
+  }
+  Vec3 gn = cross3(sub3(G[1], G[0]), sub3(G[2], G[0]));
+  Vec3 dn = cross3(sub3(D[1], D[0]), sub3(D[2], D[0]));
+  float gl = sqrtf(dot3(gn, gn)), dl = sqrtf(dot3(dn, dn));
+  if (gl == 0.f) gl += 0.01f;
+  if (dl == 0.f) dl += 0.01f;
+  loss[gid] = fabsf(gn.x / gl - dn.x / dl) + fabsf(gn.y / gl - dn.y / dl) + fabsf(gn.z / gl - dn.z / dl);
+}
+
+// single block: mean of the losses after dropping the lowest 25 % (:189-193)
+__global__ void __launch_bounds__(kLossThreads) vnl_reduce_kernel(const float* __restrict__ loss, long long n,
+                                                                  int select, float* __restrict__ out) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bc[2];
+  __shared__ double scratch[32];
+  __shared__ double s_vals[2];
+  auto take = [&](long long i) { return !isnan(loss[i]); };
+  double cnt = 0.0, tot = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    if (take(i)) { cnt += 1.0; tot += (double)loss[i]; }
+  const double c = block_sum_d(cnt, scratch);
+  const double t = block_sum_d(tot, scratch);
+  if (threadIdx.x == 0) { s_vals[0] = c; s_vals[1] = t; }
+  __syncthreads();
+  const unsigned long long count = (unsigned long long)s_vals[0];
+  const double total = s_vals[1];
+  const unsigned long long k = select ? (unsigned long long)((double)count * 0.25) : 0ull;
+  if (count == 0) { if (threadIdx.x == 0) out[0] = __int_as_float(0x7fc00000); return; }
+  double dropped = 0.0;
+  if (k > 0) {
+    const uint32_t key = block_radix_select(loss, n, k - 1, take, hist, bc);   // largest dropped value
+    const float thr = key_to_float(key);
+    double below = 0.0, nbelow = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x)
+      if (take(i) && loss[i] < thr) { below += (double)loss[i]; nbelow += 1.0; }
+    const double sb = block_sum_d(below, scratch);
+    const double nb = block_sum_d(nbelow, scratch);
+    if (threadIdx.x == 0) dropped = sb + ((double)k - nb) * (double)thr;
+  }
+  if (threadIdx.x == 0) out[0] = (float)((total - dropped) / (double)(count - k));
+}
+
+}  // namespace odb
+
+using namespace odb;
+
+extern "C" int odb_make_valid_mask(const float* mask_float, uint8_t* mask_valid, int32_t b, int32_t h,
+                                   int32_t w, int32_t pool, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!mask_float || !mask_valid || b < 1 || h < pool || w < pool || pool < 1)
+    return fail(ODB_ERR_INVALID, "make_valid_mask: bad argument");
+  const long long total = (long long)b * h * w;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  make_valid_mask_kernel<<<blocks, 256, 0, stream>>>(mask_float, mask_valid, b, h, w, pool);
+  count_launch();
+  return check_launch("make_valid_mask");
+}
+
+extern "C" int64_t odb_midas_loss_workspace_bytes(int32_t b) {
+  if (b < 1) return -1;
+  return 256 + (int64_t)b * (4 * 4 + 8 * 8 + 8 * 8) + 256;
+}
+
+extern "C" int odb_midas_loss_fwd(const float* prediction, const float* target, const uint8_t* mask,
+                                  int32_t b, int32_t h, int32_t w, float alpha, int32_t scales, float* out3,
+                                  void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!prediction || !target || !mask || !out3 || !workspace || b < 1 || h < 1 || w < 1 || scales < 1 ||
+      scales > 4 || (long long)h * w > 0x7fffffffLL)
+    return fail(ODB_ERR_INVALID, "midas_loss_fwd: bad argument");
+  if (workspace_bytes < odb_midas_loss_workspace_bytes(b) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return fail(ODB_ERR_INVALID, "midas_loss_fwd: workspace too small or not 256-byte aligned");
+  if (!(alpha > 0.f)) return fail(ODB_ERR_INVALID, "midas_loss_fwd: alpha must be > 0 (the reference leaves `total` undefined otherwise)");
+  char* base = static_cast<char*>(workspace);
+  MidasWs ws;
+  ws.sums = reinterpret_cast<double*>(base);
+  ws.grad = ws.sums + (size_t)b * 8;
+  ws.med = reinterpret_cast<float*>(ws.grad + (size_t)b * 8);
+  ws.scale = ws.med + 2 * (size_t)b;
+  const int hw = h * w;
+  midas_median_kernel<<<dim3(2, b), kLossThreads, 0, stream>>>(prediction, target, mask, ws, b, hw);
+  count_launch();
+  midas_sums_kernel<<<b, kLossThreads, 0, stream>>>(prediction, target, mask, ws, b, hw);
+  count_launch();
+  midas_grad_kernel<<<dim3(scales, b), kLossThreads, 0, stream>>>(prediction, target, mask, ws, h, w);
+  count_launch();
+  midas_finalize_kernel<<<1, 32, 0, stream>>>(ws, b, scales, alpha, out3);
+  count_launch();
+  return check_launch("midas_loss_fwd");
+}
+
+extern "C" int odb_vnl_loss_fwd(const float* first, const float* second, const int32_t* p1, const int32_t* p2,
+                                const int32_t* p3, int32_t n_points, int32_t b, int32_t h, int32_t w, float fx,
+                                float fy, float delta_z, int32_t select, float* out1, float* group_loss,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!first || !second || !p1 || !p2 || !p3 || !out1 || !group_loss || n_points < 1 || b < 1 || h < 1 ||
+      w < 1 || fx == 0.f || fy == 0.f)
+    return fail(ODB_ERR_INVALID, "vnl_loss_fwd: bad argument");
+  const long long total = (long long)b * n_points;
+  vnl_groups_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(first, second, p1, p2, p3, group_loss, b,
+                                                                         n_points, h, w, fx, fy, delta_z);
+  count_launch();
+  vnl_reduce_kernel<<<1, kLossThreads, 0, stream>>>(group_loss, total, select, out1);
+  count_launch();
+  return check_launch("vnl_loss_fwd");
+}

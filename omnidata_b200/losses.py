@@ -1,0 +1,107 @@
+"""Depth-training losses of omnidata_tools/torch, forward pass on the GPU (C ABI, csrc/loss.cu).
+
+Same constructor / call signatures as the reference modules (losses/midas_loss.py:137-157,
+losses/virtual_normal_loss.py:7-27,151-194) and the loss mix of train_depth.py:261-279.  FORWARD ONLY:
+the returned tensors carry no autograd graph (the backward of the train step is the next scope row).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _capi.OdbError(f"{name}: CUDA tensor required (no CPU path)")
+    return t.detach().float().contiguous()
+
+
+def make_valid_mask(mask_float: torch.Tensor, max_pool_size: int = 4) -> torch.Tensor:
+    """train_depth.py:215-242 (the 4-D [B,1,H,W] case): bool mask of pixels whose 4x4 cell is fully valid."""
+    if mask_float.dim() == 3:
+        mask_float = mask_float.unsqueeze(0)
+    elif mask_float.dim() == 2:
+        mask_float = mask_float.unsqueeze(0).unsqueeze(0)
+    m = _f32(mask_float, "mask_float")
+    b, c, h, w = m.shape
+    out = torch.empty((b, c, h, w), dtype=torch.uint8, device=m.device)
+    check(lib().odb_make_valid_mask(m.data_ptr(), out.data_ptr(), b * c, h, w, max_pool_size, _stream()),
+          "odb_make_valid_mask")
+    return out.bool()
+
+
+class MidasLoss(torch.nn.Module):
+    def __init__(self, alpha: float = 0.1, scales: int = 4, reduction: str = "image-based"):
+        super().__init__()
+        if reduction != "image-based":
+            raise NotImplementedError("only reduction='image-based' (what train_depth.py uses)")
+        self.alpha, self.scales = float(alpha), int(scales)
+
+    def forward(self, prediction, target, mask):
+        p, g = _f32(prediction, "prediction"), _f32(target, "target")
+        b = p.shape[0]
+        h, w = p.shape[-2:]
+        m = mask.detach().to(torch.uint8).contiguous()
+        ws_bytes = int(lib().odb_midas_loss_workspace_bytes(b))
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=p.device)
+        off = (-ws.data_ptr()) % 256
+        out = torch.empty(3, dtype=torch.float32, device=p.device)
+        check(lib().odb_midas_loss_fwd(p.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, self.alpha, self.scales,
+                                       out.data_ptr(), ws.data_ptr() + off, ws_bytes, _stream()), "odb_midas_loss_fwd")
+        return out[0], out[1], out[2]
+
+
+class VNL_Loss(torch.nn.Module):
+    def __init__(self, focal_x, focal_y, input_size, delta_cos=0.867, delta_diff_x=0.01, delta_diff_y=0.01,
+                 delta_diff_z=0.01, delta_z=0.0001, sample_ratio=0.15):
+        super().__init__()
+        self.fx, self.fy = float(focal_x), float(focal_y)
+        self.input_size = tuple(input_size)
+        self.delta_z, self.sample_ratio = float(delta_z), float(sample_ratio)
+
+    def select_index(self):
+        """Same host NumPy RNG call sequence as the reference (virtual_normal_loss.py:52-72), so that
+        np.random.seed(s) yields the same triplets on both sides; returns flat indices y*W + x."""
+        num = self.input_size[1] * self.input_size[0]
+        pts = []
+        for _ in range(3):
+            p = np.random.choice(num, int(num * self.sample_ratio), replace=True)
+            np.random.shuffle(p)
+            pts.append(p.astype(np.int32))
+        return pts
+
+    def forward(self, gt_depth, pred_depth, select=True, points=None):
+        a, d = _f32(gt_depth, "gt_depth"), _f32(pred_depth, "pred_depth")
+        b = a.shape[0]
+        h, w = a.shape[-2:]
+        if (h, w) != self.input_size:
+            raise ValueError("input size differs from the one given at construction")
+        p1, p2, p3 = points if points is not None else self.select_index()
+        dev = a.device
+        t1, t2, t3 = (torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in (p1, p2, p3))
+        n = t1.numel()
+        scratch = torch.empty(b * n, dtype=torch.float32, device=dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        check(lib().odb_vnl_loss_fwd(a.data_ptr(), d.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(), n, b, h,
+                                     w, self.fx, self.fy, self.delta_z, 1 if select else 0, out.data_ptr(),
+                                     scratch.data_ptr(), _stream()), "odb_vnl_loss_fwd")
+        return out[0]
+
+
+def depth_step_losses(depth_preds, depth_gt, mask_float, midas: MidasLoss, vnl: VNL_Loss, train: bool = True,
+                      global_step: int = 10 ** 9):
+    """The loss arithmetic of Depth._shared_step (train_depth.py:261-287), forward only."""
+    depth_preds = torch.clamp(depth_preds, 0, 1)
+    mask_valid = make_valid_mask(mask_float)
+    _, ssi, reg = midas(depth_preds, depth_gt, mask_valid)
+    vn = vnl(depth_preds, depth_gt)               # NB: reference passes (pred, gt) into (gt_depth, pred_depth)
+    if train and global_step < 15000:
+        return {"ssi_loss": ssi, "reg_loss": 0, "vn_loss": 0, "depth_loss": ssi}
+    return {"ssi_loss": ssi, "reg_loss": reg, "vn_loss": vn, "depth_loss": ssi + 0.1 * reg + 10 * vn}

@@ -81,17 +81,16 @@ def main():
                "taps": {k: summarize(k, v) for k, v in sorted(taps.items())}}
         torch.save(rec, GOLDEN / f"dpt_fp32_seed0_c{c}.pt")
         print(f"c={c}: output mean {rec['output_mean']:.6f}, taps {sorted(taps)}")
-    # ---- losses (reference modules, unmodified)
+    # ---- losses (reference modules, unmodified) on the seeded train-step tensors of loss_oracle.loss_inputs
+    from . import loss_oracle
     MidasLoss, VNL_Loss = rl.load_reference_losses()
-    g = torch.Generator().manual_seed(0)
-    pred = torch.rand(2, 1, 384, 384, generator=g)
-    gt = torch.rand(2, 1, 384, 384, generator=g)
-    mask = torch.rand(2, 1, 384, 384, generator=g) > 0.1
+    pred, gt, mf = loss_oracle.loss_inputs(0)
+    mask = loss_oracle.make_valid_mask(mf)          # train_depth.py cannot be imported (PL, kornia): restated
     total, ssi, reg = MidasLoss(alpha=0.1, scales=4, reduction="image-based")(pred, gt, mask)
     np.random.seed(0)
     vnl = VNL_Loss(1.0, 1.0, (384, 384))(pred, gt)
-    torch.save({"midas_total": float(total), "midas_ssi": float(ssi), "midas_reg": float(reg), "vnl": float(vnl)},
-               GOLDEN / "losses_seed0.pt")
+    torch.save({"midas_total": float(total), "midas_ssi": float(ssi), "midas_reg": float(reg), "vnl": float(vnl),
+                "mask_valid_count": int(mask.sum())}, GOLDEN / "losses_seed0.pt")
     print("losses", float(total), float(ssi), float(reg), float(vnl))
 
 

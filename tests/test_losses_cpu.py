@@ -1,0 +1,44 @@
+"""The loss restatement (oracle/loss_oracle.py) against the UNMODIFIED reference loss modules (build
+container only) and against the committed golden values (any box)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_oracle, reference_loader
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def test_loss_oracle_matches_golden():
+    rec = torch.load(GOLDEN / "losses_seed0.pt")
+    pred, gt, mf = loss_oracle.loss_inputs(0)
+    mask = loss_oracle.make_valid_mask(mf)
+    total, ssi, reg = loss_oracle.midas_loss(pred, gt, mask)
+    assert abs(float(total) - rec["midas_total"]) <= 2e-5 * abs(rec["midas_total"])
+    assert abs(float(ssi) - rec["midas_ssi"]) <= 2e-5 * abs(rec["midas_ssi"])
+    assert abs(float(reg) - rec["midas_reg"]) <= 2e-5 * abs(rec["midas_reg"])
+    np.random.seed(0)
+    pts = loss_oracle.vnl_select_index(384, 384)
+    vn = loss_oracle.vnl_loss(pred, gt, pts)
+    assert abs(float(vn) - rec["vnl"]) <= 2e-5 * abs(rec["vnl"])
+    assert int(mask.sum()) == rec["mask_valid_count"]
+
+
+@pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree not on this box")
+def test_loss_oracle_equals_unmodified_reference():
+    MidasLoss, VNL_Loss = reference_loader.load_reference_losses()
+    for seed in (1, 2):
+        pred, gt, mf = loss_oracle.loss_inputs(seed)
+        mask = loss_oracle.make_valid_mask(mf)
+        ref = MidasLoss(alpha=0.1, scales=4, reduction="image-based")(pred, gt, mask)
+        mine = loss_oracle.midas_loss(pred, gt, mask)
+        for a, b in zip(ref, mine):
+            assert abs(float(a) - float(b)) <= 1e-6 * abs(float(a))
+        np.random.seed(seed)
+        ref_v = VNL_Loss(1.0, 1.0, (384, 384))(pred, gt)
+        np.random.seed(seed)
+        pts = loss_oracle.vnl_select_index(384, 384)
+        mine_v = loss_oracle.vnl_loss(pred, gt, pts)
+        assert abs(float(ref_v) - float(mine_v)) <= 1e-6 * abs(float(ref_v))
