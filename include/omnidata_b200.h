@@ -85,7 +85,8 @@ typedef struct odb_conv_gemm_desc {
   int32_t block_n;        /* N tile: 256, 128, 64 (32 with the head tail); 0 = auto */
   int32_t cta_pair;       /* tcgen05 cta_group::2 (two SMs per 256-row tile): 0 = auto, 1 = on, -1 = off */
   int32_t halo;           /* 3x3 stride-1 pad-1 convs: load one halo tile per K block and address the nine
-                           * taps inside it (3x less input traffic): 0 = auto (n <= 64), 1 = on, -1 = off */
+                           * taps inside it (3x less input traffic): 0 = auto (currently off: the deeper per-tap ring measured
+                           * faster on every layer of this network), 1 = on, -1 = off */
   /* Fused DPT head tail (M/dpt_depth.py:93-97): only with n == 32.  When head_out != NULL the
    * 32-channel result relu(v + bias) is not stored; instead
    *   head_out[b][k][y][x] = relu?(head_b[k] + sum_j head_w[k][j] * relu(v_j + bias_j))  (fp32, NCHW) */

@@ -115,7 +115,7 @@ ODB_DEVINL void gn_warp_partials(const float* v, int lane, float* dst /* [groups
 // (r / (tile_w+2), r % (tile_w+2)); the two junk columns per halo row are masked in the epilogue.
 // L2 -> smem traffic for A drops from 9 x 16 KiB to <= 49 KiB per K block.  The weights keep their
 // own (tap, K block) ring.
-constexpr int kHaloAutoMaxN = 64;            // wider outputs are MMA / weight-traffic bound: per-tap boxes win
+constexpr int kHaloAutoMaxN = 0;             // measured: per-tap boxes (deeper ring) win on every layer of this net, halo stays opt-in
 constexpr int kHaloStageBytes = 49 * 1024;   // >= 390 rows x 128 B (tile_w = 128, tile_h = 1)
 
 template <int BLOCK_N, int STAGES, int NSTAGING, bool PAIR, bool HALO, bool HEAD>
@@ -669,7 +669,6 @@ static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
     if (!is_canonical_3x3(d)) return fail(ODB_ERR_INVALID, "conv_gemm: halo mode needs a 3x3 stride-1 pad-1 conv");
     halo = true;
   } else if (d->halo == 0) {
-    // automatic only where the per-tap scheme is bound by input re-reads: narrow outputs
     halo = is_canonical_3x3(d) && (tw <= 0 || th <= 0) && d->n <= kHaloAutoMaxN;
   }
   if (halo && (tw <= 0 || th <= 0)) {

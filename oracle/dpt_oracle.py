@@ -183,8 +183,8 @@ def _attention_online_bf16(q, k, v, chunk: int = 64):
     scale_log2e = float(torch.tensor(0.125, dtype=torch.float32) * torch.tensor(1.4426950408889634, dtype=torch.float32))
     n = q.shape[-2]
     o = torch.zeros_like(q)
-    m = torch.full(q.shape[:-1], float("-inf"), dtype=q.dtype)
-    l = torch.zeros(q.shape[:-1], dtype=q.dtype)
+    m = torch.full(q.shape[:-1], float("-inf"), dtype=q.dtype, device=q.device)
+    l = torch.zeros(q.shape[:-1], dtype=q.dtype, device=q.device)
     for c0 in range(0, n, chunk):
         s_ = (q @ k[..., c0:c0 + chunk, :].transpose(-2, -1)) * scale_log2e
         m_new = torch.maximum(m, s_.amax(dim=-1))
