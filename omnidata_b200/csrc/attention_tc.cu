@@ -12,7 +12,8 @@
 // pass 2 re-computes them (the tensor pipe is far from saturated), writes P = exp2(s*c - m*c) as
 // bf16 straight into the K-major UMMA operand layout in shared memory and accumulates the fp32 row
 // sum of the unrounded P.  O therefore never needs rescaling and lives in TMEM until the epilogue.
-// TMEM: S double-buffered in columns [0,256), O in [256,320).
+// TMEM: S triple-buffered in columns [0,384) (the MMA warp runs up to two S blocks ahead of the
+// softmax warps, which hides the commit -> mbarrier -> tcgen05.ld hand-off latency), O in [384,448).
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/omnidata_b200.h"
@@ -31,7 +32,8 @@ constexpr int kTcOffQ = 2 * kTcMaxBlocks * kTcTileBytes;
 constexpr int kTcOffP = kTcOffQ + 2 * kTcTileBytes;
 constexpr int kTcOffX = kTcOffP + 2 * kTcTileBytes;          // fp32 exchange [2 halves][128 rows] (max, then sum)
 constexpr int kTcOffBar = kTcOffX + 2 * 128 * 4;
-constexpr int kTcSmemBytes = kTcOffBar + 128 + 1024;
+constexpr int kTcSmemBytes = kTcOffBar + 144 + 1024;
+static_assert(kTcSmemBytes <= 232448, "attention smem plan exceeds 227 KiB");
 
 struct AttnTcParams {
   CUtensorMap qkv_map;   // dims {64 d, 3*heads, tokens, batch}; box {64, 1, 128, 1}
@@ -59,11 +61,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   const uint32_t kv_full = bar0, kv_empty = bar0 + 8;
   auto q_full = [&](int i) { return bar0 + 16u + 8u * i; };
   auto q_empty = [&](int i) { return bar0 + 32u + 8u * i; };
-  auto s_full = [&](int i) { return bar0 + 48u + 8u * i; };
-  auto s_empty = [&](int i) { return bar0 + 64u + 8u * i; };
-  const uint32_t p_full = bar0 + 80, p_empty = bar0 + 88, o_full = bar0 + 96, o_empty = bar0 + 104;
-  const uint32_t tmem_slot = bar0 + 112;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + kTcOffBar + 112);
+  auto s_full = [&](int i) { return bar0 + 48u + 8u * i; };    // 3 buffers
+  auto s_empty = [&](int i) { return bar0 + 72u + 8u * i; };   // 3 buffers
+  const uint32_t p_full = bar0 + 96, p_empty = bar0 + 104, o_full = bar0 + 112, o_empty = bar0 + 120;
+  const uint32_t tmem_slot = bar0 + 128;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + kTcOffBar + 128);
+  constexpr uint32_t kOCol = 3 * kTcBlk;                       // first TMEM column of O
   // one exchange array serves the row maxima and later the row sums: a thread can only reach its
   // row-sum write after every thread has arrived on p_full for block 0, i.e. after it read the maxima
   float* xmax = reinterpret_cast<float*>(gen_base + kTcOffX);
@@ -75,10 +78,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1);
-      mbar_init(s_full(i), 1); mbar_init(s_empty(i), 8);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 8); }
     mbar_init(p_full, kTcSoftmaxThreads); mbar_init(p_empty, 1);
     mbar_init(o_full, 1); mbar_init(o_empty, 8);
     mbar_fence_init();
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(kTcBlk, 64);
       uint32_t u_iter = 0, qt_iter = 0, sb_iter = 0, p_iter = 0;
       auto issue_s = [&](int j, int qb) {
-        const uint32_t sbuf = sb_iter & 1u;
-        mbar_wait(s_empty(sbuf), ((sb_iter >> 1) & 1u) ^ 1u);
+        const uint32_t sbuf = sb_iter % 3u;
+        mbar_wait(s_empty(sbuf), ((sb_iter / 3u) & 1u) ^ 1u);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(sbase + kTcOffQ + qb * kTcTileBytes);
         const uint64_t bdesc = umma_desc_sw128(sbase + kTcOffK + j * kTcTileBytes);
@@ -138,10 +139,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
           const int qb = qt_iter & 1u;
           mbar_wait(q_full(qb), (qt_iter >> 1) & 1u);
           tc_fence_after();
-          for (int j = 0; j < nblk; ++j) issue_s(j, qb);          // pass 1 (row maxima)
-          issue_s(0, qb);                                         // pass 2, one block of lookahead
+          // S blocks of this tile in issue order: pass 1 (row maxima) then pass 2 (probabilities);
+          // the issuer keeps up to two blocks ahead of what the softmax warps / the PV MMAs need
+          int next_s = 0;
+          auto pump = [&](int upto) {
+            const int lim = upto < 2 * nblk ? upto : 2 * nblk;
+            for (; next_s < lim; ++next_s) issue_s(next_s < nblk ? next_s : next_s - nblk, qb);
+          };
+          pump(nblk + 2);
           for (int j = 0; j < nblk; ++j) {
-            if (j + 1 < nblk) issue_s(j + 1, qb);
+            pump(nblk + j + 3);
             mbar_wait(p_full, p_iter & 1u);
             tc_fence_after();
             if (j == 0) {                                         // the epilogue has drained the previous O
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
               const uint64_t adesc =
                   umma_desc_sw128(sbase + kTcOffP + (kk >> 2) * kTcTileBytes) + 2u * (kk & 3);
               const uint64_t bdesc = umma_desc_sw128(sbase + kTcOffV + j * kTcTileBytes + kk * 2048);
-              umma_bf16_ss(tmem_base + 256, adesc, bdesc, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+              umma_bf16_ss(tmem_base + kOCol, adesc, bdesc, idesc_pv, (j | kk) != 0 ? 1u : 0u);
             }
             umma_commit(p_empty);
             ++p_iter;
@@ -179,8 +186,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         // ---- pass 1: row maximum over all valid keys
         float mx = -INFINITY;
         for (int j = 0; j < nblk; ++j, ++sb_iter) {
-          const uint32_t sbuf = sb_iter & 1u;
-          mbar_wait(s_full(sbuf), (sb_iter >> 1) & 1u);
+          const uint32_t sbuf = sb_iter % 3u;
+          mbar_wait(s_full(sbuf), (sb_iter / 3u) & 1u);
           tc_fence_after();
           uint32_t r[64];
           tmem_ld_32x32(t_lane + sbuf * kTcBlk + half * 64, r);
@@ -206,8 +213,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         // ---- pass 2: P = exp2(s*c - m*c) -> bf16 operand tile in smem, fp32 row sum
         float l = 0.f;
         for (int j = 0; j < nblk; ++j, ++sb_iter, ++p_iter) {
-          const uint32_t sbuf = sb_iter & 1u;
-          mbar_wait(s_full(sbuf), (sb_iter >> 1) & 1u);
+          const uint32_t sbuf = sb_iter % 3u;
+          mbar_wait(s_full(sbuf), (sb_iter / 3u) & 1u);
           tc_fence_after();
           uint32_t r[64];
           tmem_ld_32x32(t_lane + sbuf * kTcBlk + half * 64, r);
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         mbar_wait(o_full, qt_iter & 1u);
         tc_fence_after();
         uint32_t o[32];
-        tmem_ld_32x32(t_lane + 256 + half * 32, o);
+        tmem_ld_32x32(t_lane + kOCol + half * 32, o);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
