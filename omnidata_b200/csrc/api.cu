@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "host_util.h"
 #include "../../include/omnidata_b200.h"
@@ -28,6 +29,15 @@ int check_launch(const char* where) {
   return ODB_OK;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ODB_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int num_sms() {
   static int sms = 0;

@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  grid_dep_wait();
+  grid_dep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -317,7 +319,8 @@ extern "C" int odb_attention(const void* qkv, void* out, int32_t b, int32_t toke
   }
   const int units = b * heads;
   const int grid = units < num_sms() ? units : num_sms();
-  attention_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(p);
+  cudaError_t le = launch_pdl(attention_tc_kernel, dim3(grid), dim3(kTcThreads), kTcSmemBytes, stream, p);
   count_launch();
+  if (le != cudaSuccess) return fail_cuda(le, "attention_tc: launch");
   return check_launch("attention_tc");
 }

@@ -60,6 +60,13 @@ ODB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every forward-path kernel is launched with programmaticStreamSerialization: it may start (and run
+// its prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous kernel of the
+// stream drains.  grid_dep_wait() must precede the first access to global memory.
+ODB_DEVINL void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+ODB_DEVINL void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- fences / named barriers
 ODB_DEVINL void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -197,6 +197,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above overlapped the tail of the previous kernel (programmatic dependent launch)
+  grid_dep_wait();
+  grid_dep_launch();
 
   // work units: (n tile, m tile) for a single CTA, (n tile, pair of m tiles) for a CTA pair
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
@@ -602,16 +605,19 @@ static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_
   const int sms = num_sms();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (PAIR) {
     const long long pairs = units < sms / 2 ? units : sms / 2;
     cfg.gridDim = dim3((unsigned)(2 * pairs));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
   } else {
     cfg.gridDim = dim3((unsigned)(units < sms ? units : sms));
   }

@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace odb {
 
@@ -18,5 +19,25 @@ int num_sms();
 int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, int rank, void* base,
                  const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
                  const cuuint32_t* elem_strides, CUtensorMapSwizzle swizzle);
+
+bool pdl_enabled();
+
+// Launch with programmatic dependent launch allowed (the kernel must call grid_dep_wait()).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace odb

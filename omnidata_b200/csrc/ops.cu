@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
                                                         const float* __restrict__ beta,
                                                         bf16* __restrict__ y, long long rows,
                                                         float eps) {
+  grid_dep_wait();
+  grid_dep_launch();
   constexpr int COLS = VPL * 256;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -163,6 +165,8 @@ __global__ void __launch_bounds__(1024) groupnorm_finalize_kernel(const float* _
                                                                   float* __restrict__ stats,
                                                                   int rows, int groups, double count,
                                                                   float eps) {
+  grid_dep_wait();
+  grid_dep_launch();
   const int b = blockIdx.x;
   const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= groups) return;
@@ -210,6 +214,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
     const float* __restrict__ beta, const bf16* __restrict__ res,
     const float* __restrict__ res_stats, const float* __restrict__ res_gamma,
     const float* __restrict__ res_beta, bf16* __restrict__ y, int hw, int c, int groups, int relu) {
+  grid_dep_wait();
+  grid_dep_launch();
   extern __shared__ float coef[];  // [c] scale, [c] shift, then [c] shortcut scale (shift is folded)
   const int b = blockIdx.y;
   const int octets = c >> 3;
@@ -292,6 +298,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
 __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
     const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ beta, bf16* __restrict__ y, int h, int w, int c, int groups) {
+  grid_dep_wait();
+  grid_dep_launch();
   extern __shared__ float coef[];  // [c] scale, [c] shift
   const int b = blockIdx.y;
   const int octets = c >> 3;
@@ -339,6 +347,8 @@ __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x,
                                                           bf16* __restrict__ cols, int b, int h,
                                                           int w, int kpad) {
+  grid_dep_wait();
+  grid_dep_launch();
   const int oh = h / 2, ow = w / 2;
   const int groups8 = kpad >> 3;
   const int oy = blockIdx.x % oh, bi = blockIdx.x / oh;   // one block per output row
@@ -376,6 +386,8 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
                                                              bf16* __restrict__ out,
                                                              bf16* __restrict__ out_relu, int h, int w,
                                                              int c) {
+  grid_dep_wait();
+  grid_dep_launch();
   const int oh = 2 * h, ow = 2 * w;
   const int ox = blockIdx.x * blockDim.y + threadIdx.y;
   if (ox >= ow) return;
@@ -415,6 +427,8 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
 
 __global__ void write_cls_row_kernel(bf16* __restrict__ tokens, const float* __restrict__ cls,
                                      const float* __restrict__ pos0, int tokens_n, int c) {
+  grid_dep_wait();
+  grid_dep_launch();
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < c; i += blockDim.x)
     tokens[(long long)b * tokens_n * c + i] = __float2bfloat16_rn(cls[i] + pos0[i]);
@@ -426,6 +440,8 @@ __global__ void __launch_bounds__(256) readout_cls_bias_kernel(const bf16* __res
                                                                const bf16* __restrict__ tokens,
                                                                float* __restrict__ out, int b_n,
                                                                int tokens_n, int c) {
+  grid_dep_wait();
+  grid_dep_launch();
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)b_n * c) return;
@@ -466,10 +482,10 @@ extern "C" int odb_layernorm(const void* x, const float* gamma, const float* bet
   const bf16* xp = static_cast<const bf16*>(x);
   bf16* yp = static_cast<bf16*>(y);
   switch (cols) {
-    case 256: layernorm_kernel<1><<<grid, 256, 0, stream>>>(xp, gamma, beta, yp, rows, eps); break;
-    case 512: layernorm_kernel<2><<<grid, 256, 0, stream>>>(xp, gamma, beta, yp, rows, eps); break;
-    case 768: layernorm_kernel<3><<<grid, 256, 0, stream>>>(xp, gamma, beta, yp, rows, eps); break;
-    case 1024: layernorm_kernel<4><<<grid, 256, 0, stream>>>(xp, gamma, beta, yp, rows, eps); break;
+    case 256: launch_pdl(layernorm_kernel<1>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
+    case 512: launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
+    case 768: launch_pdl(layernorm_kernel<3>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
+    case 1024: launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
     default: return fail(ODB_ERR_UNSUPPORTED, "layernorm: cols must be 256/512/768/1024");
   }
   count_launch();
@@ -524,8 +540,8 @@ extern "C" int odb_groupnorm_finalize(const float* partial, float* stats, int32_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!partial || !stats || b < 1 || rows_per_image < 1 || groups < 1 || groups > 32 || count <= 0)
     return fail(ODB_ERR_INVALID, "groupnorm_finalize: bad argument");
-  groupnorm_finalize_kernel<<<b, 32 * groups, 0, stream>>>(partial, stats, rows_per_image, groups,
-                                                           count, eps);
+  launch_pdl(groupnorm_finalize_kernel, dim3(b), dim3(32 * groups), 0, stream, partial, stats,
+             rows_per_image, groups, count, eps);
   count_launch();
   return check_launch("groupnorm_finalize");
 }
@@ -543,9 +559,9 @@ extern "C" int odb_groupnorm_apply(const void* x, const float* stats, const floa
   int gx = grid_for((long long)hw * (c / 8), 256) / b;
   if (gx < 1) gx = 1;
   dim3 grid(gx, b);
-  groupnorm_apply_kernel<<<grid, 256, 3 * c * sizeof(float), stream>>>(
-      static_cast<const bf16*>(x), stats, gamma, beta, static_cast<const bf16*>(res), res_stats,
-      res_gamma, res_beta, static_cast<bf16*>(y), hw, c, groups, relu);
+  launch_pdl(groupnorm_apply_kernel, grid, dim3(256), 3 * c * sizeof(float), stream,
+             static_cast<const bf16*>(x), stats, gamma, beta, static_cast<const bf16*>(res), res_stats,
+             res_gamma, res_beta, static_cast<bf16*>(y), hw, c, groups, relu);
   count_launch();
   return check_launch("groupnorm_apply");
 }
@@ -560,8 +576,8 @@ extern "C" int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const
   int gx = grid_for((long long)(h / 2) * (w / 2) * (c / 8), 256) / b;
   if (gx < 1) gx = 1;
   dim3 grid(gx, b);
-  stem_gn_relu_maxpool_kernel<<<grid, 256, 2 * c * sizeof(float), stream>>>(
-      static_cast<const bf16*>(x), stats, gamma, beta, static_cast<bf16*>(y), h, w, c, groups);
+  launch_pdl(stem_gn_relu_maxpool_kernel, grid, dim3(256), 2 * c * sizeof(float), stream,
+             static_cast<const bf16*>(x), stats, gamma, beta, static_cast<bf16*>(y), h, w, c, groups);
   count_launch();
   return check_launch("stem_gn_relu_maxpool");
 }
@@ -571,7 +587,8 @@ extern "C" int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !cols || b < 1 || h < 2 || w < 2 || (h & 1) || (w & 1) || kpad < 152 || kpad % 8)
     return fail(ODB_ERR_INVALID, "stem_im2col: bad argument");
-  stem_im2col_kernel<<<b * (h / 2), 256, 0, stream>>>(x, static_cast<bf16*>(cols), b, h, w, kpad);
+  launch_pdl(stem_im2col_kernel, dim3(b * (h / 2)), dim3(256), 0, stream, x, static_cast<bf16*>(cols), b, h, w,
+             kpad);
   count_launch();
   return check_launch("stem_im2col");
 }
@@ -587,9 +604,8 @@ extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, voi
   const int pix = 256 / octets;
   dim3 block(octets, pix);
   dim3 grid((2 * w + pix - 1) / pix, 2 * h, b);
-  upsample2x_add_kernel<<<grid, block, 0, stream>>>(
-      static_cast<const bf16*>(z), static_cast<const bf16*>(res), static_cast<bf16*>(out),
-      static_cast<bf16*>(out_relu), h, w, c);
+  launch_pdl(upsample2x_add_kernel, grid, block, 0, stream, static_cast<const bf16*>(z),
+             static_cast<const bf16*>(res), static_cast<bf16*>(out), static_cast<bf16*>(out_relu), h, w, c);
   count_launch();
   return check_launch("upsample2x_add");
 }
@@ -599,7 +615,8 @@ extern "C" int odb_write_cls_row(void* tokens, const float* cls, const float* po
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!tokens || !cls || !pos0 || b < 1 || tokens_n < 1 || c < 1)
     return fail(ODB_ERR_INVALID, "write_cls_row: bad argument");
-  write_cls_row_kernel<<<b, 256, 0, stream>>>(static_cast<bf16*>(tokens), cls, pos0, tokens_n, c);
+  launch_pdl(write_cls_row_kernel, dim3(b), dim3(256), 0, stream, static_cast<bf16*>(tokens), cls, pos0,
+             tokens_n, c);
   count_launch();
   return check_launch("write_cls_row");
 }
@@ -611,9 +628,8 @@ extern "C" int odb_readout_cls_bias(const void* w, const float* bias, const void
     return fail(ODB_ERR_INVALID, "readout_cls_bias: bad argument");
   const long long warps = (long long)b * c;
   const unsigned grid = (unsigned)((warps + 7) / 8);
-  readout_cls_bias_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(w), bias,
-                                                    static_cast<const bf16*>(tokens), out, b,
-                                                    tokens_n, c);
+  launch_pdl(readout_cls_bias_kernel, dim3(grid), dim3(256), 0, stream, static_cast<const bf16*>(w), bias,
+             static_cast<const bf16*>(tokens), out, b, tokens_n, c);
   count_launch();
   return check_launch("readout_cls_bias");
 }
