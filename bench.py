@@ -275,16 +275,17 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
 
         # ---------------- timed region 2: end to end through the public API, host buffers
-        host_out = torch.empty((B, IMG, IMG), dtype=torch.float32).pin_memory()
-        for i in range(2):
-            host_out.copy_(model(host_inputs[i % 4].to(dev, non_blocking=True)), non_blocking=True)
+        # StreamingPredictor.run = DPTDepthModel.forward per batch, with the pinned-host -> device copy
+        # of the next batch and the device -> host read of the previous depth maps on copy streams.
+        from omnidata_b200.pipeline import StreamingPredictor
+        predictor = StreamingPredictor(model, dev)
+        host_outs = [torch.empty((B, IMG, IMG), dtype=torch.float32).pin_memory() for _ in range(2)]
+        predictor.run((host_inputs[i % 4] for i in range(3)), host_outs)
         torch.cuda.synchronize()
         parallel.barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        for i in range(args.steps):
-            xin = host_inputs[i % 4].to(dev, non_blocking=True)          # H2D from pinned memory
-            host_out.copy_(model(xin), non_blocking=True)                # D2H of the depth maps
+        predictor.run((host_inputs[i % 4] for i in range(args.steps)), host_outs)
         e3.record()
         torch.cuda.synchronize()
         parallel.barrier()

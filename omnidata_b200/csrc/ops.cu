@@ -23,8 +23,9 @@ ODB_DEVINL void store8(bf16* p, const float* v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, the row lives in registers (cols <= 1024 -> <= 4 vectors / lane).
-template <int VPL>  // 16-byte vectors per lane; cols = VPL * 256
+// LayerNorm: each warp normalises TWO rows held in registers (cols <= 1024 -> <= 4 vectors per lane
+// and row), so six to eight 16-byte loads are in flight per lane before the first reduction.
+template <int VPL>  // 16-byte vectors per lane and row; cols = VPL * 256
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
@@ -34,41 +35,50 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   grid_dep_launch();
   constexpr int COLS = VPL * 256;
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const bf16* xr = x + row * COLS;
-  float v[VPL][8];
-  float s = 0.f;
+  const long long row0 = 2 * ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (row0 >= rows) return;
+  const bool two = row0 + 1 < rows;
+  float v[2][VPL][8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    load8(xr + (i * 32 + lane) * 8, v[i]);
+  for (int r = 0; r < 2; ++r) {
+    if (r == 1 && !two) break;
+    const bf16* xr = x + (row0 + r) * COLS;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[i][j];
+    for (int i = 0; i < VPL; ++i) load8(xr + (i * 32 + lane) * 8, v[r][i]);
   }
-  const float mean = warp_sum(s) * (1.0f / COLS);
-  float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i)
+  for (int r = 0; r < 2; ++r) {
+    if (r == 1 && !two) break;
+    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float d = v[i][j] - mean;
-      q += d * d;
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[r][i][j];
+    const float mean = warp_sum(s) * (1.0f / COLS);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[r][i][j] - mean;
+        q += d * d;
+      }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / COLS) + eps);
+    bf16* yr = y + (row0 + r) * COLS;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c0 = (i * 32 + lane) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[r][i][j] - mean) * rstd * g[j] + bb[j];
+      store8(yr + c0, o);
     }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / COLS) + eps);
-  bf16* yr = y + row * COLS;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c0 = (i * 32 + lane) * 8;
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + bb[j];
-    store8(yr + c0, o);
   }
 }
 
@@ -477,8 +487,8 @@ extern "C" int odb_layernorm(const void* x, const float* gamma, const float* bet
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !gamma || !beta || !y || rows < 0) return fail(ODB_ERR_INVALID, "layernorm: bad argument");
   if (rows == 0) return ODB_OK;
-  const int wpb = 8;
-  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const int rpb = 16;   // 8 warps x 2 rows
+  const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
   const bf16* xp = static_cast<const bf16*>(x);
   bf16* yp = static_cast<bf16*>(y);
   switch (cols) {

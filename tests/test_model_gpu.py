@@ -139,3 +139,23 @@ def test_batch_independence(setup):
     torch.cuda.synchronize()
     model.keep_taps = True
     assert torch.equal(y1, y2[1:])                          # bit-identical regardless of batch size
+
+
+def test_streaming_predictor_matches_direct_forward(setup):
+    """Host-buffer pipeline (copy streams + events) returns exactly what forward() returns."""
+    from omnidata_b200.pipeline import StreamingPredictor
+    r = setup[1]
+    model = r["model"]
+    model.keep_taps = False
+    model.use_cuda_graph = True
+    xs = [r["x"].clone().pin_memory(), r["x"].flip(0).clone().pin_memory(), (r["x"] * 0.5).pin_memory()]
+    outs = [torch.empty(2, 384, 384).pin_memory() for _ in range(3)]
+    pred = StreamingPredictor(model, torch.device("cuda:0"))
+    n = pred.run(iter(xs), outs)
+    torch.cuda.synchronize()
+    assert n == 3
+    with torch.no_grad():
+        for x, o in zip(xs, outs):
+            assert torch.equal(model(x.cuda()).cpu(), o)
+    model.use_cuda_graph = False
+    model.keep_taps = True
