@@ -119,6 +119,10 @@ int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y,
  * for the PV product, fp32 row sum of the unrounded P.  tokens <= 640. */
 int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
                   void* stream);
+/* Same contract and arithmetic as odb_attention, organised as two independent groups per CTA working
+ * on alternate query tiles ("ping-pong", 64-key blocks) to hide the MMA <-> softmax hand-off latency. */
+int odb_attention_pp(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
+                     void* stream);
 /* Same contract on the legacy mma.sync path (flash-style online softmax over 64-key chunks); kept
  * for A/B comparison only. */
 int odb_attention_mma(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,

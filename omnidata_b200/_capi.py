@@ -67,6 +67,8 @@ _SIGNATURES = {
                                 C.c_float, C.c_void_p]),
     "odb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p]),
+    "odb_attention_pp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                   C.c_void_p]),
     "odb_attention_mma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_void_p]),
     "odb_groupnorm_scratch_bytes": (C.c_int64, [C.c_int32] * 4),

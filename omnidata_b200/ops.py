@@ -208,12 +208,18 @@ def layernorm(x, gamma, beta, out, eps: float = 1e-6):
                               x.shape[-1], eps, _stream())
 
 
-def attention(qkv, out, heads: int = 12, scale: float = 0.125, impl: str = "tc"):
+import os as _os
+
+ATTENTION_IMPL = _os.environ.get("ODB_ATTENTION", "tc")   # "tc" | "pp" (ping-pong) | "mma" (legacy)
+
+
+def attention(qkv, out, heads: int = 12, scale: float = 0.125, impl: Optional[str] = None):
+    impl = impl or ATTENTION_IMPL
     _need(qkv, torch.bfloat16, "qkv"); _need(out, torch.bfloat16, "out")
     b, n, c3 = qkv.shape
     if not (qkv.is_contiguous() and out.is_contiguous()) or c3 != 3 * heads * 64:
         raise _capi.OdbError("attention: qkv must be contiguous [B, tokens, 3*heads*64]")
-    _call("odb_attention", {"flops": 4.0 * b * heads * n * n * 64, "bytes": 2 * (qkv.numel() + out.numel())}, lib().odb_attention if impl == "tc" else lib().odb_attention_mma, qkv.data_ptr(), out.data_ptr(), b, n,
+    _call("odb_attention", {"flops": 4.0 * b * heads * n * n * 64, "bytes": 2 * (qkv.numel() + out.numel())}, {"tc": lib().odb_attention, "pp": lib().odb_attention_pp, "mma": lib().odb_attention_mma}[impl], qkv.data_ptr(), out.data_ptr(), b, n,
           heads, scale, _stream())
 
 

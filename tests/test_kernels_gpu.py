@@ -286,7 +286,7 @@ def test_layernorm():
     check(out, F.layer_norm(x.float(), (768,), g, bta, 1e-6), "layernorm")
 
 
-@pytest.mark.parametrize("impl", ["tc", "mma"])
+@pytest.mark.parametrize("impl", ["tc", "pp", "mma"])
 @pytest.mark.parametrize("b,tokens", [(2, 577), (1, 64), (1, 100), (13, 257), (33, 577)])
 def test_attention(b, tokens, impl):
     o = ops()
@@ -300,7 +300,7 @@ def test_attention(b, tokens, impl):
     s = q @ k.transpose(-1, -2) * 0.125
     # each kernel's own definition of where P is rounded to bf16 (see oracle/dpt_oracle.py)
     from oracle.dpt_oracle import _attention_bf16, _attention_online_bf16
-    ref = (_attention_bf16 if impl == "tc" else _attention_online_bf16)(q, k, v)   # plain torch ops, on the GPU
+    ref = (_attention_online_bf16 if impl == "mma" else _attention_bf16)(q, k, v)   # plain torch ops, on the GPU
     check(out, ref.transpose(1, 2).reshape(b, tokens, 768), f"attention b{b} n{tokens}", tol=1e-3)
     exact = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(b, tokens, 768)
     assert rel_l2(out.float(), exact) < 4e-3
