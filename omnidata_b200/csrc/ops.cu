@@ -387,10 +387,13 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 }
 
 // Bilinear x2, align_corners=True: src = dst * (n-1)/(2n-1).  out = up(z) (+ res); out_relu = relu(out).
-// The ncu profile of the first version showed this kernel ISSUE-bound (88 % issue slots, 26 % DRAM):
-// index divisions and 64-bit address math per 16 bytes.  This version has none: blockDim = (channel
-// octets, pixels), one output row per blockIdx.y, so every thread does a handful of integer ops,
-// 32 bf16 unpacks, 32 FMAs (four precomputed bilinear weights) and the packs.
+// ncu showed the first two versions of this kernel ISSUE-bound (75-88 % issue slots, ~30 % DRAM):
+// four gathers, 32 unpacks and 32 FMAs for every 16 output bytes.  With align_corners=True and an
+// exact x2 factor, output columns 2k+1 and 2k+2 both interpolate between source columns k and k+1
+// (and likewise for rows), so a thread now owns one SOURCE quad (m..m+1, k..k+1) and produces the
+// 2x2 output block {2m+1, 2m+2} x {2k+1, 2k+2} from a single set of four loads; m = -1 / k = -1 and
+// m = h-1 / k = w-1 produce the border rows / columns (source index clamped, weight 0 or 1).
+// blockDim = (channel octets, quads along x); no integer division, 32-bit index math.
 __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restrict__ z,
                                                              const bf16* __restrict__ res,
                                                              bf16* __restrict__ out,
@@ -399,39 +402,50 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
   grid_dep_wait();
   grid_dep_launch();
   const int oh = 2 * h, ow = 2 * w;
-  const int ox = blockIdx.x * blockDim.y + threadIdx.y;
-  if (ox >= ow) return;
-  const int oy = blockIdx.y, bi = blockIdx.z;
+  const int k = (int)(blockIdx.x * blockDim.y + threadIdx.y) - 1;   // source quad column, -1 .. w-1
+  if (k > w - 1) return;
+  const int m = (int)blockIdx.y - 1;                                // source quad row,    -1 .. h-1
+  const int bi = blockIdx.z;
   const int ch = threadIdx.x * 8;
   const float sy = (float)(h - 1) / (float)(oh - 1), sx = (float)(w - 1) / (float)(ow - 1);
-  const float fy = oy * sy, fx = ox * sx;
-  const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
-  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-  const float wy = fy - (float)y0, wx = fx - (float)x0;
-  const float w11 = wy * wx, w10 = wy - w11, w01 = wx - w11, w00 = 1.0f - wy - wx + w11;
-  const bf16* zb = z + (size_t)bi * h * w * c + ch;
-  const unsigned r0 = (unsigned)(y0 * w) * (unsigned)c, r1 = (unsigned)(y1 * w) * (unsigned)c;
-  const unsigned c0 = (unsigned)x0 * (unsigned)c, c1 = (unsigned)x1 * (unsigned)c;
-  float a[8], bq[8], cc[8], d[8], o[8];
-  load8(zb + r0 + c0, a);
-  load8(zb + r0 + c1, bq);
-  load8(zb + r1 + c0, cc);
-  load8(zb + r1 + c1, d);
-  const size_t off = ((size_t)(bi * oh + oy) * ow + ox) * c + ch;
-  if (res != nullptr) {
-    float r[8];
-    load8(res + off, r);
+  const int ys = min(max(m, 0), h - 2), xs = min(max(k, 0), w - 2);
+  const bf16* zb = z + ((size_t)bi * h + ys) * w * c + (size_t)xs * c + ch;
+  float q00[8], q01[8], q10[8], q11[8];
+  load8(zb, q00);
+  load8(zb + c, q01);
+  load8(zb + (size_t)w * c, q10);
+  load8(zb + (size_t)w * c + c, q11);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(w11, d[j], fmaf(w10, cc[j], fmaf(w01, bq[j], fmaf(w00, a[j], r[j]))));
-  } else {
+  for (int dy = 0; dy < 2; ++dy) {
+    const int oy = 2 * m + 1 + dy;
+    if (oy < 0 || oy >= oh) continue;
+    const float wy = fminf(fmaxf(oy * sy - (float)ys, 0.f), 1.f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(w11, d[j], fmaf(w10, cc[j], fmaf(w01, bq[j], w00 * a[j])));
-  }
-  store8(out + off, o);
-  if (out_relu != nullptr) {
+    for (int dx = 0; dx < 2; ++dx) {
+      const int ox = 2 * k + 1 + dx;
+      if (ox < 0 || ox >= ow) continue;
+      const float wx = fminf(fmaxf(ox * sx - (float)xs, 0.f), 1.f);
+      const float w11 = wy * wx, w10 = wy - w11, w01 = wx - w11, w00 = 1.0f - wy - wx + w11;
+      const size_t off = ((size_t)(bi * oh + oy) * ow + ox) * c + ch;
+      float o[8];
+      if (res != nullptr) {
+        float r[8];
+        load8(res + off, r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-    store8(out_relu + off, o);
+        for (int j = 0; j < 8; ++j)
+          o[j] = fmaf(w11, q11[j], fmaf(w10, q10[j], fmaf(w01, q01[j], fmaf(w00, q00[j], r[j]))));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = fmaf(w11, q11[j], fmaf(w10, q10[j], fmaf(w01, q01[j], w00 * q00[j])));
+      }
+      store8(out + off, o);
+      if (out_relu != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        store8(out_relu + off, o);
+      }
+    }
   }
 }
 
@@ -609,11 +623,11 @@ extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, voi
   if (!z || !out || b < 1 || h < 1 || w < 1 || c < 8 || c % 8)
     return fail(ODB_ERR_INVALID, "upsample2x_add: bad argument");
   const int octets = c / 8;
-  if (2 * h > 65535 || b > 65535 || octets > 256 || (256 % octets) != 0)
-    return fail(ODB_ERR_INVALID, "upsample2x_add: extent too large or channel count unsupported");
-  const int pix = 256 / octets;
-  dim3 block(octets, pix);
-  dim3 grid((2 * w + pix - 1) / pix, 2 * h, b);
+  if (h + 1 > 65535 || b > 65535 || octets > 256 || (256 % octets) != 0 || h < 2 || w < 2)
+    return fail(ODB_ERR_INVALID, "upsample2x_add: extent / channel count unsupported (h, w >= 2)");
+  const int quads = 256 / octets;                       // source quads along x per block
+  dim3 block(octets, quads);
+  dim3 grid((w + 1 + quads - 1) / quads, h + 1, b);     // quad columns -1..w-1, quad rows -1..h-1
   launch_pdl(upsample2x_add_kernel, grid, block, 0, stream, static_cast<const bf16*>(z),
              static_cast<const bf16*>(res), static_cast<bf16*>(out), static_cast<bf16*>(out_relu), h, w, c);
   count_launch();
