@@ -32,7 +32,7 @@ constexpr int kTcOffQ = 2 * kTcMaxBlocks * kTcTileBytes;
 constexpr int kTcOffP = kTcOffQ + 2 * kTcTileBytes;
 constexpr int kTcOffX = kTcOffP + 2 * kTcTileBytes;          // fp32 exchange [2 halves][128 rows] (max, then sum)
 constexpr int kTcOffBar = kTcOffX + 2 * 128 * 4;
-constexpr int kTcSmemBytes = kTcOffBar + 144 + 1024;
+constexpr int kTcSmemBytes = kTcOffBar + 256 + 1024;
 static_assert(kTcSmemBytes <= 232448, "attention smem plan exceeds 227 KiB");
 
 struct AttnTcParams {
@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   const uint32_t tmem_slot = bar0 + 128;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + kTcOffBar + 128);
   constexpr uint32_t kOCol = 3 * kTcBlk;                       // first TMEM column of O
+  // K and V arrive block by block (own barrier each): the first S block of a unit starts after 16 KiB
+  // instead of after the whole 160 KiB, the rest of the fetch hides behind pass 1
+  auto k_full = [&](int j) { return bar0 + 136u + 8u * j; };
+  auto v_full = [&](int j) { return bar0 + 176u + 8u * j; };
   // one exchange array serves the row maxima and later the row sums: a thread can only reach its
   // row-sum write after every thread has arrived on p_full for block 0, i.e. after it read the maxima
   float* xmax = reinterpret_cast<float*>(gen_base + kTcOffX);
@@ -78,6 +82,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    for (int j = 0; j < kTcMaxBlocks; ++j) { mbar_init(k_full(j), 1); mbar_init(v_full(j), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1); }
     for (int i = 0; i < 3; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 8); }
     mbar_init(p_full, kTcSoftmaxThreads); mbar_init(p_empty, 1);
@@ -103,10 +108,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u_iter) {
         const int b = unit / p.heads, h = unit % p.heads;
         mbar_wait(kv_empty, (u_iter & 1u) ^ 1u);
-        mbar_expect_tx(kv_full, 2u * nblk * kTcTileBytes);
         for (int j = 0; j < nblk; ++j) {
-          tma_load_4d(sbase + kTcOffK + j * kTcTileBytes, &p.qkv_map, kv_full, 0, p.heads + h, j * kTcBlk, b);
-          tma_load_4d(sbase + kTcOffV + j * kTcTileBytes, &p.qkv_map, kv_full, 0, 2 * p.heads + h, j * kTcBlk, b);
+          mbar_expect_tx(k_full(j), kTcTileBytes);
+          tma_load_4d(sbase + kTcOffK + j * kTcTileBytes, &p.qkv_map, k_full(j), 0, p.heads + h, j * kTcBlk, b);
+        }
+        for (int j = 0; j < nblk; ++j) {
+          mbar_expect_tx(v_full(j), kTcTileBytes);
+          tma_load_4d(sbase + kTcOffV + j * kTcTileBytes, &p.qkv_map, v_full(j), 0, 2 * p.heads + h, j * kTcBlk, b);
         }
         for (int qt = 0; qt < nblk; ++qt, ++qt_iter) {
           const int qb = qt_iter & 1u;
@@ -124,6 +132,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       uint32_t u_iter = 0, qt_iter = 0, sb_iter = 0, p_iter = 0;
       auto issue_s = [&](int j, int qb) {
         const uint32_t sbuf = sb_iter % 3u;
+        mbar_wait(k_full(j), u_iter & 1u);                      // K block j of this unit has landed
         mbar_wait(s_empty(sbuf), ((sb_iter / 3u) & 1u) ^ 1u);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(sbase + kTcOffQ + qb * kTcTileBytes);
@@ -135,8 +144,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         ++sb_iter;
       };
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u_iter) {
-        mbar_wait(kv_full, u_iter & 1u);
-        tc_fence_after();
         for (int qt = 0; qt < nblk; ++qt, ++qt_iter) {
           const int qb = qt_iter & 1u;
           mbar_wait(q_full(qb), (qt_iter >> 1) & 1u);
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
           pump(nblk + 2);
           for (int j = 0; j < nblk; ++j) {
             pump(nblk + j + 3);
+            mbar_wait(v_full(j), u_iter & 1u);                    // V block j of this unit has landed
             mbar_wait(p_full, p_iter & 1u);
             tc_fence_after();
             if (j == 0) {                                         // the epilogue has drained the previous O
