@@ -236,6 +236,10 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
 
     gh, gw = feats[2].shape[-2:]
     pos = g(P + "pos_embed")
+    if (gh, gw) != (24, 24):  # _resize_pos_embed (modules/midas/vit.py:102-116), done once at pre-pack time
+        grid = pos[0, 1:].reshape(1, 24, 24, -1).permute(0, 3, 1, 2)
+        grid = F.interpolate(grid, size=(gh, gw), mode="bilinear")
+        pos = torch.cat([pos[:, :1], grid.permute(0, 2, 3, 1).reshape(1, gh * gw, -1)], dim=1)
     tok = F.conv2d(feats[2], wq(g(P + "patch_embed.proj.weight")), g(P + "patch_embed.proj.bias"))
     tok = tok.flatten(2).transpose(1, 2) + r(pos[:, 1:])
     cls = (g(P + "cls_token") + pos[:, :1]).expand(B, -1, -1)
