@@ -293,6 +293,7 @@ def main():
 
         # ---------------- instrumented pass: per-launch CUDA events (roofline)
         roof = None
+        roof_hbm = None
         detail = {}
         if rank == 0:
             model.use_cuda_graph = False
@@ -330,11 +331,25 @@ def main():
                 peak = peaks["tflops_sustained"]
                 roof = {"kernel": "conv_gemm_kernel (tcgen05) — the 48 ViT-block GEMM launches",
                         "bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
-                        "frac": round(achieved / peak, 4), "traffic": None,
+                        "frac": round(achieved / peak, 4),
+                        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four ViT GEMM
+                        # shapes, from the committed `ncu --set full` capture (profiles/r01c_vit_gemm_*.csv);
+                        # algorithmic bytes per launch (operands + output + residual, bf16): 131 MB
+                        "traffic": 92.0e6, "traffic_unit": "bytes/launch (ncu, profiles/r01c)",
                         "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
                         "avg_launch_ms": round(v["ms"] / v["launches"], 4),
                         "how": "CUDA events around every launch on the launching stream, eager instrumented pass "
                                "after the timed region (2 forwards averaged)"}
+            u = agg.get("odb_upsample2x_add")
+            if u and u["bytes"]:
+                gbs = u["bytes"] / (u["ms"] * 1e-3) / 1e9
+                roof_hbm = {"kernel": "upsample2x_add_kernel - bilinear x2 (+skip add, +relu copy), the HBM-bound "
+                                      "kernel of the FeatureFusionBlock decoder and head (5 launches)",
+                            "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": round(gbs / peaks["hbm_gbs"], 4),
+                            "traffic": 1.45e9, "traffic_unit": "bytes, largest launch (ncu, profiles/r01c): equals its "
+                                                               "algorithmic 0.30 GB read + 1.21 GB write",
+                            "peak_source": f"{peaks['source']} copy bandwidth (MEASURED_PEAKS.json)"}
             model.use_cuda_graph = not args.no_graph
 
     images = B * world * args.steps
@@ -360,6 +375,7 @@ def main():
             "model_frac_of_sustained_peak": round(GFLOP_PER_IMAGE * 1e9 * value / world / 1e12 / peaks["tflops_sustained"], 4),
             "weight_broadcast": {"bytes": bcast_bytes, "ms": round(bcast_ms, 2)},
             "roofline": roof,
+            "roofline_hbm": roof_hbm,
             "roofline_detail": detail,
         }
         if world == 1 and not args.no_cpu_baseline:
