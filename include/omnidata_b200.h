@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ODB_ABI_VERSION 1
+#define ODB_ABI_VERSION 2
 
 typedef enum odb_status {
   ODB_OK = 0,
@@ -101,6 +101,11 @@ typedef struct odb_conv_gemm_desc {
    * written exactly once: no atomics, deterministic).  odb_groupnorm_finalize reduces them. */
   float* gn_partial;
   int32_t gn_groups;
+  /* Epilogue code path: 0 = auto (a specialised straight-line epilogue — TMEM read of the next 64-column
+   * chunk in flight, residual fetched by TMA into the output staging slot — whenever the flags are
+   * bias[+relu|+gelu] or bias+residual with a plain strided residual; the generic epilogue otherwise),
+   * -1 = always the generic epilogue.  Both produce bit-identical results. */
+  int32_t epilogue;
 } odb_conv_gemm_desc;
 
 int odb_conv_gemm(const odb_conv_gemm_desc* desc, void* stream);
@@ -206,6 +211,11 @@ int odb_abi_version(void);
 const char* odb_last_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t odb_launch_count(void);
+/* Diagnostics: when set to a device buffer of grid x (return value) uint64 slots, every following
+ * odb_conv_gemm launch stamps %globaltimer at its pipeline events (prologue done, dependency wait done,
+ * kernel end; per tile: MMA start / first stage full / MMA commit / epilogue start / epilogue end).
+ * NULL switches it off.  Used by profiles/trace_gemm.py; never set on the product path. */
+int odb_debug_conv_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }

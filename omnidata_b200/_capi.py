@@ -55,6 +55,7 @@ class ConvGemmDesc(C.Structure):
         ("head_out", C.c_void_p),
         ("gn_partial", C.c_void_p),
         ("gn_groups", C.c_int32),
+        ("epilogue", C.c_int32),
     ]
 
 
@@ -91,6 +92,7 @@ _SIGNATURES = {
     "odb_abi_version": (C.c_int, []),
     "odb_last_error": (C.c_char_p, []),
     "odb_launch_count": (C.c_int64, []),
+    "odb_debug_conv_trace": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -28,6 +28,8 @@ int check_launch(const char* where) {
   }
   return ODB_OK;
 }
+static unsigned long long* g_trace = nullptr;
+unsigned long long* debug_trace() { return g_trace; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 bool pdl_enabled() {
@@ -94,6 +96,10 @@ int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, int rank, void* ba
 
 extern "C" int odb_abi_version(void) { return ODB_ABI_VERSION; }
 extern "C" const char* odb_last_error(void) { return odb::g_err; }
+extern "C" int odb_debug_conv_trace(void* device_buffer) {
+  odb::g_trace = static_cast<unsigned long long*>(device_buffer);
+  return odb::kTraceSlots;
+}
 extern "C" int64_t odb_launch_count(void) { return odb::g_launches.load(); }
 
 extern "C" int odb_fill_zero(void* ptr, int64_t bytes, void* stream) {

@@ -40,7 +40,17 @@ struct AttnTcParams {
   bf16* out;
   int tokens, heads, batch;
   float scale_log2e;
+  unsigned long long* trace;   // diagnostics: per CTA kTraceSlots stamps; per q tile i < 8 at 8 + 12 i:
+                               // first S seen, maxima exchanged, P block 0..4 handed over, sums exchanged, O ready, tile stored
 };
+#define ODB_ATRACE(i, k)                                                                           \
+  do {                                                                                             \
+    if (p.trace != nullptr && (i) < 8u && warp == 2 && lane == 0) {                                \
+      unsigned long long t_;                                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                       \
+      p.trace[static_cast<long long>(blockIdx.x) * kTraceSlots + 8 + 12 * static_cast<int>(i) + (k)] = t_; \
+    }                                                                                              \
+  } while (0)
 
 ODB_DEVINL float fast_exp2_tc(float x) {
   float y;
@@ -199,6 +209,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
           const uint32_t sbuf = sb_iter % 3u;
           mbar_wait(s_full(sbuf), (sb_iter / 3u) & 1u);
           tc_fence_after();
+          if (j == 0) ODB_ATRACE(qt_iter, 0);
           uint32_t r[64];
           tmem_ld_32x32(t_lane + sbuf * kTcBlk + half * 64, r);
           tmem_ld_32x32(t_lane + sbuf * kTcBlk + half * 64 + 32, r + 32);
@@ -220,6 +231,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         named_bar_sync(1, kTcSoftmaxThreads);
         const float m = fmaxf(xmax[row], xmax[128 + row]);
         const float mc = m * c;
+        ODB_ATRACE(qt_iter, 1);
         // ---- pass 2: P = exp2(s*c - m*c) -> bf16 operand tile in smem, fp32 row sum
         float l = 0.f;
         for (int j = 0; j < nblk; ++j, ++sb_iter, ++p_iter) {
@@ -255,13 +267,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
           }
           fence_proxy_async_smem();
           mbar_arrive(p_full);
+          ODB_ATRACE(qt_iter, 2 + j);
         }
         xsum[half * 128 + row] = l;
         named_bar_sync(1, kTcSoftmaxThreads);
         const float inv = 1.0f / (xsum[row] + xsum[128 + row]);
+        ODB_ATRACE(qt_iter, 7);
         // ---- epilogue: O / l -> bf16 -> global (each thread: 32 of the 64 head dims of its row)
         mbar_wait(o_full, qt_iter & 1u);
         tc_fence_after();
+        ODB_ATRACE(qt_iter, 8);
         uint32_t o[32];
         tmem_ld_32x32(t_lane + kOCol + half * 32, o);
         tmem_ld_wait();
@@ -281,6 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
             *reinterpret_cast<uint4*>(dst + jj * 8) = v;
           }
         }
+        ODB_ATRACE(qt_iter, 9);
       }
     }
   }
@@ -318,6 +334,7 @@ extern "C" int odb_attention(const void* qkv, void* out, int32_t b, int32_t toke
   p.out = static_cast<bf16*>(out);
   p.tokens = tokens; p.heads = heads; p.batch = b;
   p.scale_log2e = scale * 1.4426950408889634f;
+  p.trace = debug_trace();
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -164,6 +164,20 @@ ODB_DEVINL void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 
+// waits for this thread's outstanding tcgen05.ld AND ties the destination registers to the wait, so
+// that no use of r can be scheduled above it (needed once loads are issued ahead of their use)
+ODB_DEVINL void tmem_ld_wait_regs(uint32_t* r) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+        "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+        "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+        "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+        "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 ODB_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
@@ -263,6 +277,54 @@ ODB_DEVINL float erf_as(float x) {
   return copysignf(fmaf(-p * t, e, 1.0f), x);
 }
 ODB_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+
+// ---- packed fp32 pairs (sm_100: FFMA2 — one issue slot for two fused multiply-adds)
+ODB_DEVINL uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+ODB_DEVINL void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+ODB_DEVINL uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+ODB_DEVINL float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Exact-erf GELU for the GEMM epilogue, two elements at a time:
+//   gelu(x) = x Phi(x) = max(x, 0) - |x| Phi(-|x|),   Phi(-a) = 2^P(a),  a = min(|x|, 8)
+// P = degree-10 weighted-minimax fit of log2 Phi(-a) on [0, 8] (fit: |gelu error| < 4e-8 absolute AND
+// < 6e-6 relative — the tail x -> -inf keeps RELATIVE accuracy because the error sits in the
+// exponent; measured in fp32 against float64 x Phi(x): 2.4e-7 = half an ulp of the result).
+// Cost per element: 5 FFMA2 + 1 MUFU.EX2 + 3 ALU — half the MUFU work and ~60 % of the issue slots
+// of the Abramowitz-Stegun form above, which is what bounds the fc1 epilogue (B200: 16 MUFU/clk/SM).
+ODB_DEVINL void gelu_erf_x2(float& x0, float& x1) {
+  const float a0 = fminf(fabsf(x0), 8.0f), a1 = fminf(fabsf(x1), 8.0f);
+  const uint64_t a = f32x2_pack(a0, a1);
+#define ODB_C2(c) f32x2_pack(c, c)
+  uint64_t p = f32x2_fma(ODB_C2(-4.45074694e-09f), a, ODB_C2(1.77394618e-07f));
+  p = f32x2_fma(p, a, ODB_C2(-2.91884744e-06f));
+  p = f32x2_fma(p, a, ODB_C2(2.41618334e-05f));
+  p = f32x2_fma(p, a, ODB_C2(-7.56097581e-05f));
+  p = f32x2_fma(p, a, ODB_C2(-4.90890656e-04f));
+  p = f32x2_fma(p, a, ODB_C2(7.66879548e-03f));
+  p = f32x2_fma(p, a, ODB_C2(-5.30659795e-02f));
+  p = f32x2_fma(p, a, ODB_C2(-4.58926226e-01f));
+  p = f32x2_fma(p, a, ODB_C2(-1.15116936e+00f));
+  p = f32x2_fma(p, a, ODB_C2(-9.99995267e-01f));
+#undef ODB_C2
+  float p0, p1;
+  f32x2_unpack(p, p0, p1);
+  x0 = fmaf(-a0, ex2_approx(p0), fmaxf(x0, 0.0f));
+  x1 = fmaf(-a1, ex2_approx(p1), fmaxf(x1, 0.0f));
+}
 
 ODB_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -13,6 +13,8 @@
 // 128-byte rows with the 128B swizzle, i.e. directly in the canonical K-major UMMA layout.
 //
 // What this replaces in the reference is listed in include/omnidata_b200.h (odb_conv_gemm).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/omnidata_b200.h"
@@ -54,7 +56,34 @@ struct ConvGemmParams {
   float* gn_partial;   // optional GroupNorm partial sums, [b][tiles_y*tiles_x][4 quadrants][groups][2]
   int gn_cpg;          // channels per group (2..32, power of two)
   int gn_groups;
+  CUtensorMap res_map;        // EPI_BIAS_RES: the residual, boxed like out_map
+  unsigned long long* trace;  // diagnostics (odb_debug_conv_trace): kTraceSlots globaltimer stamps per CTA
 };
+
+// trace slots per CTA: 0 prologue done, 1 dependency wait done, 2 kernel end, 3 tiles of this CTA;
+// per tile i < kTraceTiles at 8 + 5 i: MMA start, first stage full, MMA commit issued, epilogue start, epilogue end
+constexpr int kTraceTiles = 24;
+ODB_DEVINL unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define ODB_TRACE(slot)                                                                      \
+  do {                                                                                       \
+    if (p.trace != nullptr) p.trace[static_cast<long long>(blockIdx.x) * kTraceSlots + (slot)] = global_ns(); \
+  } while (0)
+#define ODB_TRACE_TILE(i, k)                                   \
+  do {                                                         \
+    if (p.trace != nullptr && (i) < kTraceTiles) ODB_TRACE(8 + 5 * static_cast<int>(i) + (k)); \
+  } while (0)
+
+// Epilogue specialisations.  EPI_GENERIC handles every flag combination at run time (GroupNorm
+// statistics, relu copy, residual with arbitrary strides / batch broadcast, missing bias).  The
+// others are straight-line bodies for the combinations that carry the ViT blocks and most decoder
+// convolutions: ~4x fewer instructions per 64-column chunk, the TMEM read of chunk c+1 in flight
+// while chunk c is processed, and (EPI_BIAS_RES) the residual fetched by TMA into the output
+// staging slot a few chunks ahead instead of 1024 scattered 16-byte loads per chunk.
+enum : int { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_GELU = 3, EPI_BIAS_RES = 4 };
 
 // ---- GroupNorm partial statistics of one epilogue warp (32 rows x 32 columns of a tile):
 // per-thread group sums over its row, then a transposing butterfly over the 32 lanes: V values are
@@ -128,8 +157,8 @@ struct SmemPlan {
   static constexpr int kBOff = kAStages * kAStageBytes;
   static constexpr int kCOff = kBOff + STAGES * kBBytes;
   static constexpr int kBarOff = kCOff + NSTAGING * kStagingBytes;
-  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], a_full[3], a_empty[3], tmem base pointer
-  static constexpr int kBarBytes = (2 * STAGES + 4 + 6) * 8 + 16;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], a_full[3], a_empty[3], res_full[4], tmem base pointer
+  static constexpr int kBarBytes = (2 * STAGES + 4 + 6 + 4) * 8 + 16;
   static constexpr int kTotal = kBarOff + kBarBytes + 1024;  // +1024: manual 1 KiB alignment
   static_assert(kTotal <= 232448, "shared memory plan exceeds 227 KiB");
 };
@@ -144,9 +173,10 @@ struct TmemCols {
 // vertically adjacent 128-row M tiles against the same N tile as ONE UMMA (M = 256): each CTA
 // TMA-loads its own A rows and HALF of the B rows, the leader CTA issues the MMAs for both, and each
 // CTA drains its own 128 TMEM lanes.  Per-SM smem fill and L2 read traffic per MMA drop by a third.
-template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR, bool HALO>
+template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR, bool HALO, int EPI = EPI_GENERIC>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  static_assert(EPI == EPI_GENERIC || (!HEAD && !HALO && NSTAGING >= 2), "fast epilogues: plain tiles only");
   using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR, HALO, HEAD>;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
@@ -158,7 +188,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   auto afull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + a); };
   auto aempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 7 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 10);
+  auto rfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 10 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 14);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -179,7 +210,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(afull_bar(a), PAIR ? 2 : 1);
       mbar_init(aempty_bar(a), 1);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(rfull_bar(a), 1);
     mbar_fence_init();
+    if (EPI == EPI_BIAS_RES) tma_prefetch_desc(&p.res_map);
     for (int v = 0; v < ODB_MAX_VIEWS; ++v) tma_prefetch_desc(&p.a_map[v]);
     tma_prefetch_desc(&p.b_map);
     if (!HEAD) tma_prefetch_desc(&p.out_map);
@@ -197,9 +230,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) ODB_TRACE(0);
   // everything above overlapped the tail of the previous kernel (programmatic dependent launch)
   grid_dep_wait();
   grid_dep_launch();
+  if (threadIdx.x == 0) ODB_TRACE(1);
 
   // work units: (n tile, m tile) for a single CTA, (n tile, pair of m tiles) for a CTA pair
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
@@ -305,6 +340,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint32_t acc_phase = (iter >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        ODB_TRACE_TILE(iter, 0);
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         if constexpr (HALO) {
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
@@ -337,6 +373,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
+            if (kb == 0) ODB_TRACE_TILE(iter, 1);
             const uint64_t adesc = umma_desc_sw128(smem_base + Plan::kAOff + stage * kABytes);
             const uint64_t bdesc = umma_desc_sw128(smem_base + Plan::kBOff + stage * Plan::kBBytes);
 #pragma unroll
@@ -354,6 +391,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         // accumulator complete
         if constexpr (PAIR) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
+        ODB_TRACE_TILE(iter, 2);
       }
     }
   } else if (!HEAD || warp < 6) {
@@ -367,6 +405,126 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int ly = row / rpitch, lx = row - ly * rpitch;
     const bool row_in_tile = HALO ? (lx < tw && ly < p.tile_h) : (row < p.tile_w * p.tile_h);
     const int srow = HALO ? (row_in_tile ? ly * tw + lx : 0) : row;   // dense row in the store staging tile
+    if constexpr (EPI != EPI_GENERIC) {
+      // ---------------------------------------------------------- specialised epilogues
+      constexpr int kChunks = BLOCK_N / 64;
+      constexpr int NS = NSTAGING;      // staging slots of one 128 x 64 chunk each
+      constexpr int D = NS / 2;         // residual prefetch distance in chunks
+      const int cofs = half * 32;
+      const uint32_t tempty0 = PAIR ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+      const uint32_t tempty1 = PAIR ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
+      const uint32_t rowoff = static_cast<uint32_t>(row) * 128u;
+      uint32_t g = 0;                   // chunks this CTA has processed
+      // residual loader (store leader): chunk ld_g of the CTA's static schedule -> slot ld_g % NS
+      int ld_tile = unit0, ld_c = 0;
+      uint32_t ld_g = 0;
+      auto issue_res_load = [&]() {
+        if (ld_tile < total_tiles) {
+          int tn, tx, ty, tb;
+          decode(ld_tile, tn, tx, ty, tb);
+          const uint32_t slot = ld_g % NS;
+          mbar_expect_tx(rfull_bar(slot), a_bytes);
+          tma_load_4d(smem_base + Plan::kCOff + slot * kStagingBytes, &p.res_map, rfull_bar(slot),
+                      tn * BLOCK_N + ld_c * 64, tx * p.tile_w, ty * p.tile_h, tb);
+          ++ld_g;
+          if (++ld_c == kChunks) { ld_c = 0; ld_tile += unit_stride; }
+        }
+      };
+      if (EPI == EPI_BIAS_RES && store_leader) {
+        for (int i = 0; i < D; ++i) issue_res_load();
+      }
+      uint32_t iter = 0;
+      for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
+        int tn, tx, ty, tb;
+        decode(tile, tn, tx, ty, tb);
+        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+        const uint32_t acc = iter & 1u;
+        const uint32_t acc_phase = (iter >> 1) & 1u;
+        const int n0 = tn * BLOCK_N;
+        const float* bias = p.bias + static_cast<long long>(tb < p.out_b ? tb : 0) * p.bias_sb + n0 + cofs;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (store_leader) ODB_TRACE_TILE(iter, 3);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_row + cofs, ra);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c, ++g) {
+          uint32_t* r = (c & 1) ? rb : ra;
+          uint32_t* rn = (c & 1) ? ra : rb;
+          float4 bv[8];
+          const float4* bp = reinterpret_cast<const float4*>(bias + c * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+          tmem_ld_wait_regs(r);
+          if (c + 1 < kChunks) {
+            tmem_ld_32x32(t_row + (c + 1) * 64 + cofs, rn);   // in flight while chunk c is processed
+          } else {
+            // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(acc ? tempty1 : tempty0);
+              else mbar_arrive(tempty_bar(acc));
+            }
+          }
+          float v[32];
+          const float* bf = reinterpret_cast<const float*>(bv);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bf[j];
+          if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) gelu_erf_x2(v[2 * j], v[2 * j + 1]);
+          } else if constexpr (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          const uint32_t slot = g % NS;
+          const uint32_t buf = smem_base + Plan::kCOff + slot * kStagingBytes;
+          if constexpr (EPI == EPI_BIAS_RES) {
+            // the residual rows of this chunk were TMA-loaded into the staging slot (same swizzled
+            // layout as the output): read own 64 bytes, add, write the result back in place
+            mbar_wait(rfull_bar(slot), (g / NS) & 1u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t addr = buf + rowoff + (static_cast<uint32_t>((half * 4 + j) ^ (row & 7)) << 4);
+              uint32_t q0, q1, q2, q3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "r"(addr) : "memory");
+              float2 t2;
+              t2 = unpack_bf16x2(q0); v[8 * j + 0] += t2.x; v[8 * j + 1] += t2.y;
+              t2 = unpack_bf16x2(q1); v[8 * j + 2] += t2.x; v[8 * j + 3] += t2.y;
+              t2 = unpack_bf16x2(q2); v[8 * j + 4] += t2.x; v[8 * j + 5] += t2.y;
+              t2 = unpack_bf16x2(q3); v[8 * j + 6] += t2.x; v[8 * j + 7] += t2.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = buf + rowoff + (static_cast<uint32_t>((half * 4 + j) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                         "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                         "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          // slot reuse without a residual: the store of chunk g+1-NS must have read its slot before any
+          // thread passes this barrier and starts writing chunk g+1 (with a residual the TMA load of
+          // chunk g+1, issued after that store was read, orders it)
+          if (EPI != EPI_BIAS_RES && store_leader) tma_store_wait_read<NS - 2>();
+          named_bar_sync(1, kEpiThreads);
+          if (store_leader) {
+            tma_store_4d(&p.out_map, buf, n0 + c * 64, x0, y0, tb);
+            tma_store_commit();
+            if constexpr (EPI == EPI_BIAS_RES) {
+              tma_store_wait_read<NS - D>();     // the store of chunk g+D-NS has read its slot
+              issue_res_load();                  // residual of chunk g+D -> that slot
+            }
+          }
+        }
+        if (store_leader) ODB_TRACE_TILE(iter, 4);
+      }
+      if (store_leader) tma_store_wait_all();
+    } else {
     uint32_t iter = 0;
     uint32_t chunk_counter = 0;
     const int bufs_per_chunk = p.has_out2 ? 2 : 1;
@@ -385,6 +543,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (store_leader) ODB_TRACE_TILE(iter, 3);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 
       if constexpr (HEAD) {
@@ -475,7 +634,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bf[j];
           if (p.act == ODB_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 16; ++j) gelu_erf_x2(v[2 * j], v[2 * j + 1]);
           } else if (p.act == ODB_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -555,12 +714,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
       }
+      if (store_leader) ODB_TRACE_TILE(iter, 4);
     }
     if (store_leader) tma_store_wait_all();
+    }  // EPI_GENERIC
   }
 
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) ODB_TRACE(2);
   if (warp == 1) {
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_cg2(tmem_base, TmemCols<BLOCK_N>::value);
@@ -591,10 +753,10 @@ static int encode_view_map(CUtensorMap* map, const odb_view& v, int box_c, int b
                       strides, box, estr, swz);
 }
 
-template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR, bool HALO>
+template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR, bool HALO, int EPI = EPI_GENERIC>
 static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_t stream) {
   using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR, HALO, HEAD>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, STAGES, NSTAGING, HEAD, PAIR, HALO>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, STAGES, NSTAGING, HEAD, PAIR, HALO, EPI>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -628,6 +790,38 @@ static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_
   count_launch();
   if (e != cudaSuccess) return fail_cuda(e, "conv_gemm: launch");
   return check_launch("conv_gemm");
+}
+
+// the plain-tile kernels (no halo, no head tail) with a specialised epilogue
+template <int EPI>
+static int launch_fast(const ConvGemmParams& p, int block_n, bool pair, long long m_tiles, long long total,
+                       cudaStream_t stream) {
+  if (pair) {
+    // the residual variant trades one of the six operand stages for two more staging slots, so that
+    // the residual TMA load runs two chunks ahead of its use (measured: see DESIGN.md)
+    static int res_stages = -1;
+    if (res_stages < 0) {
+      const char* e = getenv("ODB_PAIR_RES_STAGES");
+      res_stages = (e != nullptr && e[0] == '6') ? 6 : 5;
+    }
+    if (EPI == EPI_BIAS_RES && res_stages == 5)
+      return launch_instance<256, 5, 4, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
+    return launch_instance<256, 6, 2, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
+  }
+  switch (block_n) {
+    case 256: return launch_instance<256, 4, 2, false, false, false, EPI>(p, total, stream);
+    case 128: return launch_instance<128, 5, 4, false, false, false, EPI>(p, total, stream);
+    default: return launch_instance<64, 6, 4, false, false, false, EPI>(p, total, stream);
+  }
+}
+
+static bool fast_epilogues_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ODB_EPI_FAST");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 }  // namespace odb
@@ -818,8 +1012,23 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
     p.gn_cpg = cpg;
     p.gn_groups = g;
   }
+  p.trace = debug_trace();
 
   const long long total = m_tiles * p.tiles_n;
+  // specialised epilogue when the flag combination allows it (see the EPI_* comment)
+  if (!hp.halo && !head && block_n >= 64 && p.bias != nullptr && !p.has_out2 && p.gn_partial == nullptr &&
+      d->epilogue == 0 && fast_epilogues_enabled()) {
+    if (p.residual == nullptr) {
+      if (p.act == ODB_ACT_NONE) return launch_fast<EPI_BIAS>(p, block_n, pair, m_tiles, total, stream);
+      if (p.act == ODB_ACT_RELU) return launch_fast<EPI_BIAS_RELU>(p, block_n, pair, m_tiles, total, stream);
+      if (p.act == ODB_ACT_GELU) return launch_fast<EPI_BIAS_GELU>(p, block_n, pair, m_tiles, total, stream);
+    } else if (p.act == ODB_ACT_NONE && d->residual.c == N && d->residual.w >= ow && d->residual.h >= oh &&
+               d->residual.b >= ob && (d->residual.sb > 0 || ob == 1) && (d->residual.sy > 0 || oh == 1)) {
+      rc = encode_view_map(&p.res_map, d->residual, 64, tw, th, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      return launch_fast<EPI_BIAS_RES>(p, block_n, pair, m_tiles, total, stream);
+    }
+  }
   if (hp.halo) {
     p.halo_w = tw + 2;
     if (pair) return launch_instance<256, 4, 2, false, true, true>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);

@@ -22,6 +22,10 @@ int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, int rank, void* ba
 
 bool pdl_enabled();
 
+// diagnostics (odb_debug_conv_trace): device buffer of kTraceSlots uint64 per CTA, or nullptr
+constexpr int kTraceSlots = 128;
+unsigned long long* debug_trace();
+
 // Launch with programmatic dependent launch allowed (the kernel must call grid_dep_wait()).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,

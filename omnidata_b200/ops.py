@@ -85,7 +85,7 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
               out: Optional[torch.Tensor], *, bias: Optional[torch.Tensor] = None,
               bias_per_image: bool = False, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None, block_n: int = 0,
-              cta_pair: int = 0, halo: int = 0, gn_stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+              cta_pair: int = 0, halo: int = 0, epilogue: int = 0, gn_stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
               gn_groups: int = 32, gn_eps: float = 1e-5,
               head: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, bool]] = None,
               out_extent: Optional[Tuple[int, int, int]] = None) -> None:
@@ -124,6 +124,7 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
     d.block_n = block_n
     d.cta_pair = cta_pair
     d.halo = halo
+    d.epilogue = epilogue
     if head is not None:
         hw, hb, hout, hrelu = head
         _need(hw, torch.float32, "head_w"); _need(hb, torch.float32, "head_b"); _need(hout, torch.float32, "head_out")

@@ -426,3 +426,85 @@ def test_cls_and_readout_bias():
     assert torch.equal(t2[:, 1:], tokens[:, 1:])
     ref = tokens[:, 0].float() @ w[:, c:].float().t() + bias
     assert rel_l2(out, ref) < 1e-5
+
+
+# ---- specialised epilogues (odb_conv_gemm_desc.epilogue): the straight-line bias / bias+relu /
+# bias+gelu / bias+residual(TMA) bodies against the PyTorch reference AND bit-for-bit against the
+# generic epilogue, on every tile geometry the network uses (CTA pair, N tiles 64/128/256, ragged M)
+@pytest.mark.parametrize("m,k,n,block_n,pair", [
+    (577 * 8, 768, 2304, 0, 0), (577 * 8, 768, 768, 256, 1), (577 * 8, 768, 768, 256, -1), (1000, 256, 128, 0, 0),
+    (333, 160, 64, 64, 0), (130, 64, 256, 0, 0), (4000, 3072, 768, 0, 0), (128 * 296 + 5, 128, 256, 256, 1),
+])
+@pytest.mark.parametrize("mode", ["bias", "relu", "gelu", "res", "res_inplace"])
+def test_linear_fast_epilogues(m, k, n, block_n, pair, mode):
+    o = ops()
+    x = rnd(m, k).to(torch.bfloat16)
+    w = rnd(n, k, scale=k ** -0.5).to(torch.bfloat16)
+    bias = rnd(n)
+    res = rnd(m, n, seed=3).to(torch.bfloat16)
+    act = {"bias": 0, "relu": 1, "gelu": 2, "res": 0, "res_inplace": 0}[mode]
+    outs = []
+    for epi in (0, -1):
+        out = torch.full((m, n), float("nan"), device=dev(), dtype=torch.bfloat16)
+        kw = dict(bias=bias, act=act, block_n=block_n, cta_pair=pair, epilogue=epi)
+        if mode == "res":
+            kw["residual"] = res
+        elif mode == "res_inplace":
+            out.copy_(res)
+            kw["residual"] = out                       # x += f(x): the ViT residual stream
+        o.linear(x, w, out, **kw)
+        torch.cuda.synchronize()
+        outs.append(out)
+    v = x.float() @ w.float().t() + bias
+    v = [v, F.relu(v), F.gelu(v)][act]
+    if mode.startswith("res"):
+        v = v + res.float()
+    check(outs[0], v, f"fast epilogue {mode} {m}x{k}x{n}")
+    assert torch.equal(outs[0], outs[1]), f"fast vs generic epilogue differ ({mode})"
+
+
+@pytest.mark.parametrize("b,h,w_,c,n", [(2, 48, 48, 256, 256), (1, 24, 24, 256, 256), (2, 20, 36, 64, 128), (3, 12, 12, 256, 64)])
+@pytest.mark.parametrize("mode", ["relu", "res"])
+def test_conv3x3_fast_epilogues(b, h, w_, c, n, mode):
+    o = ops()
+    x = rnd(b, h, w_, c).to(torch.bfloat16)
+    w = rnd(n, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
+    bias = rnd(n)
+    skip = rnd(b, h, w_, n, seed=5).to(torch.bfloat16)
+    outs = []
+    for epi in (0, -1):
+        out = torch.full((b, h, w_, n), float("nan"), device=dev(), dtype=torch.bfloat16)
+        if mode == "relu":
+            o.conv3x3(x, o.pack_conv_weight(w), out, bias=bias, act=o.ACT_RELU, epilogue=epi)
+        else:
+            o.conv3x3(x, o.pack_conv_weight(w), out, bias=bias, residual=skip, epilogue=epi)
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = conv_ref(x, w) + bias
+    ref = F.relu(ref) if mode == "relu" else ref + skip.float()
+    check(outs[0], ref, f"conv3x3 fast epilogue {mode}")
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_gelu_epilogue_accuracy():
+    """The packed-FFMA2 exact-erf GELU of the epilogue: bf16 result = correctly rounded x*Phi(x) except for
+    rounding flips on near-ties (identity weight, so the GEMM adds nothing)."""
+    o = ops()
+    m, k = 4096, 64
+    g = torch.Generator().manual_seed(0)
+    # (for x < -8 the kernel clamps the exponent polynomial: |error| < 1e-14 absolute, not tested here)
+    x = torch.cat([torch.linspace(-8, 8, m * k // 2), torch.randn(m * k // 2, generator=g) * 2]).view(m, k)
+    x = x.to(dev()).to(torch.bfloat16)
+    eye = torch.eye(k, device=dev()).to(torch.bfloat16)
+    out = torch.empty(m, k, device=dev(), dtype=torch.bfloat16)
+    o.linear(x, eye, out, bias=torch.zeros(k, device=dev()), act=o.ACT_GELU)
+    torch.cuda.synchronize()
+    xd = x.double()
+    exact = xd * 0.5 * torch.special.erfc(-xd / math.sqrt(2.0))    # (1 + erf) cancels for x < -5
+    ref = exact.float().to(torch.bfloat16)
+    flips = (out != ref)
+    assert float(flips.float().mean()) < 2e-3
+    # a flipped element is still within one bf16 ulp of the exact value
+    err = (out.double() - exact).abs()
+    ulp = torch.maximum(exact.abs(), torch.tensor(1e-30, device=dev(), dtype=torch.float64)) * 2.0 ** -7
+    assert bool((err <= ulp + 1e-12).all())
