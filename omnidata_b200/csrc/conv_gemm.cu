@@ -83,7 +83,7 @@ ODB_DEVINL unsigned long long global_ns() {
 // convolutions: ~4x fewer instructions per 64-column chunk, the TMEM read of chunk c+1 in flight
 // while chunk c is processed, and (EPI_BIAS_RES) the residual fetched by TMA into the output
 // staging slot a few chunks ahead instead of 1024 scattered 16-byte loads per chunk.
-enum : int { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_GELU = 3, EPI_BIAS_RES = 4 };
+enum : int { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_GELU = 3, EPI_BIAS_RES = 4, EPI_GN = 5 };
 
 // ---- GroupNorm partial statistics of one epilogue warp (32 rows x 32 columns of a tile):
 // per-thread group sums over its row, then a transposing butterfly over the 32 lanes: V values are
@@ -441,7 +441,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint32_t acc = iter & 1u;
         const uint32_t acc_phase = (iter >> 1) & 1u;
         const int n0 = tn * BLOCK_N;
-        const float* bias = p.bias + static_cast<long long>(tb < p.out_b ? tb : 0) * p.bias_sb + n0 + cofs;
+        const float* bias = EPI == EPI_GN ? nullptr
+                                          : p.bias + static_cast<long long>(tb < p.out_b ? tb : 0) * p.bias_sb + n0 + cofs;
+        // EPI_GN: rows of this thread that really exist (ragged tiles / the padding tile of a pair)
+        const int gx = x0 + (row % p.tile_w), gy = y0 + (row / p.tile_w);
+        const bool valid = row < p.tile_w * p.tile_h && gx < p.out_w && gy < p.out_h && tb < p.out_b;
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         if (store_leader) ODB_TRACE_TILE(iter, 3);
@@ -453,9 +457,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           uint32_t* r = (c & 1) ? rb : ra;
           uint32_t* rn = (c & 1) ? ra : rb;
           float4 bv[8];
-          const float4* bp = reinterpret_cast<const float4*>(bias + c * 64);
+          if constexpr (EPI != EPI_GN) {
+            const float4* bp = reinterpret_cast<const float4*>(bias + c * 64);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+            for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           tmem_ld_wait_regs(r);
           if (c + 1 < kChunks) {
             tmem_ld_32x32(t_row + (c + 1) * 64 + cofs, rn);   // in flight while chunk c is processed
@@ -498,13 +507,37 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               t2 = unpack_bf16x2(q3); v[8 * j + 6] += t2.x; v[8 * j + 7] += t2.y;
             }
           }
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t addr = buf + rowoff + (static_cast<uint32_t>((half * 4 + j) ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                         "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
-                         "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j]),
+                         "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
                          : "memory");
+          }
+          if constexpr (EPI == EPI_GN) {
+            // fused GroupNorm statistics over the bf16-rounded values just staged (same order of
+            // operations as the generic epilogue: bit-identical partial sums)
+            float rq[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 t2 = unpack_bf16x2(packed[j]);
+              rq[2 * j] = valid ? t2.x : 0.f;
+              rq[2 * j + 1] = valid ? t2.y : 0.f;
+            }
+            if (tb < p.out_b) {
+              const int cpg = p.gn_cpg;
+              float* dst = p.gn_partial +
+                           ((((long long)tb * (p.tiles_x * p.tiles_y) + (ty * p.tiles_x + tx)) * 4 + quad) *
+                                p.gn_groups + (n0 + c * 64 + cofs) / cpg) * 2;
+              if (cpg == 2) gn_warp_partials<2>(rq, lane, dst);
+              else if (cpg == 4) gn_warp_partials<4>(rq, lane, dst);
+              else if (cpg == 8) gn_warp_partials<8>(rq, lane, dst);
+              else if (cpg == 16) gn_warp_partials<16>(rq, lane, dst);
+              else gn_warp_partials<32>(rq, lane, dst);
+            }
           }
           fence_proxy_async_smem();
           // slot reuse without a residual: the store of chunk g+1-NS must have read its slot before any
@@ -804,8 +837,10 @@ static int launch_fast(const ConvGemmParams& p, int block_n, bool pair, long lon
       const char* e = getenv("ODB_PAIR_RES_STAGES");
       res_stages = (e != nullptr && e[0] == '6') ? 6 : 5;
     }
-    if (EPI == EPI_BIAS_RES && res_stages == 5)
-      return launch_instance<256, 5, 4, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
+    if constexpr (EPI == EPI_BIAS_RES) {
+      if (res_stages == 5)
+        return launch_instance<256, 5, 4, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
+    }
     return launch_instance<256, 6, 2, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
   }
   switch (block_n) {
@@ -1016,6 +1051,9 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
 
   const long long total = m_tiles * p.tiles_n;
   // specialised epilogue when the flag combination allows it (see the EPI_* comment)
+  if (!hp.halo && !head && block_n >= 64 && p.bias == nullptr && !p.has_out2 && p.gn_partial != nullptr &&
+      p.residual == nullptr && p.act == ODB_ACT_NONE && d->epilogue == 0 && fast_epilogues_enabled())
+    return launch_fast<EPI_GN>(p, block_n, pair, m_tiles, total, stream);
   if (!hp.halo && !head && block_n >= 64 && p.bias != nullptr && !p.has_out2 && p.gn_partial == nullptr &&
       d->epilogue == 0 && fast_epilogues_enabled()) {
     if (p.residual == nullptr) {

@@ -336,7 +336,7 @@ def test_groupnorm(c, hw):
 
 
 @pytest.mark.parametrize("b,h,w_,c,n,pair", [(2, 96, 96, 64, 64, 0), (3, 48, 48, 128, 512, 0), (2, 24, 24, 256, 1024, 0),
-                                              (2, 48, 48, 256, 256, 1), (3, 24, 24, 1024, 256, 0)])
+                                              (2, 48, 48, 256, 256, 1), (3, 24, 24, 1024, 256, 0), (2, 20, 36, 64, 128, 0)])
 def test_conv_fused_groupnorm_stats(b, h, w_, c, n, pair):
     """GroupNorm statistics produced by the conv epilogue (+ finalize) == statistics of the stored output."""
     o = ops()
@@ -363,6 +363,12 @@ def test_conv_fused_groupnorm_stats(b, h, w_, c, n, pair):
     o.groupnorm_stats(out, stats3)
     torch.cuda.synchronize()
     assert rel_l2(stats3, stats) < 1e-6
+    # the specialised (default) and the generic epilogue: same output, same partial sums, bit for bit
+    out_g, stats_g = torch.empty_like(out), torch.empty_like(stats)
+    o.conv3x3(x, o.pack_conv_weight(w), out_g, gn_stats=(partial, stats_g), cta_pair=pair,
+              block_n=256 if pair else 0, epilogue=-1)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_g) and torch.equal(stats, stats_g)
 
 
 def test_stem_path():
