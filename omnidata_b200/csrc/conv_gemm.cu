@@ -53,6 +53,8 @@ struct ConvGemmParams {
   int head_relu;
   float* head_out;
   int halo_w;          // HALO mode: tile_w + 2 (row pitch of the halo tile), else 0
+  int a_stages;        // HALO + HEAD (resident weights): halo ring depth and stage size chosen by the host
+  int a_stage_bytes;
   float* gn_partial;   // optional GroupNorm partial sums, [b][tiles_y*tiles_x][4 quadrants][groups][2]
   int gn_cpg;          // channels per group (2..32, power of two)
   int gn_groups;
@@ -147,18 +149,28 @@ ODB_DEVINL void gn_warp_partials(const float* v, int lane, float* dst /* [groups
 constexpr int kHaloAutoMaxN = 0;             // measured: per-tap boxes (deeper ring) win on every layer of this net, halo stays opt-in
 constexpr int kHaloStageBytes = 49 * 1024;   // >= 390 rows x 128 B (tile_w = 128, tile_h = 1)
 
+// HALO + HEAD (the DPT head's 128 -> 32 convolution at full resolution): the whole weight matrix
+// (<= 18 K blocks x 32 rows = 72 KiB) stays resident in shared memory for the lifetime of the CTA and
+// only input halos stream through a (run-time sized) ring.  Without this the layer re-reads its
+// weights for every 128-pixel tile and its input nine times: it ran at the L2 throughput cap.
+constexpr int kResidentBTiles = 18;
+constexpr int kMaxAStages = 8;
+constexpr int kHaloAreaBytes = 3 * kHaloStageBytes;
+
 template <int BLOCK_N, int STAGES, int NSTAGING, bool PAIR, bool HALO, bool HEAD>
 struct SmemPlan {
+  static constexpr bool kBResident = HALO && HEAD;
   static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // a CTA pair splits B along N
   static constexpr int kBBytes = kBRows * 128;
   static constexpr int kAStages = HALO ? (HEAD ? 3 : 2) : STAGES;
   static constexpr int kAStageBytes = HALO ? kHaloStageBytes : kABytes;
   static constexpr int kAOff = 0;
   static constexpr int kBOff = kAStages * kAStageBytes;
-  static constexpr int kCOff = kBOff + STAGES * kBBytes;
+  static constexpr int kCOff = kBOff + (kBResident ? kResidentBTiles : STAGES) * kBBytes;
   static constexpr int kBarOff = kCOff + NSTAGING * kStagingBytes;
-  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], a_full[3], a_empty[3], res_full[4], tmem base pointer
-  static constexpr int kBarBytes = (2 * STAGES + 4 + 6 + 4) * 8 + 16;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], a_full[8], a_empty[8], res_full[4], b_resident,
+  // tmem base pointer
+  static constexpr int kBarBytes = (2 * STAGES + 4 + 2 * kMaxAStages + 4 + 1) * 8 + 16;
   static constexpr int kTotal = kBarOff + kBarBytes + 1024;  // +1024: manual 1 KiB alignment
   static_assert(kTotal <= 232448, "shared memory plan exceeds 227 KiB");
 };
@@ -187,9 +199,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   auto afull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + a); };
-  auto aempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 7 + a); };
-  auto rfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 10 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 14);
+  auto aempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + kMaxAStages + a); };
+  auto rfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + 2 * kMaxAStages + a); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * STAGES + 8 + 2 * kMaxAStages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 9 + 2 * kMaxAStages);
+  // halo ring geometry: compile-time, except for the resident-weights head variant
+  const int a_stages = Plan::kBResident ? p.a_stages : Plan::kAStages;
+  const uint32_t a_stage_bytes = Plan::kBResident ? static_cast<uint32_t>(p.a_stage_bytes)
+                                                  : static_cast<uint32_t>(Plan::kAStageBytes);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -206,11 +223,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       // one arrive per participating epilogue warp (of both CTAs for a pair)
       mbar_init(tempty_bar(a), (HEAD ? 4 : 8) * (PAIR ? 2 : 1));
     }
-    for (int a = 0; a < 3; ++a) {
+    for (int a = 0; a < kMaxAStages; ++a) {
       mbar_init(afull_bar(a), PAIR ? 2 : 1);
       mbar_init(aempty_bar(a), 1);
     }
     for (int a = 0; a < 4; ++a) mbar_init(rfull_bar(a), 1);
+    mbar_init(bres_bar, 1);
     mbar_fence_init();
     if (EPI == EPI_BIAS_RES) tma_prefetch_desc(&p.res_map);
     for (int v = 0; v < ODB_MAX_VIEWS; ++v) tma_prefetch_desc(&p.a_map[v]);
@@ -267,7 +285,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int tn, tx, ty, tb;
         decode(tile, tn, tx, ty, tb);
         const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
-        if constexpr (HALO) {
+        if constexpr (Plan::kBResident) {
+          if (tile == unit0) {
+            // the whole weight matrix, once (K blocks in (tap, kb) order, 32 rows each)
+            mbar_expect_tx(bres_bar, static_cast<uint32_t>(num_kb) * Plan::kBBytes);
+            for (int t = 0; t < num_kb; ++t)
+              tma_load_2d(smem_base + Plan::kBOff + t * Plan::kBBytes, &p.b_map, bres_bar, t * kKBlock, 0);
+          }
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(aempty_bar(astage), aphase ^ 1u);
+            mbar_expect_tx(afull_bar(astage), a_bytes);
+            tma_load_4d(smem_base + Plan::kAOff + astage * a_stage_bytes, &p.a_map[0], afull_bar(astage),
+                        kb * kKBlock, x0 - 1, y0 - 1, tb);
+            if (++astage == a_stages) { astage = 0; aphase ^= 1u; }
+          }
+        } else if constexpr (HALO) {
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             // ---- one halo box of the input per K block ...
             mbar_wait(aempty_bar(astage), aphase ^ 1u);
@@ -342,7 +374,29 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         tc_fence_after();
         ODB_TRACE_TILE(iter, 0);
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        if constexpr (HALO) {
+        if constexpr (Plan::kBResident) {
+          if (iter == 0) {
+            mbar_wait(bres_bar, 0);
+            tc_fence_after();
+          }
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            mbar_wait(afull_bar(astage), aphase);
+            tc_fence_after();
+            const uint32_t a_base = smem_base + Plan::kAOff + astage * a_stage_bytes;
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+              const uint32_t a_addr =
+                  a_base + static_cast<uint32_t>((p.tap_dy[tap] + 1) * p.halo_w + (p.tap_dx[tap] + 1)) * 128u;
+              const uint64_t adesc = umma_desc_sw128(a_addr);
+              const uint64_t bdesc =
+                  umma_desc_sw128(smem_base + Plan::kBOff + (tap * p.kb_per_tap + kb) * Plan::kBBytes);
+#pragma unroll
+              for (int k = 0; k < kKBlock / 16; ++k)
+                umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(aempty_bar(astage));     // the halo stage is free when these 36 MMAs retire
+            if (++astage == a_stages) { astage = 0; aphase ^= 1u; }
+          }
+        } else if constexpr (HALO) {
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             mbar_wait(afull_bar(astage), aphase);
             tc_fence_after();
@@ -850,6 +904,15 @@ static int launch_fast(const ConvGemmParams& p, int block_n, bool pair, long lon
   }
 }
 
+static bool halo_head_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ODB_HALO_HEAD");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool fast_epilogues_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -904,11 +967,26 @@ static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
     if (!is_canonical_3x3(d)) return fail(ODB_ERR_INVALID, "conv_gemm: halo mode needs a 3x3 stride-1 pad-1 conv");
     halo = true;
   } else if (d->halo == 0) {
-    halo = is_canonical_3x3(d) && (tw <= 0 || th <= 0) && d->n <= kHaloAutoMaxN;
+    // automatic only for the head tail (resident weights: 3x faster there); for the other layers the
+    // deeper per-tap ring measured faster
+    halo = is_canonical_3x3(d) && (tw <= 0 || th <= 0) &&
+           (d->n <= kHaloAutoMaxN || (d->head_out != nullptr && d->num_taps * ((d->views[0].c + 63) / 64) <= kResidentBTiles &&
+                                      halo_head_enabled()));
   }
   if (halo && (tw <= 0 || th <= 0)) {
     if (ow <= 126) { tw = ow; th = 130 / (ow + 2); if (th > oh) th = oh; }
-    else { const int segs = (ow + 127) / 128; tw = (ow + segs - 1) / segs; th = 1; }
+    else {
+      // wide images: the (tile_w, tile_h) with tile_h * (tile_w + 2) - 2 <= 128 accumulator rows that
+      // wastes the fewest MMA rows (ragged right / bottom edges included); ties -> smaller halo
+      double best = -1.0;
+      for (int h_ = 1; h_ <= 8 && h_ <= oh; ++h_) {
+        const int w_ = 130 / h_ - 2;
+        if (w_ < 8) break;
+        const double eff = (double)(w_ * h_) / 128.0 * (double)ow / (double)(((ow + w_ - 1) / w_) * w_) *
+                           (double)oh / (double)(((oh + h_ - 1) / h_) * h_);
+        if (eff > best + 1e-9) { best = eff; tw = w_; th = h_; }
+      }
+    }
   }
   if (halo && (th * (tw + 2) - 2 > kTileRows || (tw + 2) * (th + 2) * 128 > kHaloStageBytes))
     return fail(ODB_ERR_INVALID, "conv_gemm: halo tile does not fit (tile_h * (tile_w + 2) - 2 <= 128)");
@@ -1069,6 +1147,13 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   }
   if (hp.halo) {
     p.halo_w = tw + 2;
+    if (head) {
+      if (p.num_taps * p.kb_per_tap > kResidentBTiles)
+        return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: halo head tail needs taps * ceil(C / 64) <= 18");
+      p.a_stage_bytes = (((tw + 2) * (th + 2) * 128) + 1023) & ~1023;
+      p.a_stages = kHaloAreaBytes / p.a_stage_bytes;
+      if (p.a_stages > kMaxAStages) p.a_stages = kMaxAStages;
+    }
     if (pair) return launch_instance<256, 4, 2, false, true, true>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
     switch (block_n) {
       case 256: return launch_instance<256, 2, 2, false, false, true>(p, total, stream);

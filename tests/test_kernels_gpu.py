@@ -165,9 +165,10 @@ def test_conv3x3_halo_mode(b, h, w_, c, n, bn, pair, hmode=1):
     assert rel_l2(stats, stats_b) < 1e-4
 
 
-def test_head_tail_halo():
+@pytest.mark.parametrize("b,h,w_,c", [(2, 64, 384, 128), (1, 66, 200, 128), (2, 40, 100, 64), (1, 384, 384, 128)])
+def test_head_tail_halo(b, h, w_, c):
+    """Head tail with the resident-weights halo kernel (the default for this layer) and with per-tap boxes."""
     o = ops()
-    b, h, w_, c = 2, 64, 384, 128
     x = rnd(b, h, w_, c).to(torch.bfloat16)
     w = rnd(32, c, 3, 3, scale=(9 * c) ** -0.5).to(torch.bfloat16)
     bias, hw, hb = rnd(32), rnd(3, 32, scale=0.3), rnd(3, scale=0.1)
