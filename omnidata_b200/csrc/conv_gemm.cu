@@ -883,6 +883,8 @@ static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_
 template <int EPI>
 static int launch_fast(const ConvGemmParams& p, int block_n, bool pair, long long m_tiles, long long total,
                        cudaStream_t stream) {
+  if (pair && block_n == 128)
+    return launch_instance<128, 6, 4, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
   if (pair) {
     // the residual variant trades one of the six operand stages for two more staging slots, so that
     // the residual TMA load runs two chunks ahead of its use (measured: see DESIGN.md)
@@ -908,6 +910,15 @@ static bool halo_head_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ODB_HALO_HEAD");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static bool pair128_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ODB_PAIR128");
     v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
@@ -1019,9 +1030,11 @@ static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
   bool pair = false;
   if (d->cta_pair == 1) pair = true;
   else if (d->cta_pair == 0)
-    pair = (block_n == 256 && !head && hp->m_tiles * (N / block_n) >= 2LL * num_sms());
-  if (pair && (block_n != 256 || head))
-    return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: cta_pair needs block_n == 256 and no head tail");
+    pair = !head && hp->m_tiles * (N / block_n) >= 2LL * num_sms() &&
+           (block_n == 256 ||
+            (block_n == 128 && !halo && (long long)d->num_taps * C >= 1024 && pair128_enabled()));
+  if (pair && (!(block_n == 256 || (block_n == 128 && !halo)) || head))
+    return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: cta_pair needs block_n 256 (or 128 without halo) and no head tail");
   hp->block_n = block_n; hp->pair = pair; hp->head = head;
   return ODB_OK;
 }
@@ -1164,6 +1177,8 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
         return launch_instance<32, 8, 0, true, false, true>(p, total, stream);
     }
   }
+  if (pair && block_n == 128)
+    return launch_instance<128, 6, 4, false, true, false>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
   if (pair) return launch_instance<256, 6, 2, false, true, false>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
   switch (block_n) {
     case 256: return launch_instance<256, 4, 2, false, false, false>(p, total, stream);

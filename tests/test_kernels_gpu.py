@@ -337,7 +337,8 @@ def test_groupnorm(c, hw):
 
 
 @pytest.mark.parametrize("b,h,w_,c,n,pair", [(2, 96, 96, 64, 64, 0), (3, 48, 48, 128, 512, 0), (2, 24, 24, 256, 1024, 0),
-                                              (2, 48, 48, 256, 256, 1), (3, 24, 24, 1024, 256, 0), (2, 20, 36, 64, 128, 0)])
+                                              (2, 48, 48, 256, 256, 1), (3, 24, 24, 1024, 256, 0), (2, 20, 36, 64, 128, 0),
+                                              (3, 48, 48, 128, 128, 1)])
 def test_conv_fused_groupnorm_stats(b, h, w_, c, n, pair):
     """GroupNorm statistics produced by the conv epilogue (+ finalize) == statistics of the stored output."""
     o = ops()
@@ -346,8 +347,8 @@ def test_conv_fused_groupnorm_stats(b, h, w_, c, n, pair):
     out = torch.empty((b, h, w_, n), device=dev(), dtype=torch.bfloat16)
     partial = torch.full((b * 128 * 4 * 32 * 2,), float("nan"), device=dev())
     stats = torch.full((b, 32, 2), float("nan"), device=dev())
-    o.conv3x3(x, o.pack_conv_weight(w), out, gn_stats=(partial, stats), cta_pair=pair,
-              block_n=256 if pair else 0)
+    bn = (256 if n % 256 == 0 else 128) if pair else 0
+    o.conv3x3(x, o.pack_conv_weight(w), out, gn_stats=(partial, stats), cta_pair=pair, block_n=bn)
     torch.cuda.synchronize()
     check(out, conv_ref(x, w, padding=1), "conv with fused stats")
     y = out.double().view(b, h * w_, 32, n // 32)
@@ -356,7 +357,7 @@ def test_conv_fused_groupnorm_stats(b, h, w_, c, n, pair):
     assert rel_l2(stats[..., 0], mean) < 1e-5 or float((stats[..., 0].double() - mean).abs().max()) < 1e-6
     assert rel_l2(stats[..., 1], 1.0 / torch.sqrt(var + 1e-5)) < 1e-5
     stats2 = torch.empty_like(stats)
-    o.conv3x3(x, o.pack_conv_weight(w), out, gn_stats=(partial, stats2), cta_pair=pair, block_n=256 if pair else 0)
+    o.conv3x3(x, o.pack_conv_weight(w), out, gn_stats=(partial, stats2), cta_pair=pair, block_n=bn)
     torch.cuda.synchronize()
     assert torch.equal(stats, stats2)                      # deterministic
     # and it agrees with the standalone statistics kernel
@@ -366,8 +367,7 @@ def test_conv_fused_groupnorm_stats(b, h, w_, c, n, pair):
     assert rel_l2(stats3, stats) < 1e-6
     # the specialised (default) and the generic epilogue: same output, same partial sums, bit for bit
     out_g, stats_g = torch.empty_like(out), torch.empty_like(stats)
-    o.conv3x3(x, o.pack_conv_weight(w), out_g, gn_stats=(partial, stats_g), cta_pair=pair,
-              block_n=256 if pair else 0, epilogue=-1)
+    o.conv3x3(x, o.pack_conv_weight(w), out_g, gn_stats=(partial, stats_g), cta_pair=pair, block_n=bn, epilogue=-1)
     torch.cuda.synchronize()
     assert torch.equal(out, out_g) and torch.equal(stats, stats_g)
 
@@ -441,6 +441,7 @@ def test_cls_and_readout_bias():
 @pytest.mark.parametrize("m,k,n,block_n,pair", [
     (577 * 8, 768, 2304, 0, 0), (577 * 8, 768, 768, 256, 1), (577 * 8, 768, 768, 256, -1), (1000, 256, 128, 0, 0),
     (333, 160, 64, 64, 0), (130, 64, 256, 0, 0), (4000, 3072, 768, 0, 0), (128 * 296 + 5, 128, 256, 256, 1),
+    (128 * 300 + 77, 1152, 128, 128, 1), (128 * 300 + 77, 1152, 128, 128, -1),
 ])
 @pytest.mark.parametrize("mode", ["bias", "relu", "gelu", "res", "res_inplace"])
 def test_linear_fast_epilogues(m, k, n, block_n, pair, mode):
