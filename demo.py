@@ -18,7 +18,6 @@ from pathlib import Path
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from PIL import Image
 
 _VIRIDIS = np.array([[68, 1, 84], [72, 40, 120], [62, 74, 137], [49, 104, 142], [38, 130, 142], [31, 158, 137],
@@ -88,27 +87,36 @@ def main(argv=None):
     os.makedirs(args.output_path, exist_ok=True)
     model = build_model(args.task, args.weights_dir, args.synthetic_weights, device)
     image_size = 384
+    from omnidata_b200 import imageproc
+    preprocess = imageproc.DevicePreprocessor(args.task, image_size, device)
 
     def save_outputs(img_path, name):
         with torch.no_grad():
             save_path = os.path.join(args.output_path, f"{name}_{args.task}.png")
             print(f"Reading input {img_path} ...")
             img = Image.open(img_path)
-            t = to_tensor(resize_center_crop(img, image_size))[:3]
-            if args.task == "depth":
-                t = (t - 0.5) / 0.5                                   # Normalize(0.5, 0.5), demo.py:92-95
-            t = t.unsqueeze(0).to(device)
+            if img.mode in ("RGB", "L"):
+                # Resize(384, BILINEAR) + CenterCrop + ToTensor [+ Normalize] on the device: the decoded
+                # 8-bit image is uploaded once, the kernels reproduce Pillow's fixed-point resize exactly
+                t = preprocess(np.array(img)).unsqueeze(0)
+            else:
+                # RGBA / palette / 16-bit: Pillow converts or premultiplies before resizing — keep its path
+                t = to_tensor(resize_center_crop(img, image_size))[:3]
+                if args.task == "depth":
+                    t = (t - 0.5) / 0.5                               # Normalize(0.5, 0.5), demo.py:92-95
+                t = t.unsqueeze(0).to(device)
+                if t.shape[1] == 1:
+                    t = t.repeat_interleave(3, 1)
             resize_center_crop(img, 512).save(os.path.join(args.output_path, f"{name}_rgb.png"))
-            if t.shape[1] == 1:
-                t = t.repeat_interleave(3, 1)
-            output = model(t).clamp(min=0, max=1)
+            output = model(t)
             if args.task == "depth":
-                output = F.interpolate(output.unsqueeze(0), (512, 512), mode="bicubic").squeeze(0)
-                output = 1 - output.clamp(0, 1)
+                # clamp(0,1) -> bicubic 512 -> clamp(0,1) -> 1 - x in one kernel (demo.py:140-145)
+                output = imageproc.bicubic_resize(output.float(), (512, 512), clamp_in=True, clamp_out=True, invert=True)
                 Image.fromarray(viridis(output.detach().cpu().squeeze().numpy())).save(save_path)
             else:
-                arr = (output[0].detach().cpu().permute(1, 2, 0).numpy() * 255.0).round().astype(np.uint8)
-                Image.fromarray(arr).save(save_path)
+                # clamp(0,1) + ToPILImage: uint8 HWC = trunc(x * 255) (demo.py:140,150)
+                arr = imageproc.to_uint8_hwc(output[0].float(), clamp01=True)
+                Image.fromarray(arr.cpu().numpy()).save(save_path)
             print(f"Writing output {save_path} ...")
 
     p = Path(args.img_path)

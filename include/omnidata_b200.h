@@ -206,6 +206,36 @@ int odb_vnl_loss_fwd(const float* first, const float* second, const int32_t* p1,
 
 int odb_fill_zero(void* ptr, int64_t bytes, void* stream);
 
+/* ---- image pre- / post-processing either side of the forward ------------
+ *
+ * odb_pil_resize_crop_to_tensor replaces transforms.Resize(384, BILINEAR) + CenterCrop(384) + ToTensor
+ * [+ Normalize(0.5, 0.5)] of omnidata_tools/torch/demo.py:74-76,92-95 for an 8-bit image already on the
+ * device (src: uint8 [src_h][src_w][channels], channels 1 or 3, row pitch src_pitch bytes).  Pillow's
+ * resize is an antialiased two-pass triangle filter in 8-bit fixed point (ImagingResample, 22 fractional
+ * bits, 8-bit intermediate); the kernels evaluate exactly that, so `out` is bit-identical to the
+ * reference's input tensor.  The host supplies Pillow's coefficient tables restricted to the crop
+ * window (omnidata_b200/imageproc.py): bounds_* int32 [n][2] = (first source index, tap count),
+ * kk_* int32 [n][ksize_*] fixed-point weights; bounds_h / kk_h for the out_w kept columns, bounds_v / kk_v
+ * for the out_h kept rows; the horizontal pass runs over source rows [row0, row0 + nrows) into
+ * tmp (uint8 [nrows][out_w][channels]).  out: fp32 [3][out_h][out_w] = (u8 / 255 [- mean) / std]
+ * (a single channel is replicated, demo.py:137-138); out_u8 (optional): the cropped 8-bit image. */
+int odb_pil_resize_crop_to_tensor(const void* src, int32_t src_h, int32_t src_w, int32_t channels,
+                                  int64_t src_pitch, const int32_t* bounds_h, const int32_t* kk_h,
+                                  int32_t ksize_h, const int32_t* bounds_v, const int32_t* kk_v, int32_t ksize_v,
+                                  int32_t row0, int32_t nrows, int32_t out_h, int32_t out_w, int32_t normalize,
+                                  float mean, float stdv, void* tmp, float* out, void* out_u8, void* stream);
+
+/* F.interpolate(x, (out_h, out_w), mode='bicubic') on fp32 planes [planes][in_h][in_w] (align_corners
+ * False, A = -0.75) with the clamps of demo.py:140-145 fused: flags bit 0 = clamp the input to [0,1],
+ * bit 1 = clamp the result to [0,1], bit 2 = 1 - result. */
+int odb_bicubic_resize_f32(const float* in, int32_t planes, int32_t in_h, int32_t in_w, int32_t out_h,
+                           int32_t out_w, int32_t flags, float* out, void* stream);
+
+/* transforms.ToPILImage() on a float CHW tensor (demo.py:150): out uint8 [h][w][c] = trunc(x * 255);
+ * clamp01 != 0 applies the reference's .clamp(0, 1) first (demo.py:140). */
+int odb_f32_chw_to_u8_hwc(const float* in, int32_t c, int32_t h, int32_t w, int32_t clamp01, void* out,
+                          void* stream);
+
 /* Introspection (no GPU needed). */
 int odb_abi_version(void);
 const char* odb_last_error(void);

@@ -89,6 +89,13 @@ _SIGNATURES = {
     "odb_vnl_loss_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_float] * 3 + [C.c_int32, C.c_void_p,
                                                                                         C.c_void_p, C.c_void_p]),
     "odb_fill_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "odb_pil_resize_crop_to_tensor": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                                C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "odb_bicubic_resize_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p]),
+    "odb_f32_chw_to_u8_hwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "odb_abi_version": (C.c_int, []),
     "odb_last_error": (C.c_char_p, []),
     "odb_launch_count": (C.c_int64, []),
