@@ -353,34 +353,46 @@ __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
 }
 
 // Stem im2col: fp32 NCHW -> bf16 [b*oh*ow][kpad], column (ky*7+kx)*3+ch, TF-SAME pad (2,3), stride 2.
-// Thread = (output pixel, 8-column group); the 8 columns are gathered with scalar loads that hit L1.
+// One block per output row: the 7 input rows x 3 channels it reads are staged ONCE in shared memory
+// with coalesced loads (zero-filled borders = the convolution padding), then thread = (output pixel,
+// 8-column group) gathers its 8 columns from shared memory through a 160-entry offset table — no
+// per-element div/mod, no bounds tests, no redundant global loads (the first version issued 8 scalar
+// global loads and ~40 integer ops per 16 output bytes and ran at 1.2 TB/s).
+constexpr int kStemMaxW = 1792;                      // staged rows: 21 x (w + 5) floats <= 151 KiB
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x,
                                                           bf16* __restrict__ cols, int b, int h,
                                                           int w, int kpad) {
   grid_dep_wait();
   grid_dep_launch();
+  extern __shared__ float stage[];                   // [3 ch][7 ky][w + 5], then int off[kpad]
+  const int pitch = w + 5;
+  int* off = reinterpret_cast<int*>(stage + 21 * pitch);
   const int oh = h / 2, ow = w / 2;
   const int groups8 = kpad >> 3;
-  const int oy = blockIdx.x % oh, bi = blockIdx.x / oh;   // one block per output row
+  const int oy = blockIdx.x % oh, bi = blockIdx.x / oh;
   const float* xb = x + (long long)bi * 3 * h * w;
+  // input rows 2*oy - 2 .. 2*oy + 4, columns -2 .. w + 2
+  for (int i = threadIdx.x; i < 21 * pitch; i += blockDim.x) {
+    const int r = i / pitch, px = i - r * pitch;     // r = ch * 7 + ky
+    const int ch = r / 7, ky = r - ch * 7;
+    const int iy = 2 * oy + ky - 2, ix = px - 2;
+    stage[i] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(xb + ((long long)ch * h + iy) * w + ix) : 0.f;
+  }
+  for (int col = threadIdx.x; col < kpad; col += blockDim.x) {
+    const int ch = col % 3, kx = (col / 3) % 7, ky = col / 21;
+    off[col] = col < 147 ? (ch * 7 + ky) * pitch + kx : -1;
+  }
+  __syncthreads();
   bf16* crow = cols + ((long long)bi * oh + oy) * ow * kpad;
   const int total = ow * groups8;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int g = i % groups8;
     const int ox = i / groups8;
+    const int g = i - ox * groups8;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int col = g * 8 + j;
-      float val = 0.f;
-      if (col < 147) {
-        const int ch = col % 3;
-        const int kx = (col / 3) % 7;
-        const int ky = col / 21;
-        const int iy = 2 * oy + ky - 2, ix = 2 * ox + kx - 2;
-        if (iy >= 0 && iy < h && ix >= 0 && ix < w) val = __ldg(xb + (ch * h + iy) * w + ix);
-      }
-      v[j] = val;
+      const int o = off[g * 8 + j];
+      v[j] = o >= 0 ? stage[o + 2 * ox] : 0.f;
     }
     store8(crow + i * 8, v);
   }
@@ -484,9 +496,12 @@ __global__ void __launch_bounds__(256) readout_cls_bias_kernel(const bf16* __res
   if (lane == 0) out[wid] = acc + __ldg(bias + n);
 }
 
-static int grid_for(long long work_items, int block, int max_blocks_per_sm = 8) {
-  long long blocks = (work_items + block - 1) / block;
-  const long long cap = (long long)num_sms() * max_blocks_per_sm;
+// grid.x of a (blocks per image, image) launch: the per-image block count, capped by the share of
+// the chip-wide block budget one image gets
+static int per_image_grid(long long items_per_image, int block, int b, int max_blocks_per_sm = 8) {
+  long long blocks = (items_per_image + block - 1) / block;
+  long long cap = ((long long)num_sms() * max_blocks_per_sm + b - 1) / b;
+  if (cap < 1) cap = 1;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -580,8 +595,9 @@ extern "C" int odb_groupnorm_apply(const void* x, const float* stats, const floa
     return fail(ODB_ERR_INVALID, "groupnorm_apply: bad argument");
   if (res_stats && (!res || !res_gamma || !res_beta))
     return fail(ODB_ERR_INVALID, "groupnorm_apply: res_stats needs res, res_gamma, res_beta");
-  int gx = grid_for((long long)hw * (c / 8), 256) / b;
-  if (gx < 1) gx = 1;
+  // blocks per image: enough for one 16-byte item per thread, capped so that the whole grid
+  // (gx * b blocks) stays within ~8 resident blocks per SM
+  const int gx = per_image_grid((long long)hw * (c / 8), 256, b);
   dim3 grid(gx, b);
   launch_pdl(groupnorm_apply_kernel, grid, dim3(256), 3 * c * sizeof(float), stream,
              static_cast<const bf16*>(x), stats, gamma, beta, static_cast<const bf16*>(res), res_stats,
@@ -597,8 +613,7 @@ extern "C" int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const
   if (!x || !stats || !gamma || !beta || !y || h < 2 || w < 2 || (h & 1) || (w & 1) ||
       !gn_args_ok(b, h * w, c, groups))
     return fail(ODB_ERR_INVALID, "stem_gn_relu_maxpool: bad argument");
-  int gx = grid_for((long long)(h / 2) * (w / 2) * (c / 8), 256) / b;
-  if (gx < 1) gx = 1;
+  const int gx = per_image_grid((long long)(h / 2) * (w / 2) * (c / 8), 256, b);
   dim3 grid(gx, b);
   launch_pdl(stem_gn_relu_maxpool_kernel, grid, dim3(256), 2 * c * sizeof(float), stream,
              static_cast<const bf16*>(x), stats, gamma, beta, static_cast<bf16*>(y), h, w, c, groups);
@@ -611,7 +626,17 @@ extern "C" int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !cols || b < 1 || h < 2 || w < 2 || (h & 1) || (w & 1) || kpad < 152 || kpad % 8)
     return fail(ODB_ERR_INVALID, "stem_im2col: bad argument");
-  launch_pdl(stem_im2col_kernel, dim3(b * (h / 2)), dim3(256), 0, stream, x, static_cast<bf16*>(cols), b, h, w,
+  if (w > kStemMaxW) return fail(ODB_ERR_UNSUPPORTED, "stem_im2col: width above 1792 not supported");
+  const size_t smem = (size_t)21 * (w + 5) * sizeof(float) + (size_t)kpad * sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         21 * (kStemMaxW + 5) * (int)sizeof(float) + 4096);
+    if (e != cudaSuccess) return fail_cuda(e, "stem_im2col: cudaFuncSetAttribute");
+    configured = true;
+  }
+  if (kpad > 1024) return fail(ODB_ERR_INVALID, "stem_im2col: kpad too large");
+  launch_pdl(stem_im2col_kernel, dim3(b * (h / 2)), dim3(256), smem, stream, x, static_cast<bf16*>(cols), b, h, w,
              kpad);
   count_launch();
   return check_launch("stem_im2col");
