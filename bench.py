@@ -333,9 +333,9 @@ def main():
                         "bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
                         "frac": round(achieved / peak, 4),
                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four ViT GEMM
-                        # shapes, from the committed `ncu --set full` capture (profiles/r01c_vit_gemm_*.csv);
+                        # shapes, from the committed `ncu --set full` capture (profiles/r01d_vit_gemm_*.csv);
                         # algorithmic bytes per launch (operands + output + residual, bf16): 131 MB
-                        "traffic": 92.0e6, "traffic_unit": "bytes/launch (ncu, profiles/r01c)",
+                        "traffic": 92.8e6, "traffic_unit": "bytes/launch (ncu, profiles/r01d)",
                         "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
                         "avg_launch_ms": round(v["ms"] / v["launches"], 4),
                         "how": "CUDA events around every launch on the launching stream, eager instrumented pass "
