@@ -204,6 +204,17 @@ int odb_vnl_loss_fwd(const float* first, const float* second, const int32_t* p1,
                      const int32_t* p3, int32_t n_points, int32_t b, int32_t h, int32_t w, float fx, float fy,
                      float delta_z, int32_t select, float* out1, float* group_loss, void* stream);
 
+/* Normal-training loss pair (train_normal.py:247-258): with
+ * preds = clamp(prediction, 0, 1) when clamp_prediction != 0,
+ *   l1  = masked_l1_loss(preds, target, mask x3)                 (losses/masked_losses.py:4-7)
+ *   cos = masked_cosine_angular_loss(preds, target, mask x3)      (losses/masked_losses.py:14-23)
+ *   out3 = (cos + 10 * l1, l1, cos).
+ * prediction, target fp32 [b][3][h][w]; mask_valid uint8 [b][h][w] (odb_make_valid_mask); workspace: 3 * b doubles.
+ * Forward only; deterministic (fixed-order fp64 partial sums). */
+int odb_normal_loss_fwd(const float* prediction, const float* target, const uint8_t* mask_valid, int32_t b,
+                        int32_t h, int32_t w, int32_t clamp_prediction, float* out3, double* workspace,
+                        void* stream);
+
 int odb_fill_zero(void* ptr, int64_t bytes, void* stream);
 
 /* ---- image pre- / post-processing either side of the forward ------------

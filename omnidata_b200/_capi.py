@@ -88,6 +88,8 @@ _SIGNATURES = {
                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "odb_vnl_loss_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_float] * 3 + [C.c_int32, C.c_void_p,
                                                                                         C.c_void_p, C.c_void_p]),
+    "odb_normal_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "odb_fill_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "odb_pil_resize_crop_to_tensor": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

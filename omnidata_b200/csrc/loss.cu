@@ -251,6 +251,66 @@ __global__ void midas_finalize_kernel(MidasWs ws, int b_n, int scales, float alp
   out3[0] = ssi + alpha * reg;
 }
 
+// ------------------------------------------------------------------------------------------ normal-training losses
+// masked_l1_loss + masked_cosine_angular_loss (losses/masked_losses.py:4-7,14-23) as train_normal.py:247-258
+// uses them: preds = clamp(model(rgb), 0, 1); mask_valid [b,1,h,w] repeated over the 3 channels;
+// loss = cos + 10 * l1.  grid (b): per-image fp64 partials (sum |p - t| over valid pixels x 3 channels,
+// sum of -cos over valid pixels, valid pixel count), fixed order.
+__global__ void __launch_bounds__(kLossThreads) normal_loss_partial_kernel(const float* __restrict__ pred,
+                                                                           const float* __restrict__ target,
+                                                                           const uint8_t* __restrict__ mask,
+                                                                           int hw, int clamp_pred,
+                                                                           double* __restrict__ partial) {
+  __shared__ double scratch[32];
+  const int b = blockIdx.x;
+  const float* p = pred + (long long)b * 3 * hw;
+  const float* g = target + (long long)b * 3 * hw;
+  const uint8_t* mk = mask + (long long)b * hw;
+  double l1 = 0.0, cs = 0.0, cnt = 0.0;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    if (!mk[i]) continue;
+    float pv[3], gv[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      pv[c] = p[c * hw + i];
+      if (clamp_pred) pv[c] = fminf(fmaxf(pv[c], 0.f), 1.f);          // train_normal.py:249
+      gv[c] = g[c * hw + i];
+      l1 += (double)fabsf(pv[c] - gv[c]);
+    }
+    float pn = 0.f, gn = 0.f, dot = 0.f;
+    float pc[3], gc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      pc[c] = fminf(fmaxf(2.f * pv[c] - 1.f, -1.f), 1.f);
+      gc[c] = fminf(fmaxf(2.f * gv[c] - 1.f, -1.f), 1.f);
+      pn = fmaf(pc[c], pc[c], pn);
+      gn = fmaf(gc[c], gc[c], gn);
+    }
+    // F.normalize(p=2, dim=1): x / max(||x||, 1e-12)
+    const float pin = __fdiv_rn(1.f, fmaxf(__fsqrt_rn(pn), 1e-12f));
+    const float gin = __fdiv_rn(1.f, fmaxf(__fsqrt_rn(gn), 1e-12f));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dot = fmaf(pc[c] * pin, gc[c] * gin, dot);
+    cs -= (double)dot;
+    cnt += 1.0;
+  }
+  const double r0 = block_sum_d(l1, scratch);
+  const double r1 = block_sum_d(cs, scratch);
+  const double r2 = block_sum_d(cnt, scratch);
+  if (threadIdx.x == 0) { partial[b * 3 + 0] = r0; partial[b * 3 + 1] = r1; partial[b * 3 + 2] = r2; }
+}
+
+__global__ void normal_loss_finalize_kernel(const double* __restrict__ partial, int b_n, float* __restrict__ out3) {
+  if (threadIdx.x != 0) return;
+  double l1 = 0.0, cs = 0.0, cnt = 0.0;
+  for (int b = 0; b < b_n; ++b) { l1 += partial[b * 3]; cs += partial[b * 3 + 1]; cnt += partial[b * 3 + 2]; }
+  const float l1_loss = (float)(l1 / (3.0 * cnt));     // element sum / mask_valid.sum() (mask repeated x3)
+  const float cos_loss = (float)(cs / cnt);            // mean over valid pixels (NaN when there are none, as the reference)
+  out3[1] = l1_loss;
+  out3[2] = cos_loss;
+  out3[0] = cos_loss + 10.0f * l1_loss;
+}
+
 // ------------------------------------------------------------------------------------------ virtual normal loss
 struct Vec3 { float x, y, z; };
 ODB_DEVINL Vec3 sub3(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
@@ -402,6 +462,21 @@ extern "C" int odb_midas_loss_fwd(const float* prediction, const float* target, 
   midas_finalize_kernel<<<1, 32, 0, stream>>>(ws, b, scales, alpha, out3);
   count_launch();
   return check_launch("midas_loss_fwd");
+}
+
+extern "C" int odb_normal_loss_fwd(const float* prediction, const float* target, const uint8_t* mask_valid,
+                                   int32_t b, int32_t h, int32_t w, int32_t clamp_prediction, float* out3,
+                                   double* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!prediction || !target || !mask_valid || !out3 || !workspace || b < 1 || h < 1 || w < 1 ||
+      (long long)h * w > 0x7fffffffLL / 3)
+    return fail(ODB_ERR_INVALID, "normal_loss_fwd: bad argument");
+  normal_loss_partial_kernel<<<b, kLossThreads, 0, stream>>>(prediction, target, mask_valid, h * w,
+                                                            clamp_prediction, workspace);
+  count_launch();
+  normal_loss_finalize_kernel<<<1, 32, 0, stream>>>(workspace, b, out3);
+  count_launch();
+  return check_launch("normal_loss_fwd");
 }
 
 extern "C" int odb_vnl_loss_fwd(const float* first, const float* second, const int32_t* p1, const int32_t* p2,

@@ -105,3 +105,31 @@ def depth_step_losses(depth_preds, depth_gt, mask_float, midas: MidasLoss, vnl: 
     if train and global_step < 15000:
         return {"ssi_loss": ssi, "reg_loss": 0, "vn_loss": 0, "depth_loss": ssi}
     return {"ssi_loss": ssi, "reg_loss": reg, "vn_loss": vn, "depth_loss": ssi + 0.1 * reg + 10 * vn}
+
+
+def normal_losses(normal_preds: torch.Tensor, normal_gt: torch.Tensor, mask_valid: torch.Tensor,
+                  clamp_preds: bool = False):
+    """masked_l1_loss + masked_cosine_angular_loss (losses/masked_losses.py:4-7,14-23) in one pass.
+    normal_preds, normal_gt: [B,3,H,W]; mask_valid: bool/uint8 [B,1,H,W] or the reference's
+    `.repeat_interleave(3, 1)` form [B,3,H,W] (its first channel is used, as masked_cosine_angular_loss does).
+    Returns (cos + 10 * l1, l1, cos)."""
+    p, g = _f32(normal_preds, "normal_preds"), _f32(normal_gt, "normal_gt")
+    if p.dim() != 4 or p.shape[1] != 3 or g.shape != p.shape:
+        raise _capi.OdbError("normal_losses: [B,3,H,W] tensors expected")
+    if not mask_valid.is_cuda:
+        raise _capi.OdbError("mask_valid: CUDA tensor required (no CPU path)")
+    m = mask_valid[:, 0].to(torch.uint8).contiguous()
+    b, _, h, w = p.shape
+    out = torch.empty(3, device=p.device, dtype=torch.float32)
+    ws = torch.empty(3 * b, device=p.device, dtype=torch.float64)
+    check(lib().odb_normal_loss_fwd(p.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, 1 if clamp_preds else 0,
+                                    out.data_ptr(), ws.data_ptr(), _stream()), "odb_normal_loss_fwd")
+    return out[0], out[1], out[2]
+
+
+def normal_step_losses(normal_preds, normal_gt, mask_float):
+    """The loss arithmetic of train_normal.py:247-265 (forward only): clamp, make_valid_mask repeated over
+    the three channels, l1 + cosine losses, normal_loss = cos + 10 * l1."""
+    mask_valid = make_valid_mask(mask_float)
+    total, l1, cos = normal_losses(normal_preds, normal_gt, mask_valid, clamp_preds=True)
+    return {"l1_loss": l1, "cos_loss": cos, "normal_loss": total}

@@ -117,3 +117,41 @@ def loss_inputs(seed: int = 0, batch: int = 2, size: int = 384):
     pred[torch.rand(batch, 1, size, size, generator=g) < 0.01] = 0.0
     mask_float = (torch.rand(batch, 1, size, size, generator=g) > 0.03).float()
     return pred, gt, mask_float
+
+
+def masked_l1_loss(preds, target, mask_valid):
+    """losses/masked_losses.py:4-7."""
+    e = (preds - target).abs()
+    e = e * mask_valid
+    return e.sum() / mask_valid.sum()
+
+
+def masked_cosine_angular_loss(preds, target, mask_valid):
+    """losses/masked_losses.py:14-23."""
+    preds = (2 * preds - 1).clamp(-1, 1)
+    target = (2 * target - 1).clamp(-1, 1)
+    mv = mask_valid[:, 0, :, :].bool()
+    preds = preds.permute(0, 2, 3, 1)[mv, :]
+    target = target.permute(0, 2, 3, 1)[mv, :]
+    pn = F.normalize(preds, p=2, dim=1)
+    tn = F.normalize(target, p=2, dim=1)
+    return torch.mean(-torch.sum(pn * tn, dim=1))
+
+
+def normal_step(normal_preds, normal_gt, mask_float):
+    """train_normal.py:247-265 -> (normal_loss, l1_loss, cos_loss)."""
+    normal_preds = torch.clamp(normal_preds, 0, 1)
+    mask_valid = make_valid_mask(mask_float).repeat_interleave(3, 1)
+    l1 = masked_l1_loss(normal_preds, normal_gt, mask_valid)
+    cos = masked_cosine_angular_loss(normal_preds, normal_gt, mask_valid)
+    return cos + 10 * l1, l1, cos
+
+
+def normal_loss_inputs(seed: int = 0, batch: int = 2, size: int = 384):
+    """Seeded normal-map-like tensors in [0, 1] (prediction slightly outside to exercise the clamp)."""
+    g = torch.Generator().manual_seed(200 + seed)
+    gt = torch.rand(batch, 3, size, size, generator=g)
+    # a prediction correlated with the target (mean cosine ~0.9: a well-conditioned loss value), 10 % outside [0, 1]
+    pred = (gt + 0.25 * torch.randn(batch, 3, size, size, generator=g)) * 1.2 - 0.1
+    mask_float = (torch.rand(batch, 1, size, size, generator=g) > 0.03).float()
+    return pred, gt, mask_float

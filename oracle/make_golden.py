@@ -9,6 +9,7 @@ What it pins:
     at fixed indices.  Taps come from the reference's own `pretrained.activations` hooks
     (modules/midas/vit.py:158-165) and from forward hooks on scratch.* modules.
   * losses_seed0.pt — reference MidasLoss / VNL_Loss values on seeded inputs (config 5 inputs).
+  * normal_losses_seed0.pt — reference masked L1 / cosine-angular losses (train_normal.py loss pair).
 The fixtures are small (< 300 KiB in total) so that they can be committed.
 """
 from __future__ import annotations
@@ -92,6 +93,20 @@ def main():
     torch.save({"midas_total": float(total), "midas_ssi": float(ssi), "midas_reg": float(reg), "vnl": float(vnl),
                 "mask_valid_count": int(mask.sum())}, GOLDEN / "losses_seed0.pt")
     print("losses", float(total), float(ssi), float(reg), float(vnl))
+    make_normal_loss_golden()
+
+
+def make_normal_loss_golden():
+    """normal_losses_seed0.pt — reference masked_l1_loss / masked_cosine_angular_loss (losses/masked_losses.py,
+    unmodified) as train_normal.py:247-258 calls them, on loss_oracle.normal_loss_inputs(0)."""
+    from . import loss_oracle
+    ref_l1, ref_cos = rl.load_reference_masked_losses()
+    pred, gt, mf = loss_oracle.normal_loss_inputs(0)
+    p = torch.clamp(pred, 0, 1)
+    mask = loss_oracle.make_valid_mask(mf).repeat_interleave(3, 1)
+    l1, cos = float(ref_l1(p.clone(), gt.clone(), mask)), float(ref_cos(p.clone(), gt.clone(), mask))
+    torch.save({"l1": l1, "cos": cos}, GOLDEN / "normal_losses_seed0.pt")
+    print("normal losses", l1, cos)
 
 
 if __name__ == "__main__":

@@ -45,3 +45,12 @@ def load_reference_losses():
     midas = importlib.import_module("losses.midas_loss")
     vnl = importlib.import_module("losses.virtual_normal_loss")
     return midas.MidasLoss, vnl.VNL_Loss
+
+
+def load_reference_masked_losses():
+    """reference masked_l1_loss / masked_cosine_angular_loss, unmodified (losses/masked_losses.py)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present")
+    _prepare_path()
+    m = importlib.import_module("losses.masked_losses")
+    return m.masked_l1_loss, m.masked_cosine_angular_loss

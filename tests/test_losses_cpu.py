@@ -42,3 +42,26 @@ def test_loss_oracle_equals_unmodified_reference():
         pts = loss_oracle.vnl_select_index(384, 384)
         mine_v = loss_oracle.vnl_loss(pred, gt, pts)
         assert abs(float(ref_v) - float(mine_v)) <= 1e-6 * abs(float(ref_v))
+
+
+@pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree not on this box")
+def test_normal_loss_oracle_equals_unmodified_reference():
+    """masked_l1_loss / masked_cosine_angular_loss restatement == the reference functions (train_normal.py:247-258 mix)."""
+    ref_l1, ref_cos = reference_loader.load_reference_masked_losses()
+    for seed in (0, 1):
+        pred, gt, mf = loss_oracle.normal_loss_inputs(seed)
+        p = torch.clamp(pred, 0, 1)
+        mask = loss_oracle.make_valid_mask(mf).repeat_interleave(3, 1)
+        a, b = ref_l1(p.clone(), gt.clone(), mask), ref_cos(p.clone(), gt.clone(), mask)
+        tot, l1, cos = loss_oracle.normal_step(pred, gt, mf)
+        assert abs(float(a) - float(l1)) <= 1e-6 * abs(float(a))
+        assert abs(float(b) - float(cos)) <= 1e-6 * abs(float(b))
+        assert abs(float(b + 10 * a) - float(tot)) <= 1e-6 * abs(float(tot))
+
+
+def test_normal_loss_oracle_golden():
+    """Values of the unmodified reference functions on the seeded inputs (made in the build container)."""
+    rec = torch.load(GOLDEN / "normal_losses_seed0.pt")
+    tot, l1, cos = loss_oracle.normal_step(*loss_oracle.normal_loss_inputs(0))
+    assert abs(float(l1) - rec["l1"]) <= 2e-6 * abs(rec["l1"])
+    assert abs(float(cos) - rec["cos"]) <= 2e-6 * abs(rec["cos"])

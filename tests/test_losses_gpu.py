@@ -57,3 +57,21 @@ def test_shared_step_loss_mix(lib_built):
     early = losses.depth_step_losses(pred.cuda(), gt.cuda(), mf.cuda(), losses.MidasLoss(),
                                      losses.VNL_Loss(1.0, 1.0, (384, 384)), global_step=10)
     assert close(early["depth_loss"], ssi) and early["vn_loss"] == 0
+
+
+@pytest.mark.parametrize("seed,batch", [(0, 2), (4, 3)])
+def test_normal_losses(lib_built, seed, batch):
+    """masked_l1 + masked cosine-angular losses of train_normal.py in one kernel pass vs the oracle / reference golden."""
+    from omnidata_b200 import losses
+    from oracle import loss_oracle
+    pred, gt, mf = loss_oracle.normal_loss_inputs(seed, batch)
+    rt, rl1, rcos = loss_oracle.normal_step(pred, gt, mf)
+    out = losses.normal_step_losses(pred.cuda(), gt.cuda(), mf.cuda())
+    assert close(out["l1_loss"], rl1) and close(out["cos_loss"], rcos) and close(out["normal_loss"], rt)
+    if seed == 0 and batch == 2:
+        rec = torch.load(GOLDEN / "normal_losses_seed0.pt")
+        assert close(out["l1_loss"], rec["l1"], 2e-5) and close(out["cos_loss"], rec["cos"], 2e-5)
+    # the reference's own calling convention (mask repeated over the channels, pre-clamped prediction)
+    mask3 = losses.make_valid_mask(mf.cuda()).repeat_interleave(3, 1)
+    tot2, l12, cos2 = losses.normal_losses(pred.cuda().clamp(0, 1), gt.cuda(), mask3)
+    assert float(l12) == float(out["l1_loss"]) and float(cos2) == float(out["cos_loss"])
