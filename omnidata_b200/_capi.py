@@ -104,6 +104,8 @@ _SIGNATURES = {
     "odb_debug_conv_trace": (C.c_int, [C.c_void_p]),
 }
 
+ABI_VERSION = 2        # include/omnidata_b200.h: ODB_ABI_VERSION (descriptor layouts this module mirrors)
+
 _lib = None
 
 
@@ -123,6 +125,9 @@ def lib():
             fn = getattr(_lib, name)  # raises AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        if _lib.odb_abi_version() != ABI_VERSION:
+            raise OdbError(f"{LIB_PATH} has ABI version {_lib.odb_abi_version()}, this package expects {ABI_VERSION}: "
+                           "rebuild with `python -m omnidata_b200.build`")
     return _lib
 
 
