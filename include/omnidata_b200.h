@@ -215,6 +215,21 @@ int odb_normal_loss_fwd(const float* prediction, const float* target, const uint
                         int32_t h, int32_t w, int32_t clamp_prediction, float* out3, double* workspace,
                         void* stream);
 
+/* ---- optimizer step of the depth train step (row a21: train_depth.py:381-383 Adam(lr), :425 gradient_clip_val=10)
+ * over FLAT fp32 buffers holding all parameters / gradients / moments.
+ *
+ * odb_clip_grad_norm: torch.nn.utils.clip_grad_norm_(params, max_norm) without the host round trip:
+ * out2 = (total L2 norm, clip coefficient min(1, max_norm / (norm + 1e-6))) on the device; the gradients are NOT
+ * modified — odb_adam_step applies the coefficient while it reads them.  workspace: odb_grad_norm_workspace_bytes()
+ * bytes, 256-byte aligned, zero-filled ONCE by the caller.  Deterministic (fixed-order fp64 partial sums).
+ *
+ * odb_adam_step: torch.optim.Adam update (betas, eps as given; no weight decay, no amsgrad), step = 1, 2, …;
+ * clip2 = the out2 of odb_clip_grad_norm or NULL (no clipping). */
+int64_t odb_grad_norm_workspace_bytes(void);
+int odb_clip_grad_norm(const float* grads, int64_t n, float max_norm, void* workspace, float* out2, void* stream);
+int odb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  const float* clip2, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+
 int odb_fill_zero(void* ptr, int64_t bytes, void* stream);
 
 /* ---- image pre- / post-processing either side of the forward ------------

@@ -90,6 +90,10 @@ _SIGNATURES = {
                                                                                         C.c_void_p, C.c_void_p]),
     "odb_normal_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "odb_grad_norm_workspace_bytes": (C.c_int64, []),
+    "odb_clip_grad_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "odb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     "odb_fill_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "odb_pil_resize_crop_to_tensor": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
