@@ -173,6 +173,12 @@ int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h, int32_t w,
 int odb_upsample2x_add(const void* z, const void* res, void* out, void* out_relu, int32_t b,
                        int32_t h, int32_t w, int32_t c, void* stream);
 
+/* Patch embedding gather of the plain ViT backbones (DPT-Large `vitl16_384`, `vitb16_384`; timm PatchEmbed =
+ * Conv2d(3, D, patch, stride patch), applied at M/vit.py:131): x fp32 NCHW [b][3][h][w] ->
+ * cols bf16 [b * (h/patch) * (w/patch)][3 * patch * patch], column (c * patch + py) * patch + px = the row-major
+ * flattening of the conv weight, so the embedding is one odb_conv_gemm. */
+int odb_patchify(const float* x, void* cols, int32_t b, int32_t h, int32_t w, int32_t patch, void* stream);
+
 /* tokens[b][0][:] = cls + pos[0]  (M/vit.py:135-147); tokens bf16 [b][tokens][c]; cls, pos0 fp32 [c]. */
 int odb_write_cls_row(void* tokens, const float* cls, const float* pos0, int32_t b, int32_t tokens_n,
                       int32_t c, void* stream);

@@ -398,6 +398,32 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   }
 }
 
+// Patch embedding gather of the plain ViT backbones (timm PatchEmbed: Conv2d(3, D, 16, stride 16),
+// modules/midas/vit.py:131 `patch_embed.proj(x)`): fp32 NCHW -> bf16 [b * gh * gw][3 * p * p], column
+// (c * p + py) * p + px — the row-major flattening of the conv weight [D][3][p][p], so the conv is one GEMM.
+// Thread = (token, 8 consecutive px of one (c, py) row): two float4 loads, one 16-byte store.
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, bf16* __restrict__ cols,
+                                                       int b, int h, int w, int p) {
+  grid_dep_wait();
+  grid_dep_launch();
+  const int gh = h / p, gw = w / p;
+  const int groups = 3 * p * p / 8;                      // 8-column groups per token
+  const long long total = (long long)b * gh * gw * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long tok = i / groups;
+    const int tx = (int)(tok % gw), ty = (int)((tok / gw) % gh), bi = (int)(tok / ((long long)gw * gh));
+    const int col = g * 8;
+    const int px = col % p, py = (col / p) % p, c = col / (p * p);
+    const float* src = x + (((long long)bi * 3 + c) * h + (ty * p + py)) * w + tx * p + px;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(src + 4));
+    const float v[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+    store8(cols + i * 8, v);
+  }
+}
+
 // Bilinear x2, align_corners=True: src = dst * (n-1)/(2n-1).  out = up(z) (+ res); out_relu = relu(out).
 // ncu showed the first two versions of this kernel ISSUE-bound (75-88 % issue slots, ~30 % DRAM):
 // four gathers, 32 unpacks and 32 FMAs for every 16 output bytes.  With align_corners=True and an
@@ -640,6 +666,22 @@ extern "C" int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h,
              kpad);
   count_launch();
   return check_launch("stem_im2col");
+}
+
+extern "C" int odb_patchify(const float* x, void* cols, int32_t b, int32_t h, int32_t w, int32_t patch,
+                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !cols || b < 1 || patch < 8 || patch % 8 || h < patch || w < patch || h % patch || w % patch ||
+      (reinterpret_cast<uintptr_t>(x) & 15u) || (w % 4))
+    return fail(ODB_ERR_INVALID, "patchify: bad argument (patch a multiple of 8 dividing h and w)");
+  const long long total = (long long)b * (h / patch) * (w / patch) * (3 * patch * patch / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  launch_pdl(patchify_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, static_cast<bf16*>(cols), b, h, w,
+             patch);
+  count_launch();
+  return check_launch("patchify");
 }
 
 extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, void* out_relu,

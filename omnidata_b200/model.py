@@ -25,16 +25,99 @@ from . import ops
 from ._capi import OdbError
 
 _STAGES = ((256, 3), (512, 4), (1024, 9))   # timm ResNetV2(layers=(3,4,9)) widths / depths
-_EMBED = 768
-_HEADS = 12
-_DEPTH = 12
-_HOOKS = (8, 11)                            # modules/midas/dpt_depth.py:41-45, ViT blocks tapped
 _FEATURES = 256
+# Encoders behind the same decoder (modules/midas/blocks.py:12-47 _make_encoder, dpt_depth.py:41-45 hooks):
+#   vitb_rn50_384  DPT-Hybrid: ResNetV2 stages 0/1 give layer_1/2, ViT-B blocks 8/11 give layer_3/4
+#   vitl16_384     DPT-Large: plain ViT-L/16, blocks 5/11/17/23 give layer_1..4
+#                  (vit.py:185-290: conv1x1 then ConvTranspose 4x4/s4, 2x2/s2, identity, conv3x3/s2)
+_ARCH = {
+    "vitb_rn50_384": dict(embed=768, heads=12, depth=12, hybrid=True, hooks=(8, 11), rn_in=(256, 512, 768, 768)),
+    "vitl16_384": dict(embed=1024, heads=16, depth=24, hybrid=False, hooks=(5, 11, 17, 23),
+                       rn_in=(256, 512, 1024, 1024)),
+}
+_EMBED, _HEADS, _DEPTH, _HOOKS = 768, 12, 12, (8, 11)      # the DPT-Hybrid values (module-level names kept)
 
 
-def state_dict_spec(num_channels: int = 1, features: int = _FEATURES) -> List[Tuple[str, Tuple[int, ...]]]:
+def _decoder_spec(add, num_channels: int, features: int, rn_in) -> None:
+    for n, c in zip((1, 2, 3, 4), rn_in):
+        add(f"scratch.layer{n}_rn.weight", features, c, 3, 3)
+    for n in (1, 2, 3, 4):
+        p = f"scratch.refinenet{n}."
+        add(p + "out_conv.weight", features, features, 1, 1)
+        add(p + "out_conv.bias", features)
+        for u in (1, 2):                     # refinenet4.resConfUnit1 is dead (blocks.py:328-330)
+            for cv in (1, 2):
+                add(f"{p}resConfUnit{u}.conv{cv}.weight", features, features, 3, 3)
+                add(f"{p}resConfUnit{u}.conv{cv}.bias", features)
+    add("scratch.output_conv.0.weight", features // 2, features, 3, 3)
+    add("scratch.output_conv.0.bias", features // 2)
+    add("scratch.output_conv.2.weight", 32, features // 2, 3, 3)
+    add("scratch.output_conv.2.bias", 32)
+    add("scratch.output_conv.4.weight", num_channels, 32, 1, 1)
+    add("scratch.output_conv.4.bias", num_channels)
+
+
+def _vit_blocks_spec(add, pm: str, embed: int, depth: int) -> None:
+    for i in range(depth):
+        p = f"{pm}blocks.{i}."
+        add(p + "norm1.weight", embed)
+        add(p + "norm1.bias", embed)
+        add(p + "attn.qkv.weight", 3 * embed, embed)
+        add(p + "attn.qkv.bias", 3 * embed)
+        add(p + "attn.proj.weight", embed, embed)
+        add(p + "attn.proj.bias", embed)
+        add(p + "norm2.weight", embed)
+        add(p + "norm2.bias", embed)
+        add(p + "mlp.fc1.weight", 4 * embed, embed)
+        add(p + "mlp.fc1.bias", 4 * embed)
+        add(p + "mlp.fc2.weight", embed, 4 * embed)
+        add(p + "mlp.fc2.bias", embed)
+    add(pm + "norm.weight", embed)           # dead in the reference forward (vit.py:153) but present
+    add(pm + "norm.bias", embed)
+    add(pm + "head.weight", 1000, embed)     # dead: ImageNet classifier of the timm model
+    add(pm + "head.bias", 1000)
+
+
+def _plain_vit_spec(num_channels: int, features: int, arch: dict) -> List[Tuple[str, Tuple[int, ...]]]:
+    """DPT with a plain ViT encoder (`vitl16_384`): keys of the reference class instantiated with timm's
+    vit_large_patch16_384 (vit.py:185-318), verified against it in tests/test_boundary_cpu.py."""
+    spec: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def add(key, *shape):
+        spec.append((key, tuple(shape)))
+
+    D = arch["embed"]
+    pm = "pretrained.model."
+    add(pm + "cls_token", 1, 1, D)
+    add(pm + "pos_embed", 1, 577, D)
+    add(pm + "patch_embed.proj.weight", D, 3, 16, 16)
+    add(pm + "patch_embed.proj.bias", D)
+    _vit_blocks_spec(add, pm, D, arch["depth"])
+    for n, c in zip((1, 2, 3, 4), arch["rn_in"]):
+        p = f"pretrained.act_postprocess{n}."
+        add(p + "0.project.0.weight", D, 2 * D)
+        add(p + "0.project.0.bias", D)
+        add(p + "3.weight", c, D, 1, 1)
+        add(p + "3.bias", c)
+        if n == 1:
+            add(p + "4.weight", c, c, 4, 4)      # ConvTranspose2d(c, c, 4, stride 4): [in, out, kh, kw]
+            add(p + "4.bias", c)
+        elif n == 2:
+            add(p + "4.weight", c, c, 2, 2)      # ConvTranspose2d(c, c, 2, stride 2)
+            add(p + "4.bias", c)
+        elif n == 4:
+            add(p + "4.weight", c, c, 3, 3)      # Conv2d(c, c, 3, stride 2, padding 1)
+            add(p + "4.bias", c)
+    _decoder_spec(add, num_channels, features, arch["rn_in"])
+    return spec
+
+
+def state_dict_spec(num_channels: int = 1, features: int = _FEATURES,
+                    backbone: str = "vitb_rn50_384") -> List[Tuple[str, Tuple[int, ...]]]:
     """(key, shape) in reference `state_dict()` order (verified against the
     unmodified reference class in tests/test_boundary_cpu.py)."""
+    if not _ARCH[backbone]["hybrid"]:
+        return _plain_vit_spec(num_channels, features, _ARCH[backbone])
     spec: List[Tuple[str, Tuple[int, ...]]] = []
 
     def add(key, *shape):
@@ -68,24 +151,7 @@ def state_dict_spec(num_channels: int = 1, features: int = _FEATURES) -> List[Tu
         cin = cout
     add(pm + "patch_embed.proj.weight", _EMBED, 1024, 1, 1)
     add(pm + "patch_embed.proj.bias", _EMBED)
-    for i in range(_DEPTH):
-        p = f"{pm}blocks.{i}."
-        add(p + "norm1.weight", _EMBED)
-        add(p + "norm1.bias", _EMBED)
-        add(p + "attn.qkv.weight", 3 * _EMBED, _EMBED)
-        add(p + "attn.qkv.bias", 3 * _EMBED)
-        add(p + "attn.proj.weight", _EMBED, _EMBED)
-        add(p + "attn.proj.bias", _EMBED)
-        add(p + "norm2.weight", _EMBED)
-        add(p + "norm2.bias", _EMBED)
-        add(p + "mlp.fc1.weight", 4 * _EMBED, _EMBED)
-        add(p + "mlp.fc1.bias", 4 * _EMBED)
-        add(p + "mlp.fc2.weight", _EMBED, 4 * _EMBED)
-        add(p + "mlp.fc2.bias", _EMBED)
-    add(pm + "norm.weight", _EMBED)          # dead in the reference forward (vit.py:153) but present
-    add(pm + "norm.bias", _EMBED)
-    add(pm + "head.weight", 1000, _EMBED)    # dead: ImageNet classifier of the timm model
-    add(pm + "head.bias", 1000)
+    _vit_blocks_spec(add, pm, _EMBED, _DEPTH)
     for n in (3, 4):
         p = f"pretrained.act_postprocess{n}."
         add(p + "0.project.0.weight", _EMBED, 2 * _EMBED)
@@ -95,22 +161,7 @@ def state_dict_spec(num_channels: int = 1, features: int = _FEATURES) -> List[Tu
         if n == 4:
             add(p + "4.weight", _EMBED, _EMBED, 3, 3)
             add(p + "4.bias", _EMBED)
-    for n, c in zip((1, 2, 3, 4), (256, 512, _EMBED, _EMBED)):
-        add(f"scratch.layer{n}_rn.weight", features, c, 3, 3)
-    for n in (1, 2, 3, 4):
-        p = f"scratch.refinenet{n}."
-        add(p + "out_conv.weight", features, features, 1, 1)
-        add(p + "out_conv.bias", features)
-        for u in (1, 2):                     # refinenet4.resConfUnit1 is dead (blocks.py:328-330)
-            for cv in (1, 2):
-                add(f"{p}resConfUnit{u}.conv{cv}.weight", features, features, 3, 3)
-                add(f"{p}resConfUnit{u}.conv{cv}.bias", features)
-    add("scratch.output_conv.0.weight", features // 2, features, 3, 3)
-    add("scratch.output_conv.0.bias", features // 2)
-    add("scratch.output_conv.2.weight", 32, features // 2, 3, 3)
-    add("scratch.output_conv.2.bias", 32)
-    add("scratch.output_conv.4.weight", num_channels, 32, 1, 1)
-    add("scratch.output_conv.4.bias", num_channels)
+    _decoder_spec(add, num_channels, features, (256, 512, _EMBED, _EMBED))
     return spec
 
 
@@ -142,10 +193,12 @@ class DPTDepthModel(nn.Module):
                  backbone: str = "vitb_rn50_384", features: int = 256, readout: str = "project",
                  channels_last: bool = False, use_bn: bool = False, **kwargs):
         super().__init__()
-        if backbone != "vitb_rn50_384":
+        if backbone not in _ARCH:
             # reference: print + assert False (modules/midas/blocks.py:42-44)
             print(f"Backbone '{backbone}' not implemented")
             raise AssertionError(f"Backbone '{backbone}' not implemented")
+        self.backbone = backbone
+        self.arch = _ARCH[backbone]
         if features != 256 or readout != "project" or use_bn:
             raise NotImplementedError("only features=256, readout='project', use_bn=False (the Omnidata DPT-Hybrid)")
         self.non_negative = bool(non_negative)
@@ -165,7 +218,7 @@ class DPTDepthModel(nn.Module):
     # ------------------------------------------------------------------ parameters / state_dict
     def _build_parameters(self):
         gen = torch.Generator().manual_seed(0)
-        for key, shape in state_dict_spec(self.num_channels):
+        for key, shape in state_dict_spec(self.num_channels, backbone=self.backbone):
             *path, leaf = key.split(".")
             mod = self
             for name in path:
@@ -210,30 +263,35 @@ class DPTDepthModel(nn.Module):
         bf = lambda t: t.to(torch.bfloat16).contiguous()
         pk: dict = {}
         pm = "pretrained.model."
-        bb = pm + "patch_embed.backbone."
-        # stem 7x7: [64,3,7,7] -> [64, (ky,kx,c)=147] padded to 160 columns
-        w = _std_weight(sd[bb + "stem.conv.weight"]).permute(0, 2, 3, 1).reshape(64, 147)
-        pk["stem_w"] = bf(F.pad(w, (0, 13)))
-        pk["stem_g"], pk["stem_b"] = f32(bb + "stem.norm.weight"), f32(bb + "stem.norm.bias")
-        blocks = []
-        for s, (cout, depth) in enumerate(_STAGES):
-            for b in range(depth):
-                p = f"{bb}stages.{s}.blocks.{b}."
-                e = {"stride": 2 if (b == 0 and s > 0) else 1, "cout": cout, "mid": cout // 4}
-                if b == 0:
-                    e["wd"] = ops.pack_conv_weight(_std_weight(sd[p + "downsample.conv.weight"]))
-                    e["gd"], e["bd"] = f32(p + "downsample.norm.weight"), f32(p + "downsample.norm.bias")
-                for i in (1, 2, 3):
-                    e[f"w{i}"] = ops.pack_conv_weight(_std_weight(sd[p + f"conv{i}.weight"]))
-                    e[f"g{i}"], e[f"b{i}"] = f32(p + f"norm{i}.weight"), f32(p + f"norm{i}.bias")
-                blocks.append((s, b, e))
-        pk["rn_blocks"] = blocks
-        pk["proj_w"] = ops.pack_conv_weight(sd[pm + "patch_embed.proj.weight"])
+        D, depth = self.arch["embed"], self.arch["depth"]
+        if self.arch["hybrid"]:
+            bb = pm + "patch_embed.backbone."
+            # stem 7x7: [64,3,7,7] -> [64, (ky,kx,c)=147] padded to 160 columns
+            w = _std_weight(sd[bb + "stem.conv.weight"]).permute(0, 2, 3, 1).reshape(64, 147)
+            pk["stem_w"] = bf(F.pad(w, (0, 13)))
+            pk["stem_g"], pk["stem_b"] = f32(bb + "stem.norm.weight"), f32(bb + "stem.norm.bias")
+            blocks = []
+            for s, (cout, dep) in enumerate(_STAGES):
+                for b in range(dep):
+                    p = f"{bb}stages.{s}.blocks.{b}."
+                    e = {"stride": 2 if (b == 0 and s > 0) else 1, "cout": cout, "mid": cout // 4}
+                    if b == 0:
+                        e["wd"] = ops.pack_conv_weight(_std_weight(sd[p + "downsample.conv.weight"]))
+                        e["gd"], e["bd"] = f32(p + "downsample.norm.weight"), f32(p + "downsample.norm.bias")
+                    for i in (1, 2, 3):
+                        e[f"w{i}"] = ops.pack_conv_weight(_std_weight(sd[p + f"conv{i}.weight"]))
+                        e[f"g{i}"], e[f"b{i}"] = f32(p + f"norm{i}.weight"), f32(p + f"norm{i}.bias")
+                    blocks.append((s, b, e))
+            pk["rn_blocks"] = blocks
+            pk["proj_w"] = ops.pack_conv_weight(sd[pm + "patch_embed.proj.weight"])
+        else:
+            # PatchEmbed conv [D,3,16,16]: its row-major flattening is the GEMM weight for odb_patchify's columns
+            pk["proj_w"] = bf(sd[pm + "patch_embed.proj.weight"].reshape(D, -1))
         pk["proj_b"] = f32(pm + "patch_embed.proj.bias")
         pk["cls"] = f32(pm + "cls_token").reshape(-1)
-        pk["pos"] = f32(pm + "pos_embed")                       # [1,577,768] fp32 master copy
+        pk["pos"] = f32(pm + "pos_embed")                       # [1,577,D] fp32 master copy
         vit = []
-        for i in range(_DEPTH):
+        for i in range(depth):
             p = f"{pm}blocks.{i}."
             vit.append({
                 "ln1": (f32(p + "norm1.weight"), f32(p + "norm1.bias")),
@@ -244,16 +302,23 @@ class DPTDepthModel(nn.Module):
                 "fc2": (bf(sd[p + "mlp.fc2.weight"]), f32(p + "mlp.fc2.bias")),
             })
         pk["vit"] = vit
-        for n in (3, 4):
+        for n in ((3, 4) if self.arch["hybrid"] else (1, 2, 3, 4)):
             p = f"pretrained.act_postprocess{n}."
-            wfull = bf(sd[p + "0.project.0.weight"])               # [768,1536]
+            wfull = bf(sd[p + "0.project.0.weight"])               # [D, 2D]
             pk[f"ro{n}_wfull"] = wfull
-            pk[f"ro{n}_wtok"] = wfull[:, :_EMBED].contiguous()     # token half of the split Linear
+            pk[f"ro{n}_wtok"] = wfull[:, :D].contiguous()          # token half of the split Linear
             pk[f"ro{n}_b"] = f32(p + "0.project.0.bias")
             pk[f"pp{n}_w"] = ops.pack_conv_weight(sd[p + "3.weight"])
             pk[f"pp{n}_b"] = f32(p + "3.bias")
         pk["pp4s_w"] = ops.pack_conv_weight(sd["pretrained.act_postprocess4.4.weight"])
         pk["pp4s_b"] = f32("pretrained.act_postprocess4.4.bias")
+        if not self.arch["hybrid"]:
+            # ConvTranspose2d(c, c, k, stride k) (vit.py:216-225, 240-249): k*k independent 1x1 convolutions,
+            # one per output phase (dy, dx): W_phase[out][in] = weight[in][out][dy][dx]
+            for n, k in ((1, 4), (2, 2)):
+                w = sd[f"pretrained.act_postprocess{n}.4.weight"].float()
+                pk[f"pp{n}t_w"] = [[bf(w[:, :, dy, dx].t()) for dx in range(k)] for dy in range(k)]
+                pk[f"pp{n}t_b"] = f32(f"pretrained.act_postprocess{n}.4.bias")
         for n in (1, 2, 3, 4):
             pk[f"rn{n}_w"] = ops.pack_conv_weight(sd[f"scratch.layer{n}_rn.weight"])
             p = f"scratch.refinenet{n}."
@@ -270,7 +335,7 @@ class DPTDepthModel(nn.Module):
         return pk
 
     def _pos_for_grid(self, pk, gh: int, gw: int):
-        """(pos0 fp32 [768], grid bf16 [1,1,gh*gw,768]); bilinear resize as vit.py:102-116 if needed."""
+        """(pos0 fp32 [D], grid bf16 [1,1,gh*gw,D]); bilinear resize as vit.py:102-116 if needed."""
         key = (gh, gw)
         if key not in pk["pos_cache"]:
             pos = pk["pos"]
@@ -280,7 +345,7 @@ class DPTDepthModel(nn.Module):
                 g = F.interpolate(g, size=(gh, gw), mode="bilinear")
                 grid = g.permute(0, 2, 3, 1).reshape(gh * gw, -1)
             pk["pos_cache"][key] = (pos[0, 0].contiguous(),
-                                    grid.to(torch.bfloat16).contiguous().view(1, 1, gh * gw, _EMBED))
+                                    grid.to(torch.bfloat16).contiguous().view(1, 1, gh * gw, self.arch["embed"]))
         return pk["pos_cache"][key]
 
     # ------------------------------------------------------------------ forward
@@ -323,19 +388,10 @@ class DPTDepthModel(nn.Module):
         graph.replay()
         return static_out.clone()
 
-    @torch.no_grad()
-    def _forward_impl(self, x: torch.Tensor) -> torch.Tensor:
-        pk = self._packed
+    def _resnet_features(self, x, pk, ws, taps):
+        """ResNetV2 stem + stages of the hybrid encoder -> (layer_1, layer_2, stage-2 features)."""
         B, _, H, W = x.shape
-        key = (B, H, W)
-        ws = self._workspaces.get(key)
-        if ws is None:
-            ws = self._workspaces[key] = _Workspace(x.device)
-        taps = self.taps if self.keep_taps else None
-        if taps is not None:
-            taps.clear()
         buf = ws.get
-
         # ---------------- ResNetV2 stem + stages (timm; hooks at vit.py:363-368)
         h2, w2 = H // 2, W // 2
         n_gn = 1 + sum(3 * d + 1 for _, d in _STAGES)
@@ -410,32 +466,60 @@ class DPTDepthModel(nn.Module):
                 taps[f"{tag}_out"] = out
             if b == _STAGES[s][1] - 1:
                 feats.append(t)
-        layer_1, layer_2, f3 = feats
-        gh, gw = hh, ww
+        return feats
+
+    @torch.no_grad()
+    def _forward_impl(self, x: torch.Tensor) -> torch.Tensor:
+        pk = self._packed
+        B, _, H, W = x.shape
+        key = (B, H, W)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            ws = self._workspaces[key] = _Workspace(x.device)
+        taps = self.taps if self.keep_taps else None
+        if taps is not None:
+            taps.clear()
+        buf = ws.get
+
+        D, heads = self.arch["embed"], self.arch["heads"]
+        hooks = self.arch["hooks"]
+        if self.arch["hybrid"]:
+            layer_1, layer_2, f3 = self._resnet_features(x, pk, ws, taps)
+            gh, gw = f3.shape[1], f3.shape[2]
+        else:
+            gh, gw = H // 16, W // 16
         ntok = gh * gw + 1
 
-        # ---------------- tokens: patch proj + cls + pos (vit.py:133-147)
+        # ---------------- tokens: patch proj + cls + pos (vit.py:131-147)
         pos0, pos_grid = self._pos_for_grid(pk, gh, gw)
-        tok = buf("tok_a", (B, ntok, _EMBED))
-        tok_b = buf("tok_b", (B, ntok, _EMBED))
+        tok_bufs = [buf(f"tok_{i}", (B, ntok, D)) for i in range(len(hooks))]
+        tok = tok_bufs[0]
         ops.write_cls_row(tok, pk["cls"], pos0)
-        ops.linear(f3.view(B, 1, gh * gw, 1024), pk["proj_w"], tok[:, 1:, :].unsqueeze(1), bias=pk["proj_b"],
-                   residual=pos_grid)
+        if self.arch["hybrid"]:
+            ops.linear(f3.view(B, 1, gh * gw, 1024), pk["proj_w"], tok[:, 1:, :].unsqueeze(1), bias=pk["proj_b"],
+                       residual=pos_grid)
+        else:
+            cols = buf("patch_cols", (B, 1, gh * gw, 3 * 16 * 16))
+            ops.patchify(x, cols.view(B * gh * gw, -1), 16)
+            ops.linear(cols, pk["proj_w"], tok[:, 1:, :].unsqueeze(1), bias=pk["proj_b"], residual=pos_grid)
 
         if taps is not None:
             taps["tokens_in"] = tok.clone()
-        # ---------------- 12 ViT blocks (vit.py:150-151); final norm is dead compute and skipped
-        hbuf = buf("vit_h", (B, ntok, _EMBED))
-        qkv = buf("vit_qkv", (B, ntok, 3 * _EMBED))
-        att = buf("vit_att", (B, ntok, _EMBED))
-        mlp = buf("vit_mlp", (B, ntok, 4 * _EMBED))
+        # ---------------- ViT blocks (vit.py:150-151); final norm is dead compute and skipped.  The residual
+        # stream lives in one buffer per hooked block: the block after a hook writes its first residual add
+        # into the next buffer, which leaves the hooked activation intact.
+        hbuf = buf("vit_h", (B, ntok, D))
+        qkv = buf("vit_qkv", (B, ntok, 3 * D))
+        att = buf("vit_att", (B, ntok, D))
+        mlp = buf("vit_mlp", (B, ntok, 4 * D))
         rows = B * ntok
         cur = tok
+        hooked = []
         for i, blk in enumerate(pk["vit"]):
             ops.layernorm(cur, blk["ln1"][0], blk["ln1"][1], hbuf)
             ops.linear(hbuf.view(rows, -1), blk["qkv"][0], qkv.view(rows, -1), bias=blk["qkv"][1])
-            ops.attention(qkv, att, heads=_HEADS, scale=0.125)
-            nxt = tok_b if i == _HOOKS[0] + 1 else cur      # block 9 leaves tokens_8 intact in tok_a
+            ops.attention(qkv, att, heads=heads, scale=0.125)
+            nxt = tok_bufs[len(hooked)] if (i - 1) in hooks else cur
             ops.linear(att.view(rows, -1), blk["proj"][0], nxt.view(rows, -1), bias=blk["proj"][1],
                        residual=cur.view(rows, -1))
             cur = nxt
@@ -444,23 +528,43 @@ class DPTDepthModel(nn.Module):
                        act=ops.ACT_GELU)
             ops.linear(mlp.view(rows, -1), blk["fc2"][0], cur.view(rows, -1), bias=blk["fc2"][1],
                        residual=cur.view(rows, -1))
+            if i in hooks:
+                hooked.append(cur)
             if taps is not None:
                 taps[f"tokens_{i}"] = cur.clone()
-        tokens_8, tokens_11 = tok, tok_b
 
-        # ---------------- reassemble (vit.py:66-97, 431-462)
-        def readout(tk, n):
-            cb = buf(f"ro{n}_cb", (B, _EMBED), torch.float32)
+        # ---------------- reassemble (vit.py:66-97, 185-290 / 431-462)
+        def readout(tk, n, cout):
+            cb = buf(f"ro{n}_cb", (B, D), torch.float32)
             ops.readout_cls_bias(pk[f"ro{n}_wfull"], pk[f"ro{n}_b"], tk, cb)
-            r = buf(f"ro{n}_r", (B, 1, gh * gw, _EMBED))
+            r = buf(f"ro{n}_r", (B, 1, gh * gw, D))
             ops.linear(tk[:, 1:, :].unsqueeze(1), pk[f"ro{n}_wtok"], r, bias=cb, bias_per_image=True,
                        act=ops.ACT_GELU)
-            o = buf(f"pp{n}", (B, gh, gw, _EMBED))
-            ops.conv1x1(r.view(B, gh, gw, _EMBED), pk[f"pp{n}_w"], o, bias=pk[f"pp{n}_b"])
+            o = buf(f"pp{n}", (B, gh, gw, cout))
+            ops.conv1x1(r.view(B, gh, gw, D), pk[f"pp{n}_w"], o, bias=pk[f"pp{n}_b"])
             return o
-        layer_3 = readout(tokens_8, 3)
-        u4 = readout(tokens_11, 4)
-        layer_4 = buf("pp4s", (B, gh // 2, gw // 2, _EMBED))
+
+        def conv_transpose(t, n, k):
+            """ConvTranspose2d(c, c, k, stride k): phase (dy, dx) of the output is a 1x1 convolution of the
+            input, stored through a strided view of the output (no scatter kernel)."""
+            c = t.shape[3]
+            o = buf(f"pp{n}t", (B, gh * k, gw * k, c))
+            for dy in range(k):
+                for dx in range(k):
+                    ops.conv1x1(t, pk[f"pp{n}t_w"][dy][dx], o[:, dy::k, dx::k, :], bias=pk[f"pp{n}t_b"])
+            return o
+
+        rn_in = self.arch["rn_in"]
+        if self.arch["hybrid"]:
+            tokens_8, tokens_11 = hooked
+            layer_3 = readout(tokens_8, 3, rn_in[2])
+            u4 = readout(tokens_11, 4, rn_in[3])
+        else:
+            layer_1 = conv_transpose(readout(hooked[0], 1, rn_in[0]), 1, 4)
+            layer_2 = conv_transpose(readout(hooked[1], 2, rn_in[1]), 2, 2)
+            layer_3 = readout(hooked[2], 3, rn_in[2])
+            u4 = readout(hooked[3], 4, rn_in[3])
+        layer_4 = buf("pp4s", (B, gh // 2, gw // 2, rn_in[3]))
         ops.conv3x3_s2(u4, pk["pp4s_w"], layer_4, "sym1", bias=pk["pp4s_b"])
 
         # ---------------- scratch.layerN_rn (dpt_depth.py:73-76): raw + relu copies feed the RCUs
@@ -516,8 +620,9 @@ class DPTDepthModel(nn.Module):
         ops.conv3x3(h1u, w2, None, bias=b2, head=(w4, b4, out, self.non_negative))
 
         if taps is not None:
-            taps.update(layer_1=layer_1, layer_2=layer_2, layer_3=layer_3, layer_4=layer_4,
-                        tokens_8=tokens_8, tokens_11=tokens_11, path_1=path_1,
+            for hk, tk in zip(hooks, hooked):
+                taps[f"tokens_{hk}"] = tk
+            taps.update(layer_1=layer_1, layer_2=layer_2, layer_3=layer_3, layer_4=layer_4, path_1=path_1,
                         layer_1_rn=rn_raw[0], layer_2_rn=rn_raw[1], layer_3_rn=rn_raw[2],
                         layer_4_rn=rn_raw[3])
             self.taps = {k: v.clone() for k, v in taps.items()}

@@ -17,7 +17,7 @@ from ._capi import ACT_GELU, ACT_NONE, ACT_RELU, ConvGemmDesc, View, check, lib
 __all__ = [
     "ACT_NONE", "ACT_RELU", "ACT_GELU", "conv_gemm", "linear", "conv1x1", "conv3x3", "conv3x3_s2",
     "layernorm", "attention", "groupnorm_stats", "groupnorm_apply", "stem_gn_relu_maxpool",
-    "stem_im2col", "upsample2x_add", "write_cls_row", "readout_cls_bias", "pack_conv_weight",
+    "stem_im2col", "patchify", "upsample2x_add", "write_cls_row", "readout_cls_bias", "pack_conv_weight",
 ]
 
 
@@ -272,6 +272,16 @@ def stem_im2col(x, cols):
     if ch != 3 or not x.is_contiguous():
         raise _capi.OdbError("stem_im2col: contiguous [B,3,H,W] fp32 input required")
     _call("odb_stem_im2col", {}, lib().odb_stem_im2col, x.data_ptr(), cols.data_ptr(), b, h, w, cols.shape[-1], _stream())
+
+
+def patchify(x, cols, patch: int = 16):
+    """x fp32 [B,3,H,W] -> cols bf16 [B*(H/p)*(W/p), 3*p*p] (the im2col of a stride-p, kernel-p convolution)."""
+    _need(x, torch.float32, "x"); _need(cols, torch.bfloat16, "cols")
+    b, c, h, w = x.shape
+    if c != 3 or not x.is_contiguous() or not cols.is_contiguous() or cols.numel() != b * (h // patch) * (w // patch) * 3 * patch * patch:
+        raise _capi.OdbError("patchify: x [B,3,H,W] contiguous, cols [B*gh*gw, 3*p*p]")
+    _call("odb_patchify", {"bytes": x.numel() * 4 + cols.numel() * 2}, lib().odb_patchify, x.data_ptr(), cols.data_ptr(),
+          b, h, w, patch, _stream())
 
 
 def upsample2x_add(z, out, res=None, out_relu=None):

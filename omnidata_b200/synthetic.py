@@ -15,6 +15,8 @@ def make_state_dict(seed: int = 0, num_channels: int = 1, spec=None) -> "Ordered
         from .model import state_dict_spec
         spec = state_dict_spec(num_channels)
     g = torch.Generator(device="cpu").manual_seed(1234 + seed)
+    # the plain-ViT encoders (DPT-Large): identified by their ConvTranspose reassemble layer
+    plain_vit = any(k == "pretrained.act_postprocess1.4.weight" for k, _ in spec)
     sd = OrderedDict()
     for key, shape in spec:
         leaf = key.rsplit(".", 1)[-1]
@@ -34,6 +36,9 @@ def make_state_dict(seed: int = 0, num_channels: int = 1, spec=None) -> "Ordered
                 t = t + 0.2
         else:                                                               # conv / linear weight
             fan_in = math.prod(shape[1:])
+            if key in ("pretrained.act_postprocess1.4.weight", "pretrained.act_postprocess2.4.weight") \
+                    and len(shape) == 4 and shape[2] in (2, 4):
+                fan_in = shape[0]      # ConvTranspose2d [in, out, k, k] with stride k: one input pixel per output pixel
             gain = 1.0
             if ".attn.proj." in key or ".mlp.fc2." in key:
                 gain = 0.25            # residual branches: keep the token stream well conditioned
@@ -44,5 +49,7 @@ def make_state_dict(seed: int = 0, num_channels: int = 1, spec=None) -> "Ordered
             t = torch.randn(shape, generator=g) * (gain / math.sqrt(fan_in))
             if key.startswith("scratch.output_conv.4."):
                 t = t * 2.0
+                if plain_vit:
+                    t = 0.25 * (t.abs() - 0.6 * t.abs().mean())   # mostly positive read-out: the final ReLU stays alive
         sd[key] = t.float()
     return sd

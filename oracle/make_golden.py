@@ -96,6 +96,61 @@ def main():
     make_normal_loss_golden()
 
 
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def run_reference_large(dtype=torch.float32, n_samples: int = 4096):
+    """DPT-Large (backbone 'vitl16_384', demo.py:81) — the UNMODIFIED reference class on the timm shim's
+    vit_large_patch16_384; seeded weights over the reference's own key/shape table."""
+    from omnidata_b200.synthetic import make_state_dict as gen
+    model = rl.load_reference_dpt(1, "vitl16_384").eval()
+    spec = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    model.load_state_dict(gen(0, 1, spec=spec), strict=True)
+    model = model.to(dtype)
+    taps = {}
+
+    def grab(name):
+        def hook(mod, inp, out):
+            taps[name] = out.detach().float().clone()
+        return hook
+    for n in (1, 2, 3, 4):
+        getattr(model.scratch, f"layer{n}_rn").register_forward_hook(grab(f"layer_{n}_rn"))
+        getattr(model.scratch, f"refinenet{n}").register_forward_hook(grab(f"path_{n}"))
+        getattr(model.pretrained, f"act_postprocess{n}").register_forward_hook(grab(f"layer_{n}"))
+    model.scratch.output_conv[4].register_forward_hook(grab("head_pre_relu"))
+    x = golden_input(1)
+    with torch.no_grad():
+        y = model(x.to(dtype)).float()
+    acts = model.pretrained.activations
+    for n, hk in zip("1234", (5, 11, 17, 23)):
+        taps[f"tokens_{hk}"] = acts[n].detach().float().clone()
+    return y, taps, spec
+
+
+def make_large_golden(n_samples: int = 4096):
+    """dpt_large_fp32_seed0_c1.pt — reference DPT-Large forward (fp32) + the drift the same reference module
+    shows when run entirely in bf16 on the CPU (the yardstick for the bf16 kernels)."""
+    global N_SAMPLES
+    y, taps, spec = run_reference_large(torch.float32)
+    yb, tapsb, _ = run_reference_large(torch.bfloat16)
+    old = N_SAMPLES
+    N_SAMPLES = n_samples
+    try:
+        rec = {"output_sub8": y[..., ::8, ::8].clone(), "output_mean": float(y.mean()),
+               "taps": {k: summarize(k, v) for k, v in sorted(taps.items())},
+               "bf16_drift": {k: rel_l2(tapsb[k], taps[k]) for k in sorted(taps)},
+               "bf16_output_drift": rel_l2(yb, y),
+               "spec": [[k, list(sh)] for k, sh in spec]}
+    finally:
+        N_SAMPLES = old
+    torch.save(rec, GOLDEN / "dpt_large_fp32_seed0_c1.pt")
+    print("DPT-Large: output mean %.6f, bf16 drift (output) %.3e" % (rec["output_mean"], rec["bf16_output_drift"]))
+    for k, v in rec["bf16_drift"].items():
+        print(f"   {k:14s} rms {rec['taps'][k]['rms']:.4f}  pure-bf16 drift {v:.3e}")
+
+
 def make_normal_loss_golden():
     """normal_losses_seed0.pt — reference masked_l1_loss / masked_cosine_angular_loss (losses/masked_losses.py,
     unmodified) as train_normal.py:247-258 calls them, on loss_oracle.normal_loss_inputs(0)."""

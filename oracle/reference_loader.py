@@ -25,13 +25,13 @@ def _prepare_path():
             sys.path.insert(0, p)
 
 
-def load_reference_dpt(num_channels: int = 1):
-    """reference DPTDepthModel(backbone='vitb_rn50_384', num_channels=...) exactly as demo.py:63,82."""
+def load_reference_dpt(num_channels: int = 1, backbone: str = "vitb_rn50_384"):
+    """reference DPTDepthModel(backbone=..., num_channels=...) exactly as demo.py:63,81-82."""
     if not reference_available():
         raise RuntimeError("reference tree not present")
     _prepare_path()
     mod = importlib.import_module("modules.midas.dpt_depth")
-    return mod.DPTDepthModel(backbone="vitb_rn50_384", num_channels=num_channels)
+    return mod.DPTDepthModel(backbone=backbone, num_channels=num_channels)
 
 
 def load_reference_losses():

@@ -185,11 +185,25 @@ class Block(nn.Module):
         return x + self.mlp(self.norm2(x))
 
 
+class PatchEmbed(nn.Module):
+    """timm 0.4.12 layers/patch_embed.py: non-overlapping 16x16 patches by a strided convolution."""
+
+    def __init__(self, img_size=384, patch_size=16, in_chans=3, embed_dim=768):
+        super().__init__()
+        self.img_size = (img_size, img_size)
+        self.patch_size = (patch_size, patch_size)
+        self.num_patches = (img_size // patch_size) ** 2
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2)
+
+
 class VisionTransformer(nn.Module):
-    def __init__(self, embed_dim=768, depth=12, heads=12, num_classes=1000):
+    def __init__(self, embed_dim=768, depth=12, heads=12, num_classes=1000, hybrid=True):
         super().__init__()
         self.num_features = self.embed_dim = embed_dim
-        self.patch_embed = HybridEmbed(ResNetV2((3, 4, 9)), embed_dim)
+        self.patch_embed = HybridEmbed(ResNetV2((3, 4, 9)), embed_dim) if hybrid else PatchEmbed(384, 16, 3, embed_dim)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches + 1, embed_dim))
         self.pos_drop = nn.Dropout(0.0)
@@ -206,6 +220,10 @@ class VisionTransformer(nn.Module):
 
 
 def create_model(name, pretrained=False, **kwargs):
-    if name != "vit_base_resnet50_384":
-        raise RuntimeError(f"timm shim: only vit_base_resnet50_384 is restated (asked for {name!r})")
-    return VisionTransformer()
+    if name == "vit_base_resnet50_384":
+        return VisionTransformer()
+    if name == "vit_large_patch16_384":     # timm 0.4.12 vision_transformer.py: patch 16, dim 1024, depth 24, heads 16
+        return VisionTransformer(embed_dim=1024, depth=24, heads=16, hybrid=False)
+    if name == "vit_base_patch16_384":      # patch 16, dim 768, depth 12, heads 12
+        return VisionTransformer(embed_dim=768, depth=12, heads=12, hybrid=False)
+    raise RuntimeError(f"timm shim: {name!r} is not restated")

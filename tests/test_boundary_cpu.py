@@ -83,3 +83,18 @@ def test_hub_entry_points_exist():
     assert m.num_channels == 3
     m = hub.dpt_hybrid_384(pretrained=False, task="depth")
     assert m.num_channels == 1
+
+
+def test_dpt_large_state_dict_layout_is_the_reference_layout():
+    """backbone='vitl16_384' (demo.py:81): key / shape / order of the reference class, from the golden file (any
+    box) and from the unmodified reference class itself (build container)."""
+    from omnidata_b200.model import DPTDepthModel, state_dict_spec
+    from oracle import reference_loader
+    rec = torch.load(GOLDEN / "dpt_large_fp32_seed0_c1.pt")
+    spec = [[k, list(s)] for k, s in state_dict_spec(1, backbone="vitl16_384")]
+    assert spec == rec["spec"]
+    model = DPTDepthModel(backbone="vitl16_384")
+    assert [[k, list(v.shape)] for k, v in model.state_dict().items()] == spec
+    if reference_loader.reference_available():
+        ref = reference_loader.load_reference_dpt(1, "vitl16_384")
+        assert [[k, list(v.shape)] for k, v in ref.state_dict().items()] == spec
