@@ -64,7 +64,7 @@ def test_constructor_and_forward_errors():
     from omnidata_b200._capi import OdbError
     from omnidata_b200.model import DPTDepthModel
     with pytest.raises(AssertionError):
-        DPTDepthModel(backbone="vitl16_384")
+        DPTDepthModel(backbone="vitb16_384")       # reference: print + assert False for backbones it does not build
     m = DPTDepthModel()
     assert m.num_channels == 1 and m.non_negative
     if not torch.cuda.is_available():
