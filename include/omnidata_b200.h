@@ -210,6 +210,16 @@ int odb_vnl_loss_fwd(const float* first, const float* second, const int32_t* p1,
                      const int32_t* p3, int32_t n_points, int32_t b, int32_t h, int32_t w, float fx, float fy,
                      float delta_z, int32_t select, float* out1, float* group_loss, void* stream);
 
+/* Backward of MidasLoss: grad[b][h][w] = d(w_ssi * ssi + w_reg * reg) / d(prediction) exactly as autograd derives it
+ * for losses/midas_loss.py:137-157 (ssi through the median element and the deviation; reg through prediction_ssi AND
+ * through the least-squares scale / shift).  Call after odb_midas_loss_fwd on the SAME prediction / target / mask with
+ * its workspace untouched (fwd_workspace).  For train_depth.py:276 `ssi + 0.1 * reg`: w_ssi = 1, w_reg = 0.1.
+ * bwd_workspace: odb_midas_loss_bwd_workspace_bytes(b) bytes; gbuf: scratch fp32 [b][h][w].  Deterministic. */
+int64_t odb_midas_loss_bwd_workspace_bytes(int32_t b);
+int odb_midas_loss_bwd(const float* prediction, const float* target, const uint8_t* mask, int32_t b, int32_t h,
+                       int32_t w, int32_t scales, float w_ssi, float w_reg, const void* fwd_workspace,
+                       void* bwd_workspace, float* gbuf, float* grad, void* stream);
+
 /* Normal-training loss pair (train_normal.py:247-258): with
  * preds = clamp(prediction, 0, 1) when clamp_prediction != 0,
  *   l1  = masked_l1_loss(preds, target, mask x3)                 (losses/masked_losses.py:4-7)

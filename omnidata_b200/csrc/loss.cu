@@ -251,6 +251,182 @@ __global__ void midas_finalize_kernel(MidasWs ws, int b_n, int scales, float alp
   out3[0] = ssi + alpha * reg;
 }
 
+// ------------------------------------------------------------------------------------------ MiDaS loss, backward
+// d(w_ssi * ssi + w_reg * reg) / d(prediction), what autograd produces for MidasLoss.forward (midas_loss.py:137-157).
+// Needs the forward workspace of the SAME inputs (medians, deviations, the five sums, per-scale mask counts).
+// With V the valid pixels of an image, n = |V|, N = sum of n over the batch, t / s the median / deviation of the
+// prediction, pa = (p - t)/(s + eps), e = sign(pa - ga), sigma = sign(p - t)  (both zero outside V):
+//   ssi:  dL/dp_j = e_j / (N (s+eps)) + dL/ds * sigma_j / (n+1) + [j = median element] dL/dt,
+//         dL/ds = -sum(e (p - t)) / (N (s+eps)^2),  dL/dt = -sum(e) / (N (s+eps)) - dL/ds * sum(sigma) / (n+1)
+//         (the nanmedian passes its gradient to one element: here the lowest index holding the median value)
+//   reg:  P = x0 q + x1, q = 1/(p+eps);  G = d reg / d P (signs of the masked forward differences at the four scales,
+//         weighted 1/(B M_s)),  gx0 = sum(G q), gx1 = sum(G);  x0, x1 depend on p through a00, a01, b0:
+//         d reg/dq_j = G_j x0 + [j in V] (2 C00 q_j + C01 + Cb0 u_j),  dq/dp = -q^2.
+struct MidasBwdWs {
+  double* sc;      // [b][16]: 0 inv = 1/(N (s+eps)), 1 dL/ds / (n+1), 2 dL/dt, 3 median index, 4 gx0, 5 gx1, 6 x0, 7 x1
+};
+
+// grid (b): the ssi scalars of one image
+__global__ void __launch_bounds__(kLossThreads) midas_bwd_ssi_kernel(const float* __restrict__ pred,
+                                                                     const float* __restrict__ target,
+                                                                     const uint8_t* __restrict__ mask, MidasWs ws,
+                                                                     MidasBwdWs bw, int b_n, int hw) {
+  __shared__ double scratch[32];
+  __shared__ int s_idx[32];
+  const int b = blockIdx.x;
+  const float* p = pred + (long long)b * hw;
+  const float* g = target + (long long)b * hw;
+  const uint8_t* mk = mask + (long long)b * hw;
+  const float tp = ws.med[b], tg = ws.med[b_n + b];
+  const float sp = ws.scale[b] + 1e-6f, sg = ws.scale[b_n + b] + 1e-6f;
+  double A = 0.0, Bs = 0.0, S = 0.0, n = 0.0;
+  int first = 0x7fffffff;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    if (!mk[i]) continue;
+    const float pv = p[i];
+    const float pa = (pv - tp) / sp, ga = (g[i] - tg) / sg;
+    const float d = pa - ga;
+    const double e = d > 0.f ? 1.0 : (d < 0.f ? -1.0 : 0.0);
+    const float c = pv - tp;
+    A += e;
+    Bs += e * (double)c;
+    S += c > 0.f ? 1.0 : (c < 0.f ? -1.0 : 0.0);
+    n += 1.0;
+    if (pv == tp && i < first) first = i;
+  }
+  const double rA = block_sum_d(A, scratch);
+  const double rB = block_sum_d(Bs, scratch);
+  const double rS = block_sum_d(S, scratch);
+  const double rn = block_sum_d(n, scratch);
+  // lowest index holding the median value
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_down_sync(0xffffffffu, first, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_idx[threadIdx.x >> 5] = first;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int k = 0x7fffffff;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) k = min(k, s_idx[w]);
+    double N = 0.0;
+    for (int bb = 0; bb < b_n; ++bb) N += ws.sums[bb * 8 + 1];
+    const double se = (double)sp;
+    const double inv = 1.0 / (N * se);
+    const double dLds = -rB / (N * se * se);
+    const double dLdt = -rA * inv - dLds * rS / (rn + 1.0);
+    double* sc = bw.sc + (long long)b * 16;
+    sc[0] = inv;
+    sc[1] = dLds / (rn + 1.0);
+    sc[2] = rn > 0.0 ? dLdt : 0.0;
+    sc[3] = (rn > 0.0 && k != 0x7fffffff) ? (double)k : -1.0;
+  }
+}
+
+// grid (b): G = d reg / d prediction_ssi for every pixel (all scales), gx0 = sum G q, gx1 = sum G
+__global__ void __launch_bounds__(kLossThreads) midas_bwd_reg_kernel(const float* __restrict__ pred,
+                                                                     const float* __restrict__ target,
+                                                                     const uint8_t* __restrict__ mask, MidasWs ws,
+                                                                     MidasBwdWs bw, int b_n, int h, int w, int scales,
+                                                                     float* __restrict__ gbuf) {
+  __shared__ double scratch[32];
+  const int b = blockIdx.x;
+  const long long img = (long long)b * h * w;
+  const float a00 = (float)ws.sums[b * 8 + 2], a01 = (float)ws.sums[b * 8 + 3], a11 = (float)ws.sums[b * 8 + 4];
+  const float b0 = (float)ws.sums[b * 8 + 5], b1 = (float)ws.sums[b * 8 + 6];
+  const float det = a00 * a11 - a01 * a01;
+  float x0 = 0.f, x1 = 0.f;
+  if (det != 0.f) {
+    x0 = (a11 * b0 - a01 * b1) / (det + 1e-6f);
+    x1 = (-a01 * b0 + a00 * b1) / (det + 1e-6f);
+  }
+  float wsc[4];
+  for (int s = 0; s < 4; ++s) {
+    const double M = s < scales ? ws.grad[(b * 4 + s) * 2 + 1] : 0.0;
+    wsc[s] = s < scales ? (float)(1.0 / ((double)b_n * (M != 0.0 ? M : 1.0))) : 0.f;
+  }
+  auto dval = [&](int y, int x, bool& m) {
+    const long long i = img + (long long)y * w + x;
+    m = mask[i] != 0;
+    const float pssi = x0 * (1.0f / (pred[i] + 1e-6f)) + x1;
+    return m ? (pssi - 1.0f / (target[i] + 1e-6f)) : 0.f;
+  };
+  auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+  double gx0 = 0.0, gx1 = 0.0;
+  const int total = h * w;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int y = i / w, x = i - y * w;
+    float G = 0.f;
+    bool m0;
+    const float d0 = dval(y, x, m0);
+    if (m0) {
+      for (int s = 0; s < scales; ++s) {
+        const int st = 1 << s;
+        if ((y & (st - 1)) || (x & (st - 1))) break;       // not on the grids of this and coarser scales
+        float acc = 0.f;
+        bool m1;
+        if (x - st >= 0) { const float d1 = dval(y, x - st, m1); if (m1) acc += sgn(d0 - d1); }
+        if (x + st < w) { const float d1 = dval(y, x + st, m1); if (m1) acc -= sgn(d1 - d0); }
+        if (y - st >= 0) { const float d1 = dval(y - st, x, m1); if (m1) acc += sgn(d0 - d1); }
+        if (y + st < h) { const float d1 = dval(y + st, x, m1); if (m1) acc -= sgn(d1 - d0); }
+        G += wsc[s] * acc;
+      }
+      const float q = 1.0f / (pred[img + i] + 1e-6f);
+      gx0 += (double)G * (double)q;
+      gx1 += (double)G;
+    }
+    gbuf[img + i] = G;
+  }
+  const double r0 = block_sum_d(gx0, scratch);
+  const double r1 = block_sum_d(gx1, scratch);
+  if (threadIdx.x == 0) {
+    double* sc = bw.sc + (long long)b * 16;
+    sc[4] = r0; sc[5] = r1; sc[6] = (double)x0; sc[7] = (double)x1;
+  }
+}
+
+// grid (blocks per image, b): the gradient itself
+__global__ void __launch_bounds__(256) midas_bwd_final_kernel(const float* __restrict__ pred,
+                                                              const float* __restrict__ target,
+                                                              const uint8_t* __restrict__ mask, MidasWs ws,
+                                                              MidasBwdWs bw, int b_n, int hw, float w_ssi, float w_reg,
+                                                              const float* __restrict__ gbuf, float* __restrict__ grad) {
+  const int b = blockIdx.y;
+  const double* sc = bw.sc + (long long)b * 16;
+  const float inv = (float)sc[0], dlds_n1 = (float)sc[1], dldt = (float)sc[2];
+  const int kmed = (int)sc[3];
+  const double gx0 = sc[4], gx1 = sc[5], x0 = sc[6], x1 = sc[7];
+  const double a00 = ws.sums[b * 8 + 2], a01 = ws.sums[b * 8 + 3], a11 = ws.sums[b * 8 + 4];
+  const double b0 = ws.sums[b * 8 + 5], b1 = ws.sums[b * 8 + 6];
+  double c00 = 0.0, c01 = 0.0, cb0 = 0.0;
+  {
+    const float detf = (float)a00 * (float)a11 - (float)a01 * (float)a01;     // the forward's fp32 test for det != 0
+    if (detf != 0.f) {
+      const double D = a00 * a11 - a01 * a01 + 1e-6;
+      c00 = gx0 * (-x0 * a11 / D) + gx1 * (b1 / D - x1 * a11 / D);
+      c01 = gx0 * ((-b1 + 2.0 * a01 * x0) / D) + gx1 * ((-b0 + 2.0 * a01 * x1) / D);
+      cb0 = gx0 * (a11 / D) + gx1 * (-a01 / D);
+    }
+  }
+  const float fc00 = (float)(2.0 * c00), fc01 = (float)c01, fcb0 = (float)cb0, fx0 = (float)x0;
+  const float tp = ws.med[b], tg = ws.med[b_n + b];
+  const float sp = ws.scale[b] + 1e-6f, sg = ws.scale[b_n + b] + 1e-6f;
+  const long long img = (long long)b * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    float gr = 0.f;
+    if (mask[img + i]) {
+      const float pv = pred[img + i], gv = target[img + i];
+      const float d = (pv - tp) / sp - (gv - tg) / sg;
+      const float e = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      const float c = pv - tp;
+      const float sigma = c > 0.f ? 1.f : (c < 0.f ? -1.f : 0.f);
+      float gs = e * inv + dlds_n1 * sigma;
+      if (i == kmed) gs += dldt;
+      const float q = 1.0f / (pv + 1e-6f), u = 1.0f / (gv + 1e-6f);
+      const float dq = gbuf[img + i] * fx0 + (fc00 * q + fc01 + fcb0 * u);
+      gr = w_ssi * gs - w_reg * q * q * dq;
+    }
+    grad[img + i] = gr;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ normal-training losses
 // masked_l1_loss + masked_cosine_angular_loss (losses/masked_losses.py:4-7,14-23) as train_normal.py:247-258
 // uses them: preds = clamp(model(rgb), 0, 1); mask_valid [b,1,h,w] repeated over the 3 channels;
@@ -462,6 +638,38 @@ extern "C" int odb_midas_loss_fwd(const float* prediction, const float* target, 
   midas_finalize_kernel<<<1, 32, 0, stream>>>(ws, b, scales, alpha, out3);
   count_launch();
   return check_launch("midas_loss_fwd");
+}
+
+extern "C" int64_t odb_midas_loss_bwd_workspace_bytes(int32_t b) { return (int64_t)b * 16 * 8; }
+
+extern "C" int odb_midas_loss_bwd(const float* prediction, const float* target, const uint8_t* mask, int32_t b,
+                                  int32_t h, int32_t w, int32_t scales, float w_ssi, float w_reg,
+                                  const void* fwd_workspace, void* bwd_workspace, float* gbuf, float* grad,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!prediction || !target || !mask || !fwd_workspace || !bwd_workspace || !gbuf || !grad || b < 1 || h < 1 ||
+      w < 1 || scales < 1 || scales > 4 || (long long)h * w > 0x7fffffffLL ||
+      (reinterpret_cast<uintptr_t>(bwd_workspace) & 7u))
+    return fail(ODB_ERR_INVALID, "midas_loss_bwd: bad argument");
+  char* base = const_cast<char*>(static_cast<const char*>(fwd_workspace));
+  MidasWs ws;
+  ws.sums = reinterpret_cast<double*>(base);
+  ws.grad = ws.sums + (size_t)b * 8;
+  ws.med = reinterpret_cast<float*>(ws.grad + (size_t)b * 8);
+  ws.scale = ws.med + 2 * (size_t)b;
+  MidasBwdWs bw;
+  bw.sc = static_cast<double*>(bwd_workspace);
+  const int hw = h * w;
+  midas_bwd_ssi_kernel<<<b, kLossThreads, 0, stream>>>(prediction, target, mask, ws, bw, b, hw);
+  count_launch();
+  midas_bwd_reg_kernel<<<b, kLossThreads, 0, stream>>>(prediction, target, mask, ws, bw, b, h, w, scales, gbuf);
+  count_launch();
+  int gx = (hw + 255) / 256;
+  if (gx > 64) gx = 64;
+  midas_bwd_final_kernel<<<dim3(gx, b), 256, 0, stream>>>(prediction, target, mask, ws, bw, b, hw, w_ssi, w_reg, gbuf,
+                                                         grad);
+  count_launch();
+  return check_launch("midas_loss_bwd");
 }
 
 extern "C" int odb_normal_loss_fwd(const float* prediction, const float* target, const uint8_t* mask_valid,

@@ -1,8 +1,9 @@
 """Depth-training losses of omnidata_tools/torch, forward pass on the GPU (C ABI, csrc/loss.cu).
 
 Same constructor / call signatures as the reference modules (losses/midas_loss.py:137-157,
-losses/virtual_normal_loss.py:7-27,151-194) and the loss mix of train_depth.py:261-279.  FORWARD ONLY:
-the returned tensors carry no autograd graph (the backward of the train step is the next scope row).
+losses/virtual_normal_loss.py:7-27,151-194) and the loss mix of train_depth.py:261-279.  MidasLoss is
+differentiable with respect to the prediction (odb_midas_loss_bwd behind torch.autograd); VNL_Loss and the
+normal-loss pair are forward only (their tensors carry no autograd graph).
 """
 from __future__ import annotations
 
@@ -45,6 +46,19 @@ class MidasLoss(torch.nn.Module):
         self.alpha, self.scales = float(alpha), int(scales)
 
     def forward(self, prediction, target, mask):
+        """-> (total, ssi, reg).  Differentiable with respect to `prediction` (odb_midas_loss_bwd)."""
+        if not prediction.is_cuda:
+            raise _capi.OdbError("prediction: CUDA tensor required (no CPU path)")
+        out = _MidasFn.apply(prediction, target, mask, self.alpha, self.scales)
+        return out[0], out[1], out[2]
+
+
+class _MidasFn(torch.autograd.Function):
+    """MidasLoss forward / backward kernels behind torch.autograd (gradient with respect to the prediction only, as
+    in the train step: target and mask are data)."""
+
+    @staticmethod
+    def forward(ctx, prediction, target, mask, alpha, scales):
         p, g = _f32(prediction, "prediction"), _f32(target, "target")
         b = p.shape[0]
         h, w = p.shape[-2:]
@@ -53,9 +67,26 @@ class MidasLoss(torch.nn.Module):
         ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=p.device)
         off = (-ws.data_ptr()) % 256
         out = torch.empty(3, dtype=torch.float32, device=p.device)
-        check(lib().odb_midas_loss_fwd(p.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, self.alpha, self.scales,
+        check(lib().odb_midas_loss_fwd(p.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, alpha, scales,
                                        out.data_ptr(), ws.data_ptr() + off, ws_bytes, _stream()), "odb_midas_loss_fwd")
-        return out[0], out[1], out[2]
+        ctx.save_for_backward(p, g, m, ws)
+        ctx.meta = (b, h, w, alpha, scales, off, prediction.shape, prediction.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, g, m, ws = ctx.saved_tensors
+        b, h, w, alpha, scales, off, shape, dtype = ctx.meta
+        go = grad_out.detach().float().cpu()                       # (d/d total, d/d ssi, d/d reg)
+        w_ssi = float(go[0] + go[1])
+        w_reg = float(alpha * go[0] + go[2])
+        bws = torch.empty(int(lib().odb_midas_loss_bwd_workspace_bytes(b)) // 8, dtype=torch.float64, device=p.device)
+        gbuf = torch.empty(b * h * w, dtype=torch.float32, device=p.device)
+        grad = torch.empty(b * h * w, dtype=torch.float32, device=p.device)
+        check(lib().odb_midas_loss_bwd(p.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, scales, w_ssi, w_reg,
+                                       ws.data_ptr() + off, bws.data_ptr(), gbuf.data_ptr(), grad.data_ptr(),
+                                       _stream()), "odb_midas_loss_bwd")
+        return grad.view(shape).to(dtype), None, None, None, None
 
 
 class VNL_Loss(torch.nn.Module):

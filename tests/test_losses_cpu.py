@@ -65,3 +65,25 @@ def test_normal_loss_oracle_golden():
     tot, l1, cos = loss_oracle.normal_step(*loss_oracle.normal_loss_inputs(0))
     assert abs(float(l1) - rec["l1"]) <= 2e-6 * abs(rec["l1"])
     assert abs(float(cos) - rec["cos"]) <= 2e-6 * abs(rec["cos"])
+
+
+@pytest.mark.skipif(not reference_loader.reference_available(), reason="reference tree not on this box")
+def test_loss_oracle_gradients_equal_unmodified_reference():
+    """autograd through the oracle restatements == autograd through the reference modules (the GPU backward
+    kernels are tested against the former on the GPU box)."""
+    MidasLoss, VNL_Loss = reference_loader.load_reference_losses()
+    pred, gt, mf = loss_oracle.loss_inputs(0)
+    mask = loss_oracle.make_valid_mask(mf)
+    p1 = pred.clone().requires_grad_(True)
+    MidasLoss(alpha=0.1, scales=4, reduction="image-based")(p1, gt, mask)[0].backward()
+    p2 = pred.clone().requires_grad_(True)
+    loss_oracle.midas_loss(p2, gt, mask)[0].backward()
+    assert float((p1.grad - p2.grad).norm() / p1.grad.norm()) <= 1e-6
+    np.random.seed(0)
+    p3 = pred.clone().requires_grad_(True)
+    VNL_Loss(1.0, 1.0, (384, 384))(p3, gt).backward()
+    np.random.seed(0)
+    pts = loss_oracle.vnl_select_index(384, 384)
+    p4 = pred.clone().requires_grad_(True)
+    loss_oracle.vnl_loss(p4, gt, pts).backward()
+    assert float((p3.grad - p4.grad).norm() / p3.grad.norm()) <= 1e-6

@@ -75,3 +75,31 @@ def test_normal_losses(lib_built, seed, batch):
     mask3 = losses.make_valid_mask(mf.cuda()).repeat_interleave(3, 1)
     tot2, l12, cos2 = losses.normal_losses(pred.cuda().clamp(0, 1), gt.cuda(), mask3)
     assert float(l12) == float(out["l1_loss"]) and float(cos2) == float(out["cos_loss"])
+
+
+@pytest.mark.parametrize("seed,batch", [(0, 2), (5, 3)])
+def test_midas_loss_backward(lib_built, seed, batch):
+    """odb_midas_loss_bwd (through torch.autograd) against float64 autograd of the oracle restatement, whose
+    gradient equals the unmodified reference module's (tests/test_losses_cpu.py)."""
+    from omnidata_b200 import losses
+    from oracle import loss_oracle
+    pred, gt, mf = loss_oracle.loss_inputs(seed, batch)
+    mask = loss_oracle.make_valid_mask(mf)
+    for weights in ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (1.0, 0.3, -0.2)):
+        p64 = pred.double().requires_grad_(True)
+        tot, ssi, reg = loss_oracle.midas_loss(p64, gt.double(), mask)
+        (weights[0] * tot + weights[1] * ssi + weights[2] * reg).backward()
+        ref = p64.grad.float()
+        p = pred.cuda().requires_grad_(True)
+        t2, s2, r2 = losses.MidasLoss(alpha=0.1, scales=4)(p, gt.cuda(), mask.cuda())
+        (weights[0] * t2 + weights[1] * s2 + weights[2] * r2).backward()
+        got = p.grad.cpu()
+        err = float((got - ref).norm() / ref.norm())
+        assert err <= 1e-5, (weights, err)
+        assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    # invalid pixels get no gradient; deterministic
+    assert float(got[~mask].abs().max()) == 0.0
+    p2 = pred.cuda().requires_grad_(True)
+    t3, s3, r3 = losses.MidasLoss(alpha=0.1, scales=4)(p2, gt.cuda(), mask.cuda())
+    (1.0 * t3 + 0.3 * s3 - 0.2 * r3).backward()
+    assert torch.equal(p2.grad.cpu(), got)
