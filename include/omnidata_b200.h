@@ -220,6 +220,14 @@ int odb_midas_loss_bwd(const float* prediction, const float* target, const uint8
                        int32_t w, int32_t scales, float w_ssi, float w_reg, const void* fwd_workspace,
                        void* bwd_workspace, float* gbuf, float* grad, void* stream);
 
+/* Backward of VNL_Loss.forward(first, second) with respect to `first` (train_depth.py:272: the prediction):
+ * grad fp32 [b][h][w] = upstream * d(loss)/d(first).  Call after odb_vnl_loss_fwd with the same arguments and its
+ * group_loss untouched.  acc: scratch, 8 bytes per pixel (64-bit fixed-point accumulators: the scatter over points
+ * sampled with replacement is bit-reproducible); sel4: scratch, 4 doubles. */
+int odb_vnl_loss_bwd(const float* first, const float* second, const int32_t* p1, const int32_t* p2, const int32_t* p3,
+                     int32_t n_points, int32_t b, int32_t h, int32_t w, float fx, float fy, int32_t select,
+                     const float* group_loss, float upstream, void* acc, double* sel4, float* grad, void* stream);
+
 /* Normal-training loss pair (train_normal.py:247-258): with
  * preds = clamp(prediction, 0, 1) when clamp_prediction != 0,
  *   l1  = masked_l1_loss(preds, target, mask x3)                 (losses/masked_losses.py:4-7)

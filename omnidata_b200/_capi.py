@@ -92,6 +92,9 @@ _SIGNATURES = {
     "odb_midas_loss_bwd_workspace_bytes": (C.c_int64, [C.c_int32]),
     "odb_midas_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "odb_vnl_loss_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_float] * 2 + [C.c_int32, C.c_void_p, C.c_float,
+                                                                                   C.c_void_p, C.c_void_p, C.c_void_p,
+                                                                                   C.c_void_p]),
     "odb_normal_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "odb_grad_norm_workspace_bytes": (C.c_int64, []),

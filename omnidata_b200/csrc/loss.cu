@@ -590,6 +590,120 @@ __global__ void __launch_bounds__(kLossThreads) vnl_reduce_kernel(const float* _
   if (threadIdx.x == 0) out[0] = (float)((total - dropped) / (double)(count - k));
 }
 
+// ------------------------------------------------------------------------------------------ virtual normal loss, backward
+// d(mean of the kept group losses) / d(first): what autograd gives for VNL_Loss.forward(first, second)
+// (virtual_normal_loss.py:151-194; train_depth.py:272 passes the prediction as `first`).  The boolean masks carry no
+// gradient; a kept group k contributes through its normal n = (P1 - P0) x (P2 - P0) of the FIRST argument's points:
+//   w = dL/dn = (r / |n| - (r . n) n / |n|^3) / K',   r = sign(n/|n| - m/|m|),   dL/dP1 = b x w, dL/dP2 = w x a,
+//   dL/dP0 = -(dL/dP1 + dL/dP2),   P = (u |d|, v |d|, d)  ->  dL/dd += Gx u sign(d)/fx + Gy v sign(d)/fy + Gz.
+// Pixels are sampled with replacement, so contributions are scattered with 64-bit FIXED-POINT atomics (2^-40 units):
+// integer addition is associative, the result is bit-reproducible.
+constexpr double kVnlFixScale = 1099511627776.0;   // 2^40
+
+// single block: which groups survive the "drop the lowest 25 %" selection.  sel: [0] threshold, [1] cut index (equal
+// values below it are dropped: the sort order among ties is by index), [2] number of kept groups
+__global__ void __launch_bounds__(kLossThreads) vnl_bwd_select_kernel(const float* __restrict__ loss, long long n,
+                                                                      int select, double* __restrict__ sel) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bc[2];
+  __shared__ double scratch[32];
+  __shared__ double s_cnt;
+  auto take = [&](long long i) { return !isnan(loss[i]); };
+  double cnt = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    if (take(i)) cnt += 1.0;
+  const double c = block_sum_d(cnt, scratch);
+  if (threadIdx.x == 0) s_cnt = c;
+  __syncthreads();
+  const unsigned long long count = (unsigned long long)s_cnt;
+  const unsigned long long k = select ? (unsigned long long)((double)count * 0.25) : 0ull;
+  if (count == 0 || k == 0) {
+    if (threadIdx.x == 0) { sel[0] = -1e300; sel[1] = 0.0; sel[2] = (double)count; }
+    return;
+  }
+  const uint32_t key = block_radix_select(loss, n, k - 1, take, hist, bc);   // largest dropped value
+  const float thr = key_to_float(key);
+  double nbelow = 0.0, neq = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    if (take(i)) { if (loss[i] < thr) nbelow += 1.0; else if (loss[i] == thr) neq += 1.0; }
+  const double nb = block_sum_d(nbelow, scratch);
+  const double ne = block_sum_d(neq, scratch);
+  if (threadIdx.x == 0) {
+    const long long tie_drop = (long long)k - (long long)nb;     // >= 1
+    long long cut = n;                                           // all equal values dropped
+    if ((long long)ne > tie_drop) {                              // ambiguity: drop the first tie_drop of them
+      long long seen = 0;
+      for (long long i = 0; i < n; ++i)
+        if (take(i) && loss[i] == thr && ++seen == tie_drop) { cut = i + 1; break; }
+    }
+    sel[0] = (double)thr; sel[1] = (double)cut; sel[2] = (double)(count - k);
+  }
+}
+
+__global__ void __launch_bounds__(256) vnl_bwd_groups_kernel(const float* __restrict__ first,
+                                                             const float* __restrict__ second,
+                                                             const int* __restrict__ p1, const int* __restrict__ p2,
+                                                             const int* __restrict__ p3, const float* __restrict__ loss,
+                                                             const double* __restrict__ sel, int b_n, int n_pts, int h,
+                                                             int w, float fx, float fy,
+                                                             unsigned long long* __restrict__ acc) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)b_n * n_pts) return;
+  const float l = loss[gid];
+  if (isnan(l)) return;                                          // filtered out in the forward pass
+  const float thr = (float)sel[0];
+  if (sel[0] > -1e299 && (l < thr || (l == thr && gid < (long long)sel[1]))) return;   // dropped by the selection
+  const float inv_k = (float)(1.0 / sel[2]);
+  const int b = (int)(gid / n_pts), n = (int)(gid % n_pts);
+  const int idx[3] = {p1[n], p2[n], p3[n]};
+  const float u0 = (float)(w / 2), v0 = (float)(h / 2);
+  Vec3 G[3], D[3];
+  float uu[3], vv[3], sg[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int y = idx[j] / w, x = idx[j] - y * w;
+    const float gd = first[(long long)b * h * w + idx[j]];
+    const float dd = second[(long long)b * h * w + idx[j]];
+    uu[j] = ((float)x - u0) / fx; vv[j] = ((float)y - v0) / fy;
+    sg[j] = gd > 0.f ? 1.f : (gd < 0.f ? -1.f : 0.f);
+    G[j] = {((float)x - u0) * fabsf(gd) / fx, ((float)y - v0) * fabsf(gd) / fy, gd};
+    D[j] = {((float)x - u0) * fabsf(dd) / fx, ((float)y - v0) * fabsf(dd) / fy, dd};
+  }
+  const bool z0[3] = {D[0].z == 0.f, D[1].z == 0.f, D[2].z == 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (z0[0]) D[j].x = 0.0001f;
+    if (z0[1]) D[j].y = 0.0001f;
+    if (z0[2]) D[j].z = 0.0001f;
+  }
+  const Vec3 a = sub3(G[1], G[0]), bb = sub3(G[2], G[0]);
+  const Vec3 gn = cross3(a, bb);
+  const Vec3 dn = cross3(sub3(D[1], D[0]), sub3(D[2], D[0]));
+  float gl = sqrtf(dot3(gn, gn)), dl = sqrtf(dot3(dn, dn));
+  const bool gzero = gl == 0.f;
+  if (gzero) gl += 0.01f;
+  if (dl == 0.f) dl += 0.01f;
+  auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+  const Vec3 r = {sgn(gn.x / gl - dn.x / dl), sgn(gn.y / gl - dn.y / dl), sgn(gn.z / gl - dn.z / dl)};
+  const float rg = gzero ? 0.f : dot3(r, gn) / (gl * gl * gl);
+  const Vec3 wv = {(r.x / gl - rg * gn.x) * inv_k, (r.y / gl - rg * gn.y) * inv_k, (r.z / gl - rg * gn.z) * inv_k};
+  const Vec3 dA = cross3(bb, wv), dB = cross3(wv, a);
+  const Vec3 dP[3] = {{-(dA.x + dB.x), -(dA.y + dB.y), -(dA.z + dB.z)}, dA, dB};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double g = (double)dP[j].x * (double)(uu[j] * sg[j]) + (double)dP[j].y * (double)(vv[j] * sg[j]) + (double)dP[j].z;
+    const long long q = __double2ll_rn(g * kVnlFixScale);
+    atomicAdd(acc + (long long)b * h * w + idx[j], (unsigned long long)q);
+  }
+}
+
+__global__ void __launch_bounds__(256) vnl_bwd_finish_kernel(const unsigned long long* __restrict__ acc, long long n,
+                                                             float upstream, float* __restrict__ grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  grad[i] = (float)((double)(long long)acc[i] * (1.0 / kVnlFixScale)) * upstream;
+}
+
 }  // namespace odb
 
 using namespace odb;
@@ -670,6 +784,29 @@ extern "C" int odb_midas_loss_bwd(const float* prediction, const float* target, 
                                                          grad);
   count_launch();
   return check_launch("midas_loss_bwd");
+}
+
+extern "C" int odb_vnl_loss_bwd(const float* first, const float* second, const int32_t* p1, const int32_t* p2,
+                                const int32_t* p3, int32_t n_points, int32_t b, int32_t h, int32_t w, float fx, float fy,
+                                int32_t select, const float* group_loss, float upstream, void* acc, double* sel4,
+                                float* grad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!first || !second || !p1 || !p2 || !p3 || !group_loss || !acc || !sel4 || !grad || n_points < 1 || b < 1 ||
+      h < 1 || w < 1 || fx == 0.f || fy == 0.f || (reinterpret_cast<uintptr_t>(acc) & 7u))
+    return fail(ODB_ERR_INVALID, "vnl_loss_bwd: bad argument");
+  const long long total = (long long)b * n_points;
+  const long long px = (long long)b * h * w;
+  cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)px * 8, stream);
+  if (e != cudaSuccess) return fail_cuda(e, "vnl_loss_bwd: memset");
+  vnl_bwd_select_kernel<<<1, kLossThreads, 0, stream>>>(group_loss, total, select, sel4);
+  count_launch();
+  vnl_bwd_groups_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      first, second, p1, p2, p3, group_loss, sel4, b, n_points, h, w, fx, fy, static_cast<unsigned long long*>(acc));
+  count_launch();
+  vnl_bwd_finish_kernel<<<(unsigned)((px + 255) / 256), 256, 0, stream>>>(static_cast<const unsigned long long*>(acc), px,
+                                                                        upstream, grad);
+  count_launch();
+  return check_launch("vnl_loss_bwd");
 }
 
 extern "C" int odb_normal_loss_fwd(const float* prediction, const float* target, const uint8_t* mask_valid,

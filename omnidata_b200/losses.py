@@ -1,9 +1,10 @@
 """Depth-training losses of omnidata_tools/torch, forward pass on the GPU (C ABI, csrc/loss.cu).
 
 Same constructor / call signatures as the reference modules (losses/midas_loss.py:137-157,
-losses/virtual_normal_loss.py:7-27,151-194) and the loss mix of train_depth.py:261-279.  MidasLoss is
-differentiable with respect to the prediction (odb_midas_loss_bwd behind torch.autograd); VNL_Loss and the
-normal-loss pair are forward only (their tensors carry no autograd graph).
+losses/virtual_normal_loss.py:7-27,151-194) and the loss mix of train_depth.py:261-279.  MidasLoss and VNL_Loss
+are differentiable with respect to the prediction (odb_midas_loss_bwd / odb_vnl_loss_bwd behind torch.autograd), so
+`depth_step_losses(...)["depth_loss"].backward()` yields d(loss)/d(depth_preds) — the first step of the train
+step's backward pass; the normal-loss pair is forward only.
 """
 from __future__ import annotations
 
@@ -109,26 +110,51 @@ class VNL_Loss(torch.nn.Module):
         return pts
 
     def forward(self, gt_depth, pred_depth, select=True, points=None):
-        a, d = _f32(gt_depth, "gt_depth"), _f32(pred_depth, "pred_depth")
-        b = a.shape[0]
-        h, w = a.shape[-2:]
+        """Differentiable with respect to the FIRST argument (what train_depth.py:272 passes there: the prediction)."""
+        if not gt_depth.is_cuda:
+            raise _capi.OdbError("gt_depth: CUDA tensor required (no CPU path)")
+        h, w = gt_depth.shape[-2:]
         if (h, w) != self.input_size:
             raise ValueError("input size differs from the one given at construction")
         p1, p2, p3 = points if points is not None else self.select_index()
-        dev = a.device
-        t1, t2, t3 = (torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in (p1, p2, p3))
+        dev = gt_depth.device
+        pts = tuple(torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in (p1, p2, p3))
+        return _VnlFn.apply(gt_depth, pred_depth, pts, self.fx, self.fy, self.delta_z, bool(select))
+
+
+class _VnlFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, first, second, pts, fx, fy, delta_z, select):
+        a, d = _f32(first, "gt_depth"), _f32(second, "pred_depth")
+        b = a.shape[0]
+        h, w = a.shape[-2:]
+        t1, t2, t3 = pts
         n = t1.numel()
-        scratch = torch.empty(b * n, dtype=torch.float32, device=dev)
-        out = torch.empty(1, dtype=torch.float32, device=dev)
+        scratch = torch.empty(b * n, dtype=torch.float32, device=a.device)
+        out = torch.empty(1, dtype=torch.float32, device=a.device)
         check(lib().odb_vnl_loss_fwd(a.data_ptr(), d.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(), n, b, h,
-                                     w, self.fx, self.fy, self.delta_z, 1 if select else 0, out.data_ptr(),
+                                     w, fx, fy, delta_z, 1 if select else 0, out.data_ptr(),
                                      scratch.data_ptr(), _stream()), "odb_vnl_loss_fwd")
+        ctx.save_for_backward(a, d, t1, t2, t3, scratch)
+        ctx.meta = (b, h, w, n, fx, fy, select, first.shape, first.dtype)
         return out[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, d, t1, t2, t3, scratch = ctx.saved_tensors
+        b, h, w, n, fx, fy, select, shape, dtype = ctx.meta
+        acc = torch.empty(b * h * w, dtype=torch.int64, device=a.device)
+        sel = torch.empty(4, dtype=torch.float64, device=a.device)
+        grad = torch.empty(b * h * w, dtype=torch.float32, device=a.device)
+        check(lib().odb_vnl_loss_bwd(a.data_ptr(), d.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(), n, b, h, w,
+                                     fx, fy, 1 if select else 0, scratch.data_ptr(), float(grad_out), acc.data_ptr(),
+                                     sel.data_ptr(), grad.data_ptr(), _stream()), "odb_vnl_loss_bwd")
+        return grad.view(shape).to(dtype), None, None, None, None, None, None
 
 
 def depth_step_losses(depth_preds, depth_gt, mask_float, midas: MidasLoss, vnl: VNL_Loss, train: bool = True,
                       global_step: int = 10 ** 9):
-    """The loss arithmetic of Depth._shared_step (train_depth.py:261-287), forward only."""
+    """The loss arithmetic of Depth._shared_step (train_depth.py:261-287); differentiable w.r.t. depth_preds."""
     depth_preds = torch.clamp(depth_preds, 0, 1)
     mask_valid = make_valid_mask(mask_float)
     _, ssi, reg = midas(depth_preds, depth_gt, mask_valid)

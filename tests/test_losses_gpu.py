@@ -103,3 +103,42 @@ def test_midas_loss_backward(lib_built, seed, batch):
     t3, s3, r3 = losses.MidasLoss(alpha=0.1, scales=4)(p2, gt.cuda(), mask.cuda())
     (1.0 * t3 + 0.3 * s3 - 0.2 * r3).backward()
     assert torch.equal(p2.grad.cpu(), got)
+
+
+@pytest.mark.parametrize("seed,batch", [(0, 2), (6, 3)])
+def test_vnl_loss_backward_and_train_step_gradient(lib_built, seed, batch):
+    """odb_vnl_loss_bwd against fp32 autograd of the oracle (same fp32 mask decisions), and the gradient of the whole
+    train_depth.py loss mix (clamp -> ssi + 0.1 reg + 10 vn) with respect to the raw network output."""
+    from omnidata_b200 import losses
+    from oracle import loss_oracle
+    pred, gt, mf = loss_oracle.loss_inputs(seed, batch)
+    np.random.seed(seed)
+    pts = loss_oracle.vnl_select_index(384, 384)
+    p32 = pred.clone().requires_grad_(True)
+    loss_oracle.vnl_loss(p32, gt, pts).backward()
+    ref = p32.grad
+    p = pred.cuda().requires_grad_(True)
+    np.random.seed(seed)
+    vnl = losses.VNL_Loss(1.0, 1.0, (384, 384))
+    v = vnl(p, gt.cuda())
+    v.backward()
+    got = p.grad.cpu()
+    assert float((got - ref).norm() / ref.norm()) <= 2e-4
+    p2 = pred.cuda().requires_grad_(True)
+    np.random.seed(seed)
+    vnl(p2, gt.cuda()).backward()
+    assert torch.equal(p2.grad.cpu(), got)                               # fixed-point scatter: bit-reproducible
+    # ---- the train-step mix, through the clamp (train_depth.py:263-279)
+    raw = (pred * 1.3 - 0.1)
+    r32 = raw.clone().requires_grad_(True)
+    dp = torch.clamp(r32, 0, 1)
+    mask = loss_oracle.make_valid_mask(mf)
+    _, ssi, reg = loss_oracle.midas_loss(dp, gt, mask)
+    vn = loss_oracle.vnl_loss(dp, gt, pts)
+    (ssi + 0.1 * reg + 10 * vn).backward()
+    r = raw.cuda().requires_grad_(True)
+    np.random.seed(seed)
+    out = losses.depth_step_losses(r, gt.cuda(), mf.cuda(), losses.MidasLoss(), losses.VNL_Loss(1.0, 1.0, (384, 384)))
+    out["depth_loss"].backward()
+    g = r.grad.cpu()
+    assert float((g - r32.grad).norm() / r32.grad.norm()) <= 2e-4
