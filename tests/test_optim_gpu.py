@@ -29,7 +29,8 @@ def test_flat_adam_matches_torch(lib_built, n, max_norm):
         st = ref.state[ref_p]
         # (when the clip is active torch's coefficient carries the ~1e-5 error of its fp32 norm)
         rt = 1e-5 if max_norm is None else 1e-4
-        assert torch.allclose(opt.exp_avg.cpu(), st["exp_avg"], rtol=rt, atol=1e-12)
+        # (m = 0.9 m + 0.1 g cancels for some elements: absolute tolerance relative to the typical magnitude)
+        assert torch.allclose(opt.exp_avg.cpu(), st["exp_avg"], rtol=rt, atol=rt * float(st["exp_avg"].abs().max()))
         assert torch.allclose(opt.exp_avg_sq.cpu(), st["exp_avg_sq"], rtol=2 * rt, atol=1e-20)
         # the parameters themselves: the lr-sized update is below fp32 resolution of p, so agreement is
         # limited by one rounding of p per step (ulp(4) = 4.8e-7)
