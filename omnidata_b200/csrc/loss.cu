@@ -5,8 +5,9 @@
 //   * VNL_Loss.forward           losses/virtual_normal_loss.py:29-194
 // All inputs are fp32 (the reference trains in fp32).  Reductions are deterministic: per-thread fp64
 // partials combined in a fixed shuffle/shared-memory order, medians / order statistics by an exact
-// 4-pass radix select with integer histograms.  Forward only — the backward pass of the train step
-// is the next row of the scope table, not built yet.
+// 4-pass radix select with integer histograms.  MidasLoss and VNL_Loss also have their backward passes
+// here (gradient with respect to the prediction: the first step of the train step's backward; the network's
+// own backward is not built).
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/omnidata_b200.h"
