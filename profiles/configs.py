@@ -34,9 +34,11 @@ def main():
     depth = DPTDepthModel()
     depth.load_state_dict(synthetic.make_state_dict(0, 1))
     depth = depth.to(dev).eval()
+    depth.use_cuda_graph = True
     normal = DPTDepthModel(num_channels=3)
     normal.load_state_dict(synthetic.make_state_dict(1, 3))
     normal = normal.to(dev).eval()
+    normal.use_cuda_graph = True
     g = torch.Generator().manual_seed(0)
     with torch.no_grad():
         x64 = (torch.rand(64, 3, 384, 384, generator=g) * 2 - 1).to(dev)
