@@ -254,6 +254,20 @@ int odb_clip_grad_norm(const float* grads, int64_t n, float max_norm, void* work
 int odb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   const float* clip2, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
 
+/* ---- 3-D refocus augmentation (data/refocus_augmentation.py) ------------------------------
+ * odb_refocus_quantiles: compute_quantiles (:82-87): quantile_vals fp32 [b][n_quantiles + 1] = torch.quantile(depth[b],
+ * i / n_quantiles) (linear interpolation; exact order statistics by radix select), first -= eps, last += eps.
+ * odb_refocus_compose: refocus_image (:144-157) after the blur radii are known: the Gaussian blur stack
+ * (separable, replicate padding, cutoff int(3 r) made odd, r < 0.1 = copy; radii fp32 [b][levels]) and the per-pixel
+ * blend of the two levels bracketing the pixel's depth with weights 1 - dist^2.  rgb fp32 [b][3][h][w], depth fp32
+ * [b][h][w], out fp32 [b][3][h][w]; stack_tmp / stack: scratch fp32 [b][levels][3][h][w] each; segments (optional)
+ * int32 [b][h][w] = the left quantile index (`return_segments`). */
+int odb_refocus_quantiles(const float* depth, int32_t b, int32_t h, int32_t w, int32_t n_quantiles, float eps,
+                          float* quantile_vals, void* stream);
+int odb_refocus_compose(const float* rgb, const float* depth, const float* quantile_vals, const float* blur_radii,
+                        int32_t b, int32_t h, int32_t w, int32_t levels, float* stack_tmp, float* stack, float* out,
+                        int32_t* segments, void* stream);
+
 int odb_fill_zero(void* ptr, int64_t bytes, void* stream);
 
 /* ---- image pre- / post-processing either side of the forward ------------

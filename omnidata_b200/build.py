@@ -16,7 +16,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libomnidata_b200.so"
 SOURCES = ["api.cu", "conv_gemm.cu", "ops.cu", "attention.cu", "attention_tc.cu", "attention_tc2.cu", "loss.cu",
-           "imageproc.cu", "optim.cu"]
+           "imageproc.cu", "optim.cu", "refocus.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

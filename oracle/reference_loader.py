@@ -54,3 +54,28 @@ def load_reference_masked_losses():
     _prepare_path()
     m = importlib.import_module("losses.masked_losses")
     return m.masked_l1_loss, m.masked_cosine_angular_loss
+
+
+def load_reference_refocus():
+    """data/refocus_augmentation.py, unmodified.  The module imports matplotlib / seaborn at the top (plotting
+    helpers it never calls on this path); both are absent here, so empty stand-in modules are registered first."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present")
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.lines", "seaborn"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib.lines"].__dict__.setdefault("Line2D", object)
+    sys.modules["matplotlib"].__dict__.setdefault("pyplot", sys.modules["matplotlib.pyplot"])
+    sys.modules["matplotlib"].__dict__.setdefault("lines", sys.modules["matplotlib.lines"])
+    _prepare_path()
+    mod = importlib.import_module("data.refocus_augmentation")
+    import torch
+    if not torch.cuda.is_available():
+        # torch >= 2.5 refuses torch.nn.parallel.parallel_apply without an accelerator; it only runs the given
+        # callables on threads, so a sequential map is the same computation
+        mod.parallel_apply = lambda modules, args: [m(*a) for m, a in zip(modules, args)]
+    return mod
