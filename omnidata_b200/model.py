@@ -34,7 +34,20 @@ _ARCH = {
     "vitb_rn50_384": dict(embed=768, heads=12, depth=12, hybrid=True, hooks=(8, 11), rn_in=(256, 512, 768, 768)),
     "vitl16_384": dict(embed=1024, heads=16, depth=24, hybrid=False, hooks=(5, 11, 17, 23),
                        rn_in=(256, 512, 1024, 1024)),
+    #   vitb16_384   plain ViT-B/16, blocks 2/5/8/11, reassemble widths 96/192/384/768 (vit.py:311-318); the 96
+    #                channels are carried zero-padded to 128 internally (the GEMM N tile is a multiple of 64)
+    "vitb16_384": dict(embed=768, heads=12, depth=12, hybrid=False, hooks=(2, 5, 8, 11),
+                       rn_in=(96, 192, 384, 768)),
 }
+
+
+def _pad_to(t: torch.Tensor, dim: int, size: int) -> torch.Tensor:
+    """zero-pad `t` along `dim` up to `size` (weights / biases of layers whose width is not a multiple of 64)."""
+    if t.shape[dim] == size:
+        return t
+    shape = list(t.shape)
+    shape[dim] = size - t.shape[dim]
+    return torch.cat([t, torch.zeros(shape, dtype=t.dtype, device=t.device)], dim=dim)
 _EMBED, _HEADS, _DEPTH, _HOOKS = 768, 12, 12, (8, 11)      # the DPT-Hybrid values (module-level names kept)
 
 
@@ -199,6 +212,7 @@ class DPTDepthModel(nn.Module):
             raise AssertionError(f"Backbone '{backbone}' not implemented")
         self.backbone = backbone
         self.arch = _ARCH[backbone]
+        self._rn_pad = tuple((c + 63) // 64 * 64 for c in self.arch["rn_in"])
         if features != 256 or readout != "project" or use_bn:
             raise NotImplementedError("only features=256, readout='project', use_bn=False (the Omnidata DPT-Hybrid)")
         self.non_negative = bool(non_negative)
@@ -308,19 +322,21 @@ class DPTDepthModel(nn.Module):
             pk[f"ro{n}_wfull"] = wfull
             pk[f"ro{n}_wtok"] = wfull[:, :D].contiguous()          # token half of the split Linear
             pk[f"ro{n}_b"] = f32(p + "0.project.0.bias")
-            pk[f"pp{n}_w"] = ops.pack_conv_weight(sd[p + "3.weight"])
-            pk[f"pp{n}_b"] = f32(p + "3.bias")
+            cp = self._rn_pad[n - 1]
+            pk[f"pp{n}_w"] = ops.pack_conv_weight(_pad_to(sd[p + "3.weight"], 0, cp))
+            pk[f"pp{n}_b"] = _pad_to(f32(p + "3.bias"), 0, cp)
         pk["pp4s_w"] = ops.pack_conv_weight(sd["pretrained.act_postprocess4.4.weight"])
         pk["pp4s_b"] = f32("pretrained.act_postprocess4.4.bias")
         if not self.arch["hybrid"]:
             # ConvTranspose2d(c, c, k, stride k) (vit.py:216-225, 240-249): k*k independent 1x1 convolutions,
             # one per output phase (dy, dx): W_phase[out][in] = weight[in][out][dy][dx]
             for n, k in ((1, 4), (2, 2)):
-                w = sd[f"pretrained.act_postprocess{n}.4.weight"].float()
+                cp = self._rn_pad[n - 1]
+                w = _pad_to(_pad_to(sd[f"pretrained.act_postprocess{n}.4.weight"].float(), 0, cp), 1, cp)
                 pk[f"pp{n}t_w"] = [[bf(w[:, :, dy, dx].t()) for dx in range(k)] for dy in range(k)]
-                pk[f"pp{n}t_b"] = f32(f"pretrained.act_postprocess{n}.4.bias")
+                pk[f"pp{n}t_b"] = _pad_to(f32(f"pretrained.act_postprocess{n}.4.bias"), 0, cp)
         for n in (1, 2, 3, 4):
-            pk[f"rn{n}_w"] = ops.pack_conv_weight(sd[f"scratch.layer{n}_rn.weight"])
+            pk[f"rn{n}_w"] = ops.pack_conv_weight(_pad_to(sd[f"scratch.layer{n}_rn.weight"], 1, self._rn_pad[n - 1]))
             p = f"scratch.refinenet{n}."
             pk[f"ff{n}_out"] = (ops.pack_conv_weight(sd[p + "out_conv.weight"]), f32(p + "out_conv.bias"))
             for u in (1, 2):
@@ -554,7 +570,7 @@ class DPTDepthModel(nn.Module):
                     ops.conv1x1(t, pk[f"pp{n}t_w"][dy][dx], o[:, dy::k, dx::k, :], bias=pk[f"pp{n}t_b"])
             return o
 
-        rn_in = self.arch["rn_in"]
+        rn_in = self._rn_pad                 # (reassemble widths, zero-padded to the GEMM's N granularity)
         if self.arch["hybrid"]:
             tokens_8, tokens_11 = hooked
             layer_3 = readout(tokens_8, 3, rn_in[2])

@@ -101,11 +101,11 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def run_reference_large(dtype=torch.float32, n_samples: int = 4096):
-    """DPT-Large (backbone 'vitl16_384', demo.py:81) — the UNMODIFIED reference class on the timm shim's
-    vit_large_patch16_384; seeded weights over the reference's own key/shape table."""
+def run_reference_large(dtype=torch.float32, n_samples: int = 4096, backbone: str = "vitl16_384"):
+    """DPT-Large (backbone 'vitl16_384', demo.py:81) / plain ViT-B ('vitb16_384') — the UNMODIFIED reference class
+    on the timm shim's plain ViTs; seeded weights over the reference's own key/shape table."""
     from omnidata_b200.synthetic import make_state_dict as gen
-    model = rl.load_reference_dpt(1, "vitl16_384").eval()
+    model = rl.load_reference_dpt(1, backbone).eval()
     spec = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
     model.load_state_dict(gen(0, 1, spec=spec), strict=True)
     model = model.to(dtype)
@@ -124,17 +124,18 @@ def run_reference_large(dtype=torch.float32, n_samples: int = 4096):
     with torch.no_grad():
         y = model(x.to(dtype)).float()
     acts = model.pretrained.activations
-    for n, hk in zip("1234", (5, 11, 17, 23)):
+    for n, hk in zip("1234", (5, 11, 17, 23) if backbone == "vitl16_384" else (2, 5, 8, 11)):
         taps[f"tokens_{hk}"] = acts[n].detach().float().clone()
     return y, taps, spec
 
 
-def make_large_golden(n_samples: int = 4096):
-    """dpt_large_fp32_seed0_c1.pt — reference DPT-Large forward (fp32) + the drift the same reference module
-    shows when run entirely in bf16 on the CPU (the yardstick for the bf16 kernels)."""
+def make_large_golden(n_samples: int = 4096, backbone: str = "vitl16_384", fname: str = "dpt_large_fp32_seed0_c1.pt"):
+    """dpt_large_fp32_seed0_c1.pt / dpt_vitb16_fp32_seed0_c1.pt — reference forward (fp32) of the plain-ViT DPTs +
+    the drift the same reference module shows when run entirely in bf16 on the CPU (the yardstick for the bf16
+    kernels)."""
     global N_SAMPLES
-    y, taps, spec = run_reference_large(torch.float32)
-    yb, tapsb, _ = run_reference_large(torch.bfloat16)
+    y, taps, spec = run_reference_large(torch.float32, backbone=backbone)
+    yb, tapsb, _ = run_reference_large(torch.bfloat16, backbone=backbone)
     old = N_SAMPLES
     N_SAMPLES = n_samples
     try:
@@ -145,8 +146,8 @@ def make_large_golden(n_samples: int = 4096):
                "spec": [[k, list(sh)] for k, sh in spec]}
     finally:
         N_SAMPLES = old
-    torch.save(rec, GOLDEN / "dpt_large_fp32_seed0_c1.pt")
-    print("DPT-Large: output mean %.6f, bf16 drift (output) %.3e" % (rec["output_mean"], rec["bf16_output_drift"]))
+    torch.save(rec, GOLDEN / fname)
+    print(backbone + ": output mean %.6f, bf16 drift (output) %.3e" % (rec["output_mean"], rec["bf16_output_drift"]))
     for k, v in rec["bf16_drift"].items():
         print(f"   {k:14s} rms {rec['taps'][k]['rms']:.4f}  pure-bf16 drift {v:.3e}")
 

@@ -64,7 +64,7 @@ def test_constructor_and_forward_errors():
     from omnidata_b200._capi import OdbError
     from omnidata_b200.model import DPTDepthModel
     with pytest.raises(AssertionError):
-        DPTDepthModel(backbone="vitb16_384")       # reference: print + assert False for backbones it does not build
+        DPTDepthModel(backbone="resnext101_wsl")   # reference: print + assert False for backbones it does not build
     m = DPTDepthModel()
     assert m.num_channels == 1 and m.non_negative
     if not torch.cuda.is_available():
@@ -85,16 +85,18 @@ def test_hub_entry_points_exist():
     assert m.num_channels == 1
 
 
-def test_dpt_large_state_dict_layout_is_the_reference_layout():
-    """backbone='vitl16_384' (demo.py:81): key / shape / order of the reference class, from the golden file (any
-    box) and from the unmodified reference class itself (build container)."""
+@pytest.mark.parametrize("backbone,golden", [("vitl16_384", "dpt_large_fp32_seed0_c1.pt"),
+                                             ("vitb16_384", "dpt_vitb16_fp32_seed0_c1.pt")])
+def test_plain_vit_state_dict_layout_is_the_reference_layout(backbone, golden):
+    """backbones 'vitl16_384' (demo.py:81) / 'vitb16_384': key / shape / order of the reference class, from the golden
+    file (any box) and from the unmodified reference class itself (build container)."""
     from omnidata_b200.model import DPTDepthModel, state_dict_spec
     from oracle import reference_loader
-    rec = torch.load(GOLDEN / "dpt_large_fp32_seed0_c1.pt")
-    spec = [[k, list(s)] for k, s in state_dict_spec(1, backbone="vitl16_384")]
+    rec = torch.load(GOLDEN / golden)
+    spec = [[k, list(s)] for k, s in state_dict_spec(1, backbone=backbone)]
     assert spec == rec["spec"]
-    model = DPTDepthModel(backbone="vitl16_384")
+    model = DPTDepthModel(backbone=backbone)
     assert [[k, list(v.shape)] for k, v in model.state_dict().items()] == spec
     if reference_loader.reference_available():
-        ref = reference_loader.load_reference_dpt(1, "vitl16_384")
+        ref = reference_loader.load_reference_dpt(1, backbone)
         assert [[k, list(v.shape)] for k, v in ref.state_dict().items()] == spec

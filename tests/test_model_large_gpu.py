@@ -1,5 +1,5 @@
-"""DPT-Large (`backbone='vitl16_384'`, SURVEY.md 8(f) rank 3: plain ViT-L/16 encoder, ConvTranspose reassemble)
-through the same kernels, against golden vectors produced by the UNMODIFIED reference class in the build
+"""DPT-Large (`backbone='vitl16_384'`) and the plain ViT-B DPT (`'vitb16_384'`) — SURVEY.md 8(f) rank 3: plain
+ViT/16 encoders with the ConvTranspose reassemble — through the same kernels, against golden vectors produced by the UNMODIFIED reference class in the build
 container (tests/golden/dpt_large_fp32_seed0_c1.pt, oracle/make_golden.py::make_large_golden).
 
 Criterion: at every tap the mismatch against the reference's fp32 result is at most
@@ -20,15 +20,19 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-@pytest.fixture(scope="module")
-def setup(lib_built):
+CASES = {"vitl16_384": "dpt_large_fp32_seed0_c1.pt", "vitb16_384": "dpt_vitb16_fp32_seed0_c1.pt"}
+
+
+@pytest.fixture(scope="module", params=sorted(CASES))
+def setup(lib_built, request):
     from omnidata_b200 import synthetic
     from omnidata_b200.model import DPTDepthModel, state_dict_spec
     from oracle import make_golden
-    rec = torch.load(GOLDEN / "dpt_large_fp32_seed0_c1.pt")
-    spec = state_dict_spec(1, backbone="vitl16_384")
+    backbone = request.param
+    rec = torch.load(GOLDEN / CASES[backbone])
+    spec = state_dict_spec(1, backbone=backbone)
     assert [[k, list(s)] for k, s in spec] == rec["spec"]          # the reference's own key / shape table
-    model = DPTDepthModel(backbone="vitl16_384")
+    model = DPTDepthModel(backbone=backbone)
     model.load_state_dict(synthetic.make_state_dict(0, 1, spec=spec), strict=True)
     model = model.cuda().eval()
     x = torch.cat([make_golden.golden_input(1, seed=0), make_golden.golden_input(1, seed=7)]).cuda()
