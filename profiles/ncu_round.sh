@@ -10,7 +10,7 @@ timeout 600 ncu --set full --import-source on $COMMON -k regex:conv_gemm -s 53 -
 timeout 600 ncu --set full --import-source on $COMMON -k regex:attention_tc -c 1 -o gpurun_out/${TAG}_attention python profiles/ncu_target.py > gpurun_out/${TAG}_ncu_c.log 2>&1
 timeout 600 ncu --set full --import-source on $COMMON -k regex:upsample2x -s 2 -c 3 -o gpurun_out/${TAG}_upsample python profiles/ncu_target.py > gpurun_out/${TAG}_ncu_d.log 2>&1
 timeout 600 ncu --set full $COMMON -k regex:groupnorm_apply -s 2 -c 2 -o gpurun_out/${TAG}_gn_apply python profiles/ncu_target.py > gpurun_out/${TAG}_ncu_e.log 2>&1
-timeout 600 ncu --set full --import-source on $COMMON -k regex:conv_gemm -s 130 -c 1 -o gpurun_out/${TAG}_head_conv python profiles/ncu_target.py > gpurun_out/${TAG}_ncu_f.log 2>&1
+timeout 600 ncu --set full --import-source on $COMMON -k regex:conv_gemm -s 129 -c 1 -o gpurun_out/${TAG}_head_conv python profiles/ncu_target.py > gpurun_out/${TAG}_ncu_f.log 2>&1
 for f in vit_gemm attention upsample gn_apply head_conv; do
   ncu -i gpurun_out/${TAG}_${f}.ncu-rep --page raw --csv > gpurun_out/${TAG}_${f}_ncu_full_metrics.csv 2>/dev/null
 done
