@@ -268,6 +268,13 @@ int odb_refocus_compose(const float* rgb, const float* depth, const float* quant
                         int32_t b, int32_t h, int32_t w, int32_t levels, float* stack_tmp, float* stack, float* out,
                         int32_t* segments, void* stream);
 
+/* Backward of the normal-training loss pair: grad fp32 [b][3][h][w] = d(w_l1 * l1 + w_cos * cos) / d(prediction)
+ * (through the clamp when clamp_prediction != 0); for train_normal.py:258 `cos + 10 * l1`: w_l1 = 10, w_cos = 1.
+ * fwd_workspace: the workspace odb_normal_loss_fwd filled for the same inputs. */
+int odb_normal_loss_bwd(const float* prediction, const float* target, const uint8_t* mask_valid, int32_t b, int32_t h,
+                        int32_t w, int32_t clamp_prediction, float w_l1, float w_cos, const double* fwd_workspace,
+                        float* grad, void* stream);
+
 int odb_fill_zero(void* ptr, int64_t bytes, void* stream);
 
 /* ---- image pre- / post-processing either side of the forward ------------

@@ -104,6 +104,8 @@ _SIGNATURES = {
     "odb_refocus_quantiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                         C.c_void_p]),
     "odb_refocus_compose": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 5),
+    "odb_normal_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "odb_fill_zero": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "odb_pil_resize_crop_to_tensor": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

@@ -448,7 +448,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         ODB_TRACE_TILE(iter, 2);
       }
     }
-  } else if (!HEAD || warp < 6) {
+  } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;      // which 32 of the 64 chunk columns this warp owns
@@ -620,6 +620,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t tempty0 = PAIR ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const uint32_t tempty1 = PAIR ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
     for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
+      // head tail: the two warp sets (warps 2-5 / 6-9, one warp per TMEM lane quadrant each) alternate tiles —
+      // set `half` owns accumulator buffer `half` — so that each has two tile periods for its epilogue (with a
+      // single set the 128 -> 32 head convolution was bound by this epilogue, one warp per SM sub-partition)
+      if (HEAD && (iter & 1u) != static_cast<uint32_t>(half)) continue;
       int tn, tx, ty, tb;
       decode(tile, tn, tx, ty, tb);
       const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
@@ -656,16 +660,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         if (valid) {
           for (int k = 0; k < p.head_c; ++k) {
-            float o = __ldg(p.head_b + k);
             const float4* wk = reinterpret_cast<const float4*>(p.head_w + k * 32);
+            float o0 = __ldg(p.head_b + k), o1 = 0.f, o2 = 0.f, o3 = 0.f;     // four independent chains
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 w4 = __ldg(wk + j);
-              o = fmaf(v[4 * j + 0], w4.x, o);
-              o = fmaf(v[4 * j + 1], w4.y, o);
-              o = fmaf(v[4 * j + 2], w4.z, o);
-              o = fmaf(v[4 * j + 3], w4.w, o);
+              o0 = fmaf(v[4 * j + 0], w4.x, o0);
+              o1 = fmaf(v[4 * j + 1], w4.y, o1);
+              o2 = fmaf(v[4 * j + 2], w4.z, o2);
+              o3 = fmaf(v[4 * j + 3], w4.w, o3);
             }
+            float o = (o0 + o1) + (o2 + o3);
             if (p.head_relu) o = fmaxf(o, 0.f);
             p.head_out[((static_cast<long long>(tb) * p.head_c + k) * p.out_h + y) * p.out_w + x] = o;
           }

@@ -424,6 +424,58 @@ __global__ void normal_loss_finalize_kernel(const double* __restrict__ partial, 
   out3[0] = cos_loss + 10.0f * l1_loss;
 }
 
+// backward of the pair: grad[b][c][h][w] = d(w_l1 * l1 + w_cos * cos) / d(prediction) (through the optional clamp)
+__global__ void __launch_bounds__(256) normal_loss_bwd_kernel(const float* __restrict__ pred,
+                                                              const float* __restrict__ target,
+                                                              const uint8_t* __restrict__ mask,
+                                                              const double* __restrict__ partial, int b_n, int hw,
+                                                              int clamp_pred, float w_l1, float w_cos,
+                                                              float* __restrict__ grad) {
+  const int b = blockIdx.y;
+  double cnt = 0.0;
+  for (int i = 0; i < b_n; ++i) cnt += partial[i * 3 + 2];
+  const float k_l1 = (float)((double)w_l1 / (3.0 * cnt));
+  const float k_cos = (float)((double)w_cos / cnt);
+  const float* p = pred + (long long)b * 3 * hw;
+  const float* g = target + (long long)b * 3 * hw;
+  float* o = grad + (long long)b * 3 * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    float out[3] = {0.f, 0.f, 0.f};
+    if (mask[(long long)b * hw + i]) {
+      float pv[3], gv[3], pass[3], pc[3], gc[3], pass2[3];
+      float pn = 0.f, gn = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float raw = p[c * hw + i];
+        pass[c] = (!clamp_pred || (raw >= 0.f && raw <= 1.f)) ? 1.f : 0.f;      // torch.clamp backward: inclusive
+        pv[c] = clamp_pred ? fminf(fmaxf(raw, 0.f), 1.f) : raw;
+        gv[c] = g[c * hw + i];
+        const float t = 2.f * pv[c] - 1.f;
+        pass2[c] = (t >= -1.f && t <= 1.f) ? 1.f : 0.f;
+        pc[c] = fminf(fmaxf(t, -1.f), 1.f);
+        gc[c] = fminf(fmaxf(2.f * gv[c] - 1.f, -1.f), 1.f);
+        pn = fmaf(pc[c], pc[c], pn);
+        gn = fmaf(gc[c], gc[c], gn);
+      }
+      const float pl = __fsqrt_rn(pn), gl = __fsqrt_rn(gn);
+      const float pin = __fdiv_rn(1.f, fmaxf(pl, 1e-12f)), gin = __fdiv_rn(1.f, fmaxf(gl, 1e-12f));
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dot = fmaf(pc[c] * pin, gc[c] * gin, dot);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float d = pv[c] - gv[c];
+        const float s = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        // d(-<pn, gn>)/d pc = -(gn_c - <pn, gn> pn_c) / |pc|   (F.normalize backward; below eps the norm is clamped)
+        const float dcos = pl > 1e-12f ? -(gc[c] * gin - dot * pc[c] * pin) * pin : -(gc[c] * gin) * 1e12f;
+        out[c] = pass[c] * (k_l1 * s + k_cos * 2.f * pass2[c] * dcos);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c * hw + i] = out[c];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ virtual normal loss
 struct Vec3 { float x, y, z; };
 ODB_DEVINL Vec3 sub3(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
@@ -721,6 +773,21 @@ extern "C" int odb_midas_loss_bwd(const float* prediction, const float* target, 
                                                          grad);
   count_launch();
   return check_launch("midas_loss_bwd");
+}
+
+extern "C" int odb_normal_loss_bwd(const float* prediction, const float* target, const uint8_t* mask_valid, int32_t b,
+                                   int32_t h, int32_t w, int32_t clamp_prediction, float w_l1, float w_cos,
+                                   const double* fwd_workspace, float* grad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!prediction || !target || !mask_valid || !fwd_workspace || !grad || b < 1 || h < 1 || w < 1 ||
+      (long long)h * w > 0x7fffffffLL / 3 || b > 65535)
+    return fail(ODB_ERR_INVALID, "normal_loss_bwd: bad argument");
+  int gx = (h * w + 255) / 256;
+  if (gx > 64) gx = 64;
+  normal_loss_bwd_kernel<<<dim3(gx, b), 256, 0, stream>>>(prediction, target, mask_valid, fwd_workspace, b, h * w,
+                                                         clamp_prediction, w_l1, w_cos, grad);
+  count_launch();
+  return check_launch("normal_loss_bwd");
 }
 
 extern "C" int odb_vnl_loss_bwd(const float* first, const float* second, const int32_t* p1, const int32_t* p2,

@@ -4,7 +4,7 @@ Same constructor / call signatures as the reference modules (losses/midas_loss.p
 losses/virtual_normal_loss.py:7-27,151-194) and the loss mix of train_depth.py:261-279.  MidasLoss and VNL_Loss
 are differentiable with respect to the prediction (odb_midas_loss_bwd / odb_vnl_loss_bwd behind torch.autograd), so
 `depth_step_losses(...)["depth_loss"].backward()` yields d(loss)/d(depth_preds) — the first step of the train
-step's backward pass; the normal-loss pair is forward only.
+step's backward pass; so is the normal-training pair (odb_normal_loss_bwd).
 """
 from __future__ import annotations
 
@@ -164,23 +164,43 @@ def depth_step_losses(depth_preds, depth_gt, mask_float, midas: MidasLoss, vnl: 
     return {"ssi_loss": ssi, "reg_loss": reg, "vn_loss": vn, "depth_loss": ssi + 0.1 * reg + 10 * vn}
 
 
+class _NormalLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, preds, gt, mask_u8, clamp_preds):
+        p, g = _f32(preds, "normal_preds"), _f32(gt, "normal_gt")
+        b, _, h, w = p.shape
+        out = torch.empty(3, device=p.device, dtype=torch.float32)
+        ws = torch.empty(3 * b, device=p.device, dtype=torch.float64)
+        check(lib().odb_normal_loss_fwd(p.data_ptr(), g.data_ptr(), mask_u8.data_ptr(), b, h, w, 1 if clamp_preds else 0,
+                                        out.data_ptr(), ws.data_ptr(), _stream()), "odb_normal_loss_fwd")
+        ctx.save_for_backward(p, g, mask_u8, ws)
+        ctx.meta = (b, h, w, clamp_preds, preds.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, g, m, ws = ctx.saved_tensors
+        b, h, w, clamp_preds, dtype = ctx.meta
+        go = grad_out.detach().float().cpu()                          # (d/d total, d/d l1, d/d cos); total = cos + 10 l1
+        w_l1, w_cos = float(10.0 * go[0] + go[1]), float(go[0] + go[2])
+        grad = torch.empty_like(p)
+        check(lib().odb_normal_loss_bwd(p.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, 1 if clamp_preds else 0,
+                                        w_l1, w_cos, ws.data_ptr(), grad.data_ptr(), _stream()), "odb_normal_loss_bwd")
+        return grad.to(dtype), None, None, None
+
+
 def normal_losses(normal_preds: torch.Tensor, normal_gt: torch.Tensor, mask_valid: torch.Tensor,
                   clamp_preds: bool = False):
     """masked_l1_loss + masked_cosine_angular_loss (losses/masked_losses.py:4-7,14-23) in one pass.
     normal_preds, normal_gt: [B,3,H,W]; mask_valid: bool/uint8 [B,1,H,W] or the reference's
     `.repeat_interleave(3, 1)` form [B,3,H,W] (its first channel is used, as masked_cosine_angular_loss does).
-    Returns (cos + 10 * l1, l1, cos)."""
-    p, g = _f32(normal_preds, "normal_preds"), _f32(normal_gt, "normal_gt")
-    if p.dim() != 4 or p.shape[1] != 3 or g.shape != p.shape:
+    Returns (cos + 10 * l1, l1, cos); differentiable with respect to normal_preds."""
+    if not normal_preds.is_cuda or not mask_valid.is_cuda:
+        raise _capi.OdbError("normal_losses: CUDA tensors required (no CPU path)")
+    if normal_preds.dim() != 4 or normal_preds.shape[1] != 3 or normal_gt.shape != normal_preds.shape:
         raise _capi.OdbError("normal_losses: [B,3,H,W] tensors expected")
-    if not mask_valid.is_cuda:
-        raise _capi.OdbError("mask_valid: CUDA tensor required (no CPU path)")
     m = mask_valid[:, 0].to(torch.uint8).contiguous()
-    b, _, h, w = p.shape
-    out = torch.empty(3, device=p.device, dtype=torch.float32)
-    ws = torch.empty(3 * b, device=p.device, dtype=torch.float64)
-    check(lib().odb_normal_loss_fwd(p.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, 1 if clamp_preds else 0,
-                                    out.data_ptr(), ws.data_ptr(), _stream()), "odb_normal_loss_fwd")
+    out = _NormalLossFn.apply(normal_preds, normal_gt, m, bool(clamp_preds))
     return out[0], out[1], out[2]
 
 

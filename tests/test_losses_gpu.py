@@ -142,3 +142,20 @@ def test_vnl_loss_backward_and_train_step_gradient(lib_built, seed, batch):
     out["depth_loss"].backward()
     g = r.grad.cpu()
     assert float((g - r32.grad).norm() / r32.grad.norm()) <= 2e-4
+
+
+def test_normal_losses_backward(lib_built):
+    """odb_normal_loss_bwd against autograd of the oracle (== the reference functions, tests/test_losses_cpu.py)."""
+    from omnidata_b200 import losses
+    from oracle import loss_oracle
+    pred, gt, mf = loss_oracle.normal_loss_inputs(2, 2)
+    for weights in ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)):
+        p64 = pred.double().requires_grad_(True)
+        tot, l1, cos = loss_oracle.normal_step(p64, gt.double(), mf.double())
+        (weights[0] * tot + weights[1] * l1 + weights[2] * cos).backward()
+        ref = p64.grad.float()
+        p = pred.cuda().requires_grad_(True)
+        out = losses.normal_step_losses(p, gt.cuda(), mf.cuda())
+        (weights[0] * out["normal_loss"] + weights[1] * out["l1_loss"] + weights[2] * out["cos_loss"]).backward()
+        got = p.grad.cpu()
+        assert float((got - ref).norm() / ref.norm()) <= 1e-5, weights
