@@ -141,6 +141,24 @@ ODB_DEVINL void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, ui
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the two shared-memory descriptors given as their low words (start address >> 4 | LBO) plus the common
+// high word: small tiles (N = 32: 16 tensor-pipe cycles per instruction) are bound by how fast ONE thread can issue,
+// so the per-instruction descriptor arithmetic is kept to 32-bit adds.
+constexpr uint32_t kUmmaDescHiSw128 = 64u | (1u << 14) | (2u << 29);
+ODB_DEVINL uint32_t umma_desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+ODB_DEVINL void umma_bf16_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 // (implicitly performs tcgen05.fence::before_thread_sync).
 ODB_DEVINL void umma_commit(uint32_t bar) {

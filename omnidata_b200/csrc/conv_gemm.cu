@@ -367,6 +367,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       int stage = 0, astage = 0;
       uint32_t phase = 0, aphase = 0;
       uint32_t iter = 0;
+      uint32_t tap_off[9];                   // resident-weights halo kernel: tap shift in 16-byte descriptor units
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        tap_off[t] = Plan::kBResident
+                         ? static_cast<uint32_t>((p.tap_dy[t] + 1) * p.halo_w + (p.tap_dx[t] + 1)) * 8u : 0u;
       for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
         const uint32_t acc = iter & 1u;
         const uint32_t acc_phase = (iter >> 1) & 1u;
@@ -379,19 +384,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_wait(bres_bar, 0);
             tc_fence_after();
           }
+          // nine taps x four K steps per K block, fully unrolled: per instruction only 32-bit descriptor adds
+          const uint32_t b_tap_step = static_cast<uint32_t>(p.kb_per_tap) * (Plan::kBBytes >> 4);
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             mbar_wait(afull_bar(astage), aphase);
             tc_fence_after();
-            const uint32_t a_base = smem_base + Plan::kAOff + astage * a_stage_bytes;
-            for (int tap = 0; tap < p.num_taps; ++tap) {
-              const uint32_t a_addr =
-                  a_base + static_cast<uint32_t>((p.tap_dy[tap] + 1) * p.halo_w + (p.tap_dx[tap] + 1)) * 128u;
-              const uint64_t adesc = umma_desc_sw128(a_addr);
-              const uint64_t bdesc =
-                  umma_desc_sw128(smem_base + Plan::kBOff + (tap * p.kb_per_tap + kb) * Plan::kBBytes);
+            const uint32_t a_lo0 = umma_desc_lo_sw128(smem_base + Plan::kAOff + astage * a_stage_bytes);
+            const uint32_t b_lo0 = umma_desc_lo_sw128(smem_base + Plan::kBOff + kb * Plan::kBBytes);
+            const uint32_t first = kb != 0 ? 1u : 0u;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_lo = a_lo0 + tap_off[tap];
+              const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(tap) * b_tap_step;
 #pragma unroll
               for (int k = 0; k < kKBlock / 16; ++k)
-                umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+                umma_bf16_ss_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, idesc, (tap | k) != 0 ? 1u : first);
             }
             umma_commit(aempty_bar(astage));     // the halo stage is free when these 36 MMAs retire
             if (++astage == a_stages) { astage = 0; aphase ^= 1u; }
