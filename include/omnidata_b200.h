@@ -188,7 +188,8 @@ int odb_write_cls_row(void* tokens, const float* cls, const float* pos0, int32_t
 int odb_readout_cls_bias(const void* w, const float* bias, const void* tokens, float* out, int32_t b,
                          int32_t tokens_n, int32_t c, void* stream);
 
-/* ---- depth-training losses, FORWARD ONLY (train_depth.py:261-279); all tensors fp32 [b][h][w] ------- */
+/* ---- depth-training losses (train_depth.py:261-279), forward and (odb_*_bwd) backward with respect to the
+ * prediction; all tensors fp32 [b][h][w] ------- */
 
 /* make_valid_mask (train_depth.py:215-242): valid = nearest_upsample(max_pool2d(1 - mask, pool)) == 0. */
 int odb_make_valid_mask(const float* mask_float, uint8_t* mask_valid, int32_t b, int32_t h, int32_t w,
@@ -234,7 +235,7 @@ int odb_vnl_loss_bwd(const float* first, const float* second, const int32_t* p1,
  *   cos = masked_cosine_angular_loss(preds, target, mask x3)      (losses/masked_losses.py:14-23)
  *   out3 = (cos + 10 * l1, l1, cos).
  * prediction, target fp32 [b][3][h][w]; mask_valid uint8 [b][h][w] (odb_make_valid_mask); workspace: 3 * b doubles.
- * Forward only; deterministic (fixed-order fp64 partial sums). */
+ * Deterministic (fixed-order fp64 partial sums); backward: odb_normal_loss_bwd. */
 int odb_normal_loss_fwd(const float* prediction, const float* target, const uint8_t* mask_valid, int32_t b,
                         int32_t h, int32_t w, int32_t clamp_prediction, float* out3, double* workspace,
                         void* stream);

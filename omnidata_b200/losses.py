@@ -205,7 +205,7 @@ def normal_losses(normal_preds: torch.Tensor, normal_gt: torch.Tensor, mask_vali
 
 
 def normal_step_losses(normal_preds, normal_gt, mask_float):
-    """The loss arithmetic of train_normal.py:247-265 (forward only): clamp, make_valid_mask repeated over
+    """The loss arithmetic of train_normal.py:247-265 (differentiable w.r.t. normal_preds): clamp, make_valid_mask repeated over
     the three channels, l1 + cosine losses, normal_loss = cos + 10 * l1."""
     mask_valid = make_valid_mask(mask_float)
     total, l1, cos = normal_losses(normal_preds, normal_gt, mask_valid, clamp_preds=True)
