@@ -61,3 +61,16 @@ def test_reference_compose_equals_resize_crop_scale(task):
     if task == "depth":
         v = (v - 0.5) / 0.5
     assert torch.equal(t, v)
+
+
+def test_restated_pillow_resize_random_geometries():
+    """Seeded sweep over odd sizes / aspect ratios (incl. up-scaling from tiny images and panoramas)."""
+    rng = np.random.RandomState(7)
+    sizes = [(int(rng.randint(40, 900)), int(rng.randint(40, 900))) for _ in range(10)] + [(2000, 97), (61, 1500)]
+    for w, h in sizes:
+        img = io_.synthetic_image(w, h, seed=w * 31 + h)
+        nw, nh = ip.resized_size(w, h, 384)
+        ref = img.resize((nw, nh), Image.BILINEAR)
+        left, top = ip.center_crop_offset(nw, 384), ip.center_crop_offset(nh, 384)
+        ref = np.asarray(ref.crop((left, top, left + 384, top + 384)))
+        assert np.array_equal(emulate(np.asarray(img)), ref), (w, h)
