@@ -100,3 +100,28 @@ def test_plain_vit_state_dict_layout_is_the_reference_layout(backbone, golden):
     if reference_loader.reference_available():
         ref = reference_loader.load_reference_dpt(1, backbone)
         assert [[k, list(v.shape)] for k, v in ref.state_dict().items()] == spec
+
+
+def test_every_host_module_refuses_cpu_tensors():
+    """No CPU / eager fallback anywhere: the host mirrors raise instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    from omnidata_b200 import imageproc, losses, optim, refocus
+    from omnidata_b200._capi import OdbError
+    with pytest.raises(OdbError):
+        optim.FlatAdam(torch.zeros(8))
+    with pytest.raises(OdbError):
+        imageproc.bicubic_resize(torch.zeros(1, 4, 4), (8, 8))
+    with pytest.raises(OdbError):
+        imageproc.to_uint8_hwc(torch.zeros(3, 4, 4))
+    with pytest.raises(OdbError):
+        losses.MidasLoss()(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8), torch.ones(1, 1, 8, 8, dtype=torch.bool))
+    with pytest.raises(OdbError):
+        losses.VNL_Loss(1.0, 1.0, (8, 8))(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+    with pytest.raises(OdbError):
+        losses.normal_losses(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, 8, 8), torch.ones(1, 1, 8, 8, dtype=torch.bool))
+    with pytest.raises(OdbError):
+        refocus.compute_quantiles(torch.zeros(1, 1, 8, 8), 4)
+    with pytest.raises((OdbError, RuntimeError, AssertionError)):
+        imageproc.DevicePreprocessor("depth")(np.zeros((8, 8, 3), dtype=np.uint8))
