@@ -52,3 +52,40 @@ def test_ctypes_structs_match_the_header(tmp_path):
         assert getattr(mirrors[struct], field).offset == int(off), key
         checked += 1
     assert checked == len(_capi.View._fields_) + len(_capi.ConvGemmDesc._fields_)
+
+
+def test_ctypes_signatures_have_the_headers_arity_and_scalar_kinds():
+    """Every prototype of include/omnidata_b200.h against its ctypes signature: same number of parameters, and
+    pointer / 32-bit / 64-bit / float / double kinds in the same positions."""
+    import ctypes as C
+    import re
+    from omnidata_b200 import _capi
+    text = (ROOT / "include" / "omnidata_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char\*)\s+(odb_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 30
+    kind_of = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int32: "i32", C.c_int: "i32", C.c_int64: "i64",
+               C.c_float: "f32", C.c_double: "f64"}
+    seen = set()
+    for name, params in protos:
+        seen.add(name)
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        res, args = _capi._SIGNATURES[name]
+        assert len(args) == len(plist), (name, len(args), len(plist))
+        for p, a in zip(plist, args):
+            if "*" in p:
+                want = "ptr"
+            elif p.startswith("int64_t"):
+                want = "i64"
+            elif p.startswith("int32_t") or p.startswith("int "):
+                want = "i32"
+            elif p.startswith("float"):
+                want = "f32"
+            elif p.startswith("double"):
+                want = "f64"
+            else:
+                raise AssertionError(f"{name}: unparsed parameter {p!r}")
+            have = "ptr" if isinstance(a, type) and issubclass(a, C._Pointer) else kind_of[a]
+            assert have == want, (name, p, a)
+    assert seen == set(_capi._SIGNATURES), seen ^ set(_capi._SIGNATURES)
