@@ -11,6 +11,8 @@
  *   - all pointers are DEVICE pointers unless the name says host; no torch types cross this ABI;
  *   - activations are channels-last (NHWC / token-major) bf16 unless stated; strides are in
  *     ELEMENTS, the channel stride is always 1;
+ *   - an `int32_t dtype` (or x_dtype / y_dtype) parameter is an odb_dtype naming the storage type of the
+ *     activation tensors of that call (bf16 in production, fp32 in the correctness mode);
  *   - every function only enqueues work on `stream` (a cudaStream_t passed as void*); nothing
  *     allocates, synchronises or touches the host heap — safe under CUDA-graph capture;
  *   - return value: 0 on success, a negative odb_status otherwise; odb_last_error() returns a
@@ -26,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ODB_ABI_VERSION 2
+#define ODB_ABI_VERSION 3
 
 typedef enum odb_status {
   ODB_OK = 0,
@@ -37,7 +39,13 @@ typedef enum odb_status {
 
 typedef enum odb_act { ODB_ACT_NONE = 0, ODB_ACT_RELU = 1, ODB_ACT_GELU = 2 } odb_act;
 
-/* A strided channels-last view [b][h][w][c] over bf16 storage. */
+/* Storage type of an activation tensor.  bf16 is the production format; fp32 carries the ViT residual stream
+ * (the reference adds every block's output to an fp32 stream: timm Block.forward `x = x + ...`) and every
+ * activation of the fp32 correctness mode (the reference itself is fp32-only). */
+typedef enum odb_dtype { ODB_DTYPE_BF16 = 0, ODB_DTYPE_F32 = 1 } odb_dtype;
+
+/* A strided channels-last view [b][h][w][c] (bf16 storage unless the owning descriptor says fp32; strides in
+ * elements of the storage type). */
 typedef struct odb_view {
   const void* ptr;
   int32_t c, w, h, b;
@@ -96,9 +104,10 @@ typedef struct odb_conv_gemm_desc {
   int32_t head_relu;
   float* head_out;
   /* Fused GroupNorm statistics (timm GroupNormAct after every StdConv2dSame): when gn_partial != NULL
-   * each epilogue warp also writes, for the bf16 values it stores, the per-group (sum, sum of squares)
+   * each epilogue warp also writes, for the rows it owns, the per-group (sum, sum of squares)
    * of its 32 rows to  gn_partial[b][ty*tiles_x+tx][quadrant 0..3][group][2]  (fp32, every entry is
-   * written exactly once: no atomics, deterministic).  odb_groupnorm_finalize reduces them. */
+   * written exactly once: no atomics, deterministic).  The sums are taken over the UNROUNDED fp32 accumulators
+   * (timm GroupNormAct normalises the fp32 conv output), not over the stored bf16 values.  odb_groupnorm_finalize reduces them. */
   float* gn_partial;
   int32_t gn_groups;
   /* Epilogue code path: 0 = auto (a specialised straight-line epilogue — TMEM read of the next 64-column
@@ -106,6 +115,14 @@ typedef struct odb_conv_gemm_desc {
    * bias[+relu|+gelu] or bias+residual with a plain strided residual; the generic epilogue otherwise),
    * -1 = always the generic epilogue.  Both produce bit-identical results. */
   int32_t epilogue;
+  /* Storage types (odb_dtype).  in_dtype: views + weight.  out_dtype: out, out2, residual.
+   *   (BF16, BF16)  the tcgen05 tensor-core path described above;
+   *   (BF16, F32)   tensor-core path with an fp32 epilogue: out = residual + (acc + bias), residual and out fp32
+   *                 (requires bias and residual, no act / out2 / gn / head): the ViT residual stream;
+   *   (F32,  F32)   fp32 correctness mode: the same contraction on the FP32 FMA pipe (weight fp32 [n][taps*C]),
+   *                 partial sums combined in fp64; bias / act / residual / out2 as above, no gn_partial / head. */
+  int32_t in_dtype;
+  int32_t out_dtype;
 } odb_conv_gemm_desc;
 
 int odb_conv_gemm(const odb_conv_gemm_desc* desc, void* stream);
@@ -116,7 +133,7 @@ int odb_conv_gemm_plan(const odb_conv_gemm_desc* desc, int32_t* out4);
 /* LayerNorm over the last dim (timm Block.norm1/norm2, eps 1e-6): y = (x-mean)/sqrt(var+eps)*g + b.
  * x, y bf16 [rows][cols] (cols multiple of 256, <= 1024); gamma/beta fp32. */
 int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
-                  int32_t cols, float eps, void* stream);
+                  int32_t cols, float eps, int32_t x_dtype, int32_t y_dtype, void* stream);
 
 /* Fused multi-head attention (timm Attention.forward): qkv bf16 [b][tokens][3][heads][64] as written
  * by the qkv linear; out bf16 [b][tokens][heads*64]; softmax(q k^T * scale) v.  tcgen05 kernel:
@@ -124,14 +141,16 @@ int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y,
  * for the PV product, fp32 row sum of the unrounded P.  tokens <= 640. */
 int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
                   void* stream);
-/* Same contract and arithmetic as odb_attention, organised as two independent groups per CTA working
- * on alternate query tiles ("ping-pong", 64-key blocks) to hide the MMA <-> softmax hand-off latency. */
-int odb_attention_pp(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
-                     void* stream);
-/* Same contract on the legacy mma.sync path (flash-style online softmax over 64-key chunks); kept
- * for A/B comparison only. */
-int odb_attention_mma(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
+/* fp32 correctness mode of odb_attention: qkv fp32 [b][tokens][3][heads][64], out fp32 [b][tokens][heads*64];
+ * dot products and the PV sum in fp64, exp / division exact (no fast-math). */
+int odb_attention_f32(const float* qkv, float* out, int32_t b, int32_t tokens, int32_t heads, float scale,
                       void* stream);
+
+/* fp32 correctness mode of the DPT head tail (M/dpt_depth.py:95-97; the tensor-core path fuses this into
+ * odb_conv_gemm's head epilogue): x fp32 [b][h][w][32] = relu(conv3x3 + bias), out[b][k][y][x] = relu?(bias[k] +
+ * sum_j w[k][j] x[..j]) fp32 NCHW; `pre` (optional) receives the value before the final ReLU. */
+int odb_head_tail_f32(const float* x, const float* w, const float* bias, float* out, float* pre, int32_t b,
+                      int32_t h, int32_t wd, int32_t head_c, int32_t relu, void* stream);
 
 /* GroupNorm statistics (timm GroupNormAct, 32 groups), deterministic (no floating-point atomics):
  * stats fp32 [b][groups][2] = (mean, 1/sqrt(var + eps)) over x bf16 [b][hw][c], biased variance,
@@ -140,7 +159,7 @@ int odb_attention_mma(const void* qkv, void* out, int32_t b, int32_t tokens, int
  * kernel leaves it zeroed); it may be shared by successive calls on one stream. */
 int64_t odb_groupnorm_scratch_bytes(int32_t b, int32_t hw, int32_t c, int32_t groups);
 int odb_groupnorm_stats(const void* x, float* stats, void* scratch, int64_t scratch_bytes, int32_t b,
-                        int32_t hw, int32_t c, int32_t groups, float eps, void* stream);
+                        int32_t hw, int32_t c, int32_t groups, float eps, int32_t dtype, void* stream);
 
 /* Reduce the partial sums written by odb_conv_gemm (gn_partial) in a fixed order with fp64
  * combination: stats[b][g] = (mean, 1/sqrt(var + eps)); rows_per_image = tiles_x * tiles_y * 4,
@@ -154,39 +173,44 @@ int odb_groupnorm_finalize(const float* partial, float* stats, int32_t b, int32_
 int odb_groupnorm_apply(const void* x, const float* stats, const float* gamma, const float* beta,
                         const void* res, const float* res_stats, const float* res_gamma,
                         const float* res_beta, void* y, int32_t b, int32_t hw, int32_t c,
-                        int32_t groups, int32_t relu, void* stream);
+                        int32_t groups, int32_t relu, int32_t dtype, void* stream);
 
 /* Stem tail (timm ResNetV2 stem.norm + stem.pool): GroupNorm+ReLU then MaxPool 3x3 stride 2 with
  * TF-SAME padding (0,1).  x bf16 [b][h][w][c] -> y bf16 [b][h/2][w/2][c]. */
 int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const float* gamma,
                              const float* beta, void* y, int32_t b, int32_t h, int32_t w, int32_t c,
-                             int32_t groups, void* stream);
+                             int32_t groups, int32_t dtype, void* stream);
 
 /* im2col for the 7x7 stride-2 TF-SAME stem conv (timm StdConv2dSame 3->64): x fp32 NCHW
  * [b][3][h][w] -> cols bf16 [b*(h/2)*(w/2)][kpad], column (ky*7+kx)*3+ch, zero padded. */
 int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h, int32_t w, int32_t kpad,
-                    void* stream);
+                    int32_t dtype, void* stream);
 
 /* Bilinear x2 upsampling, align_corners=True (M/blocks.py:335-337, M/dpt_depth.py:93), fused with
  * the skip add of the next fusion block (M/blocks.py:330): out = up2(z) + res; out_relu = relu(out).
  * z bf16 [b][h][w][c]; res/out/out_relu bf16 [b][2h][2w][c]; res and out_relu may be NULL. */
 int odb_upsample2x_add(const void* z, const void* res, void* out, void* out_relu, int32_t b,
-                       int32_t h, int32_t w, int32_t c, void* stream);
+                       int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream);
 
 /* Patch embedding gather of the plain ViT backbones (DPT-Large `vitl16_384`, `vitb16_384`; timm PatchEmbed =
  * Conv2d(3, D, patch, stride patch), applied at M/vit.py:131): x fp32 NCHW [b][3][h][w] ->
  * cols bf16 [b * (h/patch) * (w/patch)][3 * patch * patch], column (c * patch + py) * patch + px = the row-major
  * flattening of the conv weight, so the embedding is one odb_conv_gemm. */
-int odb_patchify(const float* x, void* cols, int32_t b, int32_t h, int32_t w, int32_t patch, void* stream);
+int odb_patchify(const float* x, void* cols, int32_t b, int32_t h, int32_t w, int32_t patch, int32_t dtype,
+                 void* stream);
 
 /* tokens[b][0][:] = cls + pos[0]  (M/vit.py:135-147); tokens bf16 [b][tokens][c]; cls, pos0 fp32 [c]. */
 int odb_write_cls_row(void* tokens, const float* cls, const float* pos0, int32_t b, int32_t tokens_n,
-                      int32_t c, void* stream);
+                      int32_t c, int32_t dtype, void* stream);
 
 /* ProjectReadout cls term (M/vit.py:43-47): out[b][n] = bias[n] + sum_k w[n][c + k] * tokens[b][0][k]
  * w bf16 [c][2c] (the Linear(2c, c) weight), tokens bf16 [b][tokens][c], out fp32 [b][c]. */
 int odb_readout_cls_bias(const void* w, const float* bias, const void* tokens, float* out, int32_t b,
-                         int32_t tokens_n, int32_t c, void* stream);
+                         int32_t tokens_n, int32_t c, int32_t dtype, void* stream);
+
+/* dst bf16[n] = round(src fp32[n]) (n a multiple of 8): the hooked ViT activations (M/vit.py:158-165 `get_activation`)
+ * leave the fp32 residual stream as bf16 operands of the readout GEMM. */
+int odb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /* ---- depth-training losses (train_depth.py:261-279), forward and (odb_*_bwd) backward with respect to the
  * prediction; all tensors fp32 [b][h][w] ------- */

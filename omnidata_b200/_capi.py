@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libomnidata_b200.so"
 ODB_MAX_VIEWS = 4
 ODB_MAX_TAPS = 9
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+DTYPE_BF16, DTYPE_F32 = 0, 1
 
 
 class OdbError(RuntimeError):
@@ -56,6 +57,8 @@ class ConvGemmDesc(C.Structure):
         ("gn_partial", C.c_void_p),
         ("gn_groups", C.c_int32),
         ("epilogue", C.c_int32),
+        ("in_dtype", C.c_int32),
+        ("out_dtype", C.c_int32),
     ]
 
 
@@ -65,24 +68,25 @@ _SIGNATURES = {
     "odb_groupnorm_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                          C.c_float, C.c_void_p]),
     "odb_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
-                                C.c_float, C.c_void_p]),
+                                C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "odb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p]),
-    "odb_attention_pp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
-                                   C.c_void_p]),
-    "odb_attention_mma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+    "odb_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_void_p]),
+    "odb_head_tail_f32": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]),
     "odb_groupnorm_scratch_bytes": (C.c_int64, [C.c_int32] * 4),
     "odb_groupnorm_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
-                                      C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
-    "odb_groupnorm_apply": (C.c_int, [C.c_void_p] * 9 + [C.c_int32] * 5 + [C.c_void_p]),
-    "odb_stem_gn_relu_maxpool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]),
-    "odb_stem_im2col": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "odb_groupnorm_apply": (C.c_int, [C.c_void_p] * 9 + [C.c_int32] * 6 + [C.c_void_p]),
+    "odb_stem_gn_relu_maxpool": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 6 + [C.c_void_p]),
+    "odb_stem_im2col": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_void_p]),
-    "odb_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
-    "odb_upsample2x_add": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
-    "odb_write_cls_row": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p]),
-    "odb_readout_cls_bias": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
+    "odb_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_void_p]),
+    "odb_upsample2x_add": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_void_p]),
+    "odb_write_cls_row": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p]),
+    "odb_readout_cls_bias": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
+    "odb_cast_f32_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "odb_make_valid_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "odb_midas_loss_workspace_bytes": (C.c_int64, [C.c_int32]),
     "odb_midas_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
@@ -120,7 +124,7 @@ _SIGNATURES = {
     "odb_debug_conv_trace": (C.c_int, [C.c_void_p]),
 }
 
-ABI_VERSION = 2        # include/omnidata_b200.h: ODB_ABI_VERSION (descriptor layouts this module mirrors)
+ABI_VERSION = 3        # include/omnidata_b200.h: ODB_ABI_VERSION (descriptor layouts this module mirrors)
 
 _lib = None
 

@@ -15,14 +15,17 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libomnidata_b200.so"
-SOURCES = ["api.cu", "conv_gemm.cu", "ops.cu", "attention.cu", "attention_tc.cu", "attention_tc2.cu", "loss.cu",
+SOURCES = ["api.cu", "conv_gemm.cu", "ops.cu", "attention_tc.cu", "fp32_path.cu", "loss.cu",
            "imageproc.cu", "optim.cu", "refocus.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
-    "--use_fast_math",
 ]
+# fast-math (approximate division / sqrt / exp, denormals flushed) only where the arithmetic is bf16-bound anyway:
+# the tensor-core GEMM / attention epilogues and the bf16 elementwise kernels.  The fp32 losses, the optimizer, the
+# fp32 correctness mode, image resampling and the refocus blur promise reference fp32 arithmetic and are built without.
+FAST_MATH_SOURCES = {"conv_gemm.cu", "ops.cu", "attention_tc.cu"}
 
 
 def _nvcc() -> str:
@@ -39,7 +42,7 @@ def _stamp() -> str:
         if f.is_file():
             h.update(f.name.encode())
             h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + sorted(FAST_MATH_SOURCES)).encode())
     return h.hexdigest()
 
 
@@ -57,7 +60,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         if not (CSRC / src).exists():
             continue
         obj = obj_dir / (src + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["--use_fast_math"] if src in FAST_MATH_SOURCES else []), "-c", str(CSRC / src),
+               "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

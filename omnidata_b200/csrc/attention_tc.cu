@@ -335,12 +335,13 @@ extern "C" int odb_attention(const void* qkv, void* out, int32_t b, int32_t toke
   p.tokens = tokens; p.heads = heads; p.batch = b;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.trace = debug_trace();
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev_ = current_device();
+  if (!configured[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kTcSmemBytes);
     if (e != cudaSuccess) return fail_cuda(e, "attention: cudaFuncSetAttribute");
-    configured = true;
+    configured[dev_] = true;
   }
   const int units = b * heads;
   const int grid = units < num_sms() ? units : num_sms();

@@ -13,8 +13,6 @@
 // 128-byte rows with the 128B swizzle, i.e. directly in the canonical K-major UMMA layout.
 //
 // What this replaces in the reference is listed in include/omnidata_b200.h (odb_conv_gemm).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/omnidata_b200.h"
@@ -85,7 +83,11 @@ ODB_DEVINL unsigned long long global_ns() {
 // convolutions: ~4x fewer instructions per 64-column chunk, the TMEM read of chunk c+1 in flight
 // while chunk c is processed, and (EPI_BIAS_RES) the residual fetched by TMA into the output
 // staging slot a few chunks ahead instead of 1024 scattered 16-byte loads per chunk.
-enum : int { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_GELU = 3, EPI_BIAS_RES = 4, EPI_GN = 5 };
+// EPI_BIAS_RES_F32: fp32 residual in, fp32 out (the ViT residual stream: attn.proj / mlp.fc2 / patch proj).  A
+// 64-column chunk is two 128-row x 32-fp32 TMA boxes (128-byte swizzled rows), one per epilogue warp half, so a
+// chunk occupies TWO 16 KiB staging units.
+enum : int { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_GELU = 3, EPI_BIAS_RES = 4, EPI_GN = 5,
+             EPI_BIAS_RES_F32 = 6 };
 
 // ---- GroupNorm partial statistics of one epilogue warp (32 rows x 32 columns of a tile):
 // per-thread group sums over its row, then a transposing butterfly over the 32 lanes: V values are
@@ -189,6 +191,7 @@ template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR, bool HALO
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   static_assert(EPI == EPI_GENERIC || (!HEAD && !HALO && NSTAGING >= 2), "fast epilogues: plain tiles only");
+  static_assert(EPI != EPI_BIAS_RES_F32 || NSTAGING >= 4, "fp32 epilogue: two staging slots of two 16 KiB units");
   using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR, HALO, HEAD>;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
@@ -230,7 +233,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int a = 0; a < 4; ++a) mbar_init(rfull_bar(a), 1);
     mbar_init(bres_bar, 1);
     mbar_fence_init();
-    if (EPI == EPI_BIAS_RES) tma_prefetch_desc(&p.res_map);
+    if (EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES_F32) tma_prefetch_desc(&p.res_map);
     for (int v = 0; v < ODB_MAX_VIEWS; ++v) tma_prefetch_desc(&p.a_map[v]);
     tma_prefetch_desc(&p.b_map);
     if (!HEAD) tma_prefetch_desc(&p.out_map);
@@ -469,8 +472,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if constexpr (EPI != EPI_GENERIC) {
       // ---------------------------------------------------------- specialised epilogues
       constexpr int kChunks = BLOCK_N / 64;
-      constexpr int NS = NSTAGING;      // staging slots of one 128 x 64 chunk each
-      constexpr int D = NS / 2;         // residual prefetch distance in chunks
+      constexpr bool F32 = (EPI == EPI_BIAS_RES_F32);
+      constexpr bool RES = (EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES_F32);
+      constexpr int kSlotBytes = F32 ? 2 * kStagingBytes : kStagingBytes;
+      constexpr int NS = F32 ? NSTAGING / 2 : NSTAGING;   // staging slots of one 128 x 64 chunk each
+      constexpr int D = NS >= 4 ? NS / 2 : (NS >= 2 ? NS - 1 : 0);   // residual prefetch distance in chunks
+      static_assert(!RES || NS >= 2, "residual epilogues need two staging slots");
       const int cofs = half * 32;
       const uint32_t tempty0 = PAIR ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
       const uint32_t tempty1 = PAIR ? mapa_shared(tempty_bar(1), 0) : tempty_bar(1);
@@ -484,14 +491,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           int tn, tx, ty, tb;
           decode(ld_tile, tn, tx, ty, tb);
           const uint32_t slot = ld_g % NS;
-          mbar_expect_tx(rfull_bar(slot), a_bytes);
-          tma_load_4d(smem_base + Plan::kCOff + slot * kStagingBytes, &p.res_map, rfull_bar(slot),
+          mbar_expect_tx(rfull_bar(slot), F32 ? 2u * a_bytes : a_bytes);
+          tma_load_4d(smem_base + Plan::kCOff + slot * kSlotBytes, &p.res_map, rfull_bar(slot),
                       tn * BLOCK_N + ld_c * 64, tx * p.tile_w, ty * p.tile_h, tb);
+          if constexpr (F32)
+            tma_load_4d(smem_base + Plan::kCOff + slot * kSlotBytes + kStagingBytes, &p.res_map, rfull_bar(slot),
+                        tn * BLOCK_N + ld_c * 64 + 32, tx * p.tile_w, ty * p.tile_h, tb);
           ++ld_g;
           if (++ld_c == kChunks) { ld_c = 0; ld_tile += unit_stride; }
         }
       };
-      if (EPI == EPI_BIAS_RES && store_leader) {
+      if (RES && store_leader) {
         for (int i = 0; i < D; ++i) issue_res_load();
       }
       uint32_t iter = 0;
@@ -550,7 +560,22 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           const uint32_t slot = g % NS;
-          const uint32_t buf = smem_base + Plan::kCOff + slot * kStagingBytes;
+          const uint32_t buf = smem_base + Plan::kCOff + slot * kSlotBytes;
+          if constexpr (F32) {
+            // fp32 residual + fp32 result: this warp half owns the 32-column (128-byte) sub-tile `half` of the slot
+            mbar_wait(rfull_bar(slot), (g / NS) & 1u);
+            const uint32_t sub = buf + static_cast<uint32_t>(half) * kStagingBytes + rowoff;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t addr = sub + (static_cast<uint32_t>(j ^ (row & 7)) << 4);
+              float q0, q1, q2, q3;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(q0), "=f"(q1), "=f"(q2), "=f"(q3) : "r"(addr) : "memory");
+              q0 += v[4 * j + 0]; q1 += v[4 * j + 1]; q2 += v[4 * j + 2]; q3 += v[4 * j + 3];
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(q0), "f"(q1), "f"(q2), "f"(q3)
+                           : "memory");
+            }
+          } else {
           if constexpr (EPI == EPI_BIAS_RES) {
             // the residual rows of this chunk were TMA-loaded into the staging slot (same swizzled
             // layout as the output): read own 64 bytes, add, write the result back in place
@@ -579,15 +604,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                          : "memory");
           }
           if constexpr (EPI == EPI_GN) {
-            // fused GroupNorm statistics over the bf16-rounded values just staged (same order of
-            // operations as the generic epilogue: bit-identical partial sums)
+            // fused GroupNorm statistics over the UNROUNDED fp32 accumulators (the reference normalises the fp32
+            // conv output: timm GroupNormAct after StdConv2dSame); same order of operations as the generic
+            // epilogue: bit-identical partial sums
             float rq[32];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 t2 = unpack_bf16x2(packed[j]);
-              rq[2 * j] = valid ? t2.x : 0.f;
-              rq[2 * j + 1] = valid ? t2.y : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) rq[j] = valid ? v[j] : 0.f;
             if (tb < p.out_b) {
               const int cpg = p.gn_cpg;
               float* dst = p.gn_partial +
@@ -600,16 +622,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               else gn_warp_partials<32>(rq, lane, dst);
             }
           }
+          }  // !F32
           fence_proxy_async_smem();
           // slot reuse without a residual: the store of chunk g+1-NS must have read its slot before any
           // thread passes this barrier and starts writing chunk g+1 (with a residual the TMA load of
           // chunk g+1, issued after that store was read, orders it)
-          if (EPI != EPI_BIAS_RES && store_leader) tma_store_wait_read<NS - 2>();
+          if (!RES && store_leader) tma_store_wait_read<(NS >= 2 ? NS - 2 : 0)>();
           named_bar_sync(1, kEpiThreads);
           if (store_leader) {
             tma_store_4d(&p.out_map, buf, n0 + c * 64, x0, y0, tb);
+            if constexpr (F32) tma_store_4d(&p.out_map, buf + kStagingBytes, n0 + c * 64 + 32, x0, y0, tb);
             tma_store_commit();
-            if constexpr (EPI == EPI_BIAS_RES) {
+            if constexpr (RES) {
               tma_store_wait_read<NS - D>();     // the store of chunk g+D-NS has read its slot
               issue_res_load();                  // residual of chunk g+D -> that slot
             }
@@ -747,15 +771,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             v[2 * j + 1] += rr.y;
             packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
-          // ---- fused GroupNorm statistics over the bf16-rounded values this warp is about to store
+          // ---- fused GroupNorm statistics over the unrounded fp32 values (before the bf16 store)
           if (p.gn_partial != nullptr) {
             float rq[32];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 t2 = unpack_bf16x2(packed[j]);
-              rq[2 * j] = valid ? t2.x : 0.f;
-              rq[2 * j + 1] = valid ? t2.y : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) rq[j] = valid ? v[j] : 0.f;
             if (tb < p.out_b) {
               const int cpg = p.gn_cpg;
               float* dst = p.gn_partial +
@@ -832,11 +852,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 // ------------------------------------------------------------------------------------------ host
 
 static int encode_view_map(CUtensorMap* map, const odb_view& v, int box_c, int box_w, int box_h,
-                           CUtensorMapSwizzle swz) {
+                           CUtensorMapSwizzle swz, bool f32 = false) {
   if (v.ptr == nullptr) return fail(ODB_ERR_INVALID, "conv_gemm: null view pointer");
   if ((reinterpret_cast<uintptr_t>(v.ptr) & 15u) != 0)
     return fail(ODB_ERR_INVALID, "conv_gemm: view pointer must be 16-byte aligned");
   if (v.c % 8 != 0) return fail(ODB_ERR_INVALID, "conv_gemm: channel count must be a multiple of 8");
+  const int esz = f32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.b};
   // strides of dims 1..3 in bytes; a unit extent may carry any (16B-multiple) stride
   long long sx = v.sx, sy = v.sy, sb = v.sb;
@@ -845,23 +866,24 @@ static int encode_view_map(CUtensorMap* map, const odb_view& v, int box_c, int b
   if (v.b == 1 && sb == 0) sb = (long long)v.h * sy;
   if (sx % 8 != 0 || sy % 8 != 0 || sb % 8 != 0 || sx <= 0 || sy <= 0 || sb <= 0)
     return fail(ODB_ERR_INVALID, "conv_gemm: view strides must be positive multiples of 8 elements");
-  cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sb * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)sx * esz, (cuuint64_t)sy * esz, (cuuint64_t)sb * esz};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  return encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims,
-                      strides, box, estr, swz);
+  return encode_tiled(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                      const_cast<void*>(v.ptr), dims, strides, box, estr, swz);
 }
 
 template <int BLOCK_N, int STAGES, int NSTAGING, bool HEAD, bool PAIR, bool HALO, int EPI = EPI_GENERIC>
 static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_t stream) {
   using Plan = SmemPlan<BLOCK_N, STAGES, NSTAGING, PAIR, HALO, HEAD>;
   auto kernel = conv_gemm_kernel<BLOCK_N, STAGES, NSTAGING, HEAD, PAIR, HALO, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};      // the opt-in is per device
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e =
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kTotal);
     if (e != cudaSuccess) return fail_cuda(e, "conv_gemm: cudaFuncSetAttribute");
-    configured = true;
+    configured[dev] = true;
   }
   const int sms = num_sms();
   cudaLaunchConfig_t cfg;
@@ -895,20 +917,25 @@ static int launch_instance(const ConvGemmParams& p, long long units, cudaStream_
 template <int EPI>
 static int launch_fast(const ConvGemmParams& p, int block_n, bool pair, long long m_tiles, long long total,
                        cudaStream_t stream) {
+  if constexpr (EPI == EPI_BIAS_RES_F32) {
+    // fp32 residual stream: a chunk needs two 16 KiB staging units; the pair kernel keeps three slots so that the
+    // residual TMA load still runs two chunks ahead of its use
+    if (pair && block_n == 128)
+      return launch_instance<128, 6, 4, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
+    if (pair) return launch_instance<256, 4, 6, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
+    switch (block_n) {
+      case 256: return launch_instance<256, 3, 4, false, false, false, EPI>(p, total, stream);
+      case 128: return launch_instance<128, 5, 4, false, false, false, EPI>(p, total, stream);
+      default: return launch_instance<64, 6, 4, false, false, false, EPI>(p, total, stream);
+    }
+  } else {
   if (pair && block_n == 128)
     return launch_instance<128, 6, 4, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
   if (pair) {
     // the residual variant trades one of the six operand stages for two more staging slots, so that
     // the residual TMA load runs two chunks ahead of its use (measured: see DESIGN.md)
-    static int res_stages = -1;
-    if (res_stages < 0) {
-      const char* e = getenv("ODB_PAIR_RES_STAGES");
-      res_stages = (e != nullptr && e[0] == '6') ? 6 : 5;
-    }
-    if constexpr (EPI == EPI_BIAS_RES) {
-      if (res_stages == 5)
-        return launch_instance<256, 5, 4, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
-    }
+    if constexpr (EPI == EPI_BIAS_RES)
+      return launch_instance<256, 5, 4, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
     return launch_instance<256, 6, 2, false, true, false, EPI>(p, ((m_tiles + 1) / 2) * p.tiles_n, stream);
   }
   switch (block_n) {
@@ -916,36 +943,12 @@ static int launch_fast(const ConvGemmParams& p, int block_n, bool pair, long lon
     case 128: return launch_instance<128, 5, 4, false, false, false, EPI>(p, total, stream);
     default: return launch_instance<64, 6, 4, false, false, false, EPI>(p, total, stream);
   }
-}
-
-static bool halo_head_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ODB_HALO_HEAD");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  return v == 1;
-}
-
-static bool pair128_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ODB_PAIR128");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-static bool fast_epilogues_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ODB_EPI_FAST");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
 }
 
 }  // namespace odb
+
+namespace odb { int conv_gemm_f32(const odb_conv_gemm_desc* d, cudaStream_t stream); }   // fp32_path.cu
 
 using namespace odb;
 
@@ -993,8 +996,7 @@ static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
     // automatic only for the head tail (resident weights: 3x faster there); for the other layers the
     // deeper per-tap ring measured faster
     halo = is_canonical_3x3(d) && (tw <= 0 || th <= 0) &&
-           (d->n <= kHaloAutoMaxN || (d->head_out != nullptr && d->num_taps * ((d->views[0].c + 63) / 64) <= kResidentBTiles &&
-                                      halo_head_enabled()));
+           (d->n <= kHaloAutoMaxN || (d->head_out != nullptr && d->num_taps * ((d->views[0].c + 63) / 64) <= kResidentBTiles));
   }
   if (halo && (tw <= 0 || th <= 0)) {
     if (ow <= 126) { tw = ow; th = 130 / (ow + 2); if (th > oh) th = oh; }
@@ -1044,7 +1046,7 @@ static int make_plan(const odb_conv_gemm_desc* d, HostPlan* hp) {
   else if (d->cta_pair == 0)
     pair = !head && hp->m_tiles * (N / block_n) >= 2LL * num_sms() &&
            (block_n == 256 ||
-            (block_n == 128 && !halo && (long long)d->num_taps * C >= 1024 && pair128_enabled()));
+            (block_n == 128 && !halo && (long long)d->num_taps * C >= 1024));
   if (pair && (!(block_n == 256 || (block_n == 128 && !halo)) || head))
     return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: cta_pair needs block_n 256 (or 128 without halo) and no head tail");
   hp->block_n = block_n; hp->pair = pair; hp->head = head;
@@ -1064,6 +1066,7 @@ extern "C" int odb_conv_gemm_plan(const odb_conv_gemm_desc* d, int32_t* out4) {
 
 extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (d != nullptr && d->in_dtype == ODB_DTYPE_F32) return conv_gemm_f32(d, stream);   // fp32 correctness mode
   HostPlan hp;
   int rc = make_plan(d, &hp);
   if (rc) return rc;
@@ -1111,6 +1114,25 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
                       dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  const bool out_f32 = d->out_dtype == ODB_DTYPE_F32;
+  if (d->in_dtype != ODB_DTYPE_BF16) return fail(ODB_ERR_INVALID, "conv_gemm: tensor-core path takes bf16 operands");
+  if (out_f32) {
+    // fp32 residual stream (ViT attn.proj / mlp.fc2 / patch projection): out = residual + (acc + bias), all fp32
+    if (head || hp.halo || d->out2.ptr || d->gn_partial || d->act != ODB_ACT_NONE || !d->bias || !d->residual.ptr ||
+        d->epilogue != 0)
+      return fail(ODB_ERR_UNSUPPORTED, "conv_gemm: fp32 output needs bias + fp32 residual and no act/out2/gn/head/halo");
+    if (d->out.c != N || d->residual.c != N || d->residual.w < ow || d->residual.h < oh || d->residual.b < ob)
+      return fail(ODB_ERR_INVALID, "conv_gemm: fp32 out/residual extent mismatch");
+    rc = encode_view_map(&p.out_map, d->out, 32, tw, th, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    if (rc) return rc;
+    rc = encode_view_map(&p.res_map, d->residual, 32, tw, th, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    if (rc) return rc;
+    p.out2_map = p.out_map;
+    p.bias = d->bias;
+    p.bias_sb = d->bias_sb;
+    p.trace = debug_trace();
+    return launch_fast<EPI_BIAS_RES_F32>(p, block_n, pair, m_tiles, m_tiles * p.tiles_n, stream);
+  }
   if (!head) {
     if (d->out.c != N) return fail(ODB_ERR_INVALID, "conv_gemm: out.c must equal n");
     rc = encode_view_map(&p.out_map, d->out, 64, tw, th, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1155,10 +1177,10 @@ extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   const long long total = m_tiles * p.tiles_n;
   // specialised epilogue when the flag combination allows it (see the EPI_* comment)
   if (!hp.halo && !head && block_n >= 64 && p.bias == nullptr && !p.has_out2 && p.gn_partial != nullptr &&
-      p.residual == nullptr && p.act == ODB_ACT_NONE && d->epilogue == 0 && fast_epilogues_enabled())
+      p.residual == nullptr && p.act == ODB_ACT_NONE && d->epilogue == 0)
     return launch_fast<EPI_GN>(p, block_n, pair, m_tiles, total, stream);
   if (!hp.halo && !head && block_n >= 64 && p.bias != nullptr && !p.has_out2 && p.gn_partial == nullptr &&
-      d->epilogue == 0 && fast_epilogues_enabled()) {
+      d->epilogue == 0) {
     if (p.residual == nullptr) {
       if (p.act == ODB_ACT_NONE) return launch_fast<EPI_BIAS>(p, block_n, pair, m_tiles, total, stream);
       if (p.act == ODB_ACT_RELU) return launch_fast<EPI_BIAS_RELU>(p, block_n, pair, m_tiles, total, stream);

@@ -14,13 +14,18 @@ int fail(int status, const char* msg);
 int fail_cuda(cudaError_t e, const char* where);
 int check_launch(const char* where);
 void count_launch();
-int num_sms();
+int num_sms();            // of the current device (cached per device)
+constexpr int kMaxDevices = 64;
+int current_device();     // cudaGetDevice, clamped to [0, kMaxDevices)
 
 int encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, int rank, void* base,
                  const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
                  const cuuint32_t* elem_strides, CUtensorMapSwizzle swizzle);
 
 bool pdl_enabled();
+
+// fp32 correctness mode of odb_conv_gemm (fp32_path.cu)
+
 
 // diagnostics (odb_debug_conv_trace): device buffer of kTraceSlots uint64 per CTA, or nullptr
 constexpr int kTraceSlots = 128;

@@ -22,14 +22,27 @@ ODB_DEVINL void store8(bf16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// fp32 storage (the ViT residual stream, and every activation in the fp32 correctness mode): the same 8-element
+// item is two 16-byte vectors
+ODB_DEVINL void load8(const float* p, float* v) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+ODB_DEVINL void store8(float* p, const float* v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+ODB_DEVINL void store1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+ODB_DEVINL void store1(float* p, float v) { *p = v; }
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm: each warp normalises TWO rows held in registers (cols <= 1024 -> <= 4 vectors per lane
 // and row), so six to eight 16-byte loads are in flight per lane before the first reduction.
-template <int VPL>  // 16-byte vectors per lane and row; cols = VPL * 256
-__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x,
+template <int VPL, typename TI, typename TO>  // 8-element items per lane and row; cols = VPL * 256
+__global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
-                                                        bf16* __restrict__ y, long long rows,
+                                                        TO* __restrict__ y, long long rows,
                                                         float eps) {
   grid_dep_wait();
   grid_dep_launch();
@@ -42,7 +55,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     if (r == 1 && !two) break;
-    const bf16* xr = x + (row0 + r) * COLS;
+    const TI* xr = x + (row0 + r) * COLS;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) load8(xr + (i * 32 + lane) * 8, v[r][i]);
   }
@@ -64,7 +77,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
         q += d * d;
       }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / COLS) + eps);
-    bf16* yr = y + (row0 + r) * COLS;
+    TO* yr = y + (row0 + r) * COLS;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c0 = (i * 32 + lane) * 8;
@@ -91,8 +104,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 // run to run and independent of the batch size.
 constexpr int kGnMaxC = 1024;
 
+template <typename T>
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(
-    const bf16* __restrict__ x, float* __restrict__ stats, double* __restrict__ partial,
+    const T* __restrict__ x, float* __restrict__ stats, double* __restrict__ partial,
     unsigned int* __restrict__ counters, int hw, int c, int groups, int pixels_per_block,
     float eps) {
   __shared__ float s_thr[2][256 * 8];     // per-thread channel partials, [plane][channel]
@@ -108,7 +122,7 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(
   const int planes = blockDim.x / octets;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (plane < planes) {
-    const bf16* base = x + ((long long)b * hw) * c + oct * 8;
+    const T* base = x + ((long long)b * hw) * c + oct * 8;
     for (int p = p0 + plane; p < p1; p += planes) {
       float v[8];
       load8(base + (long long)p * c, v);
@@ -219,11 +233,12 @@ ODB_DEVINL GnCoef gn_coef(const float* stats, const float* gamma, const float* b
 // y = relu?( gn(x) + shortcut ).  Each block first folds the statistics and the affine parameters
 // of its image into a per-channel (scale, shift) table in shared memory, so the streaming loop is
 // one FMA per element; thread = (pixel, channel octet), 16-byte accesses.
+template <typename T>
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
-    const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-    const float* __restrict__ beta, const bf16* __restrict__ res,
+    const T* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const T* __restrict__ res,
     const float* __restrict__ res_stats, const float* __restrict__ res_gamma,
-    const float* __restrict__ res_beta, bf16* __restrict__ y, int hw, int c, int groups, int relu) {
+    const float* __restrict__ res_beta, T* __restrict__ y, int hw, int c, int groups, int relu) {
   grid_dep_wait();
   grid_dep_launch();
   extern __shared__ float coef[];  // [c] scale, [c] shift, then [c] shortcut scale (shift is folded)
@@ -246,9 +261,9 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
   const unsigned total = (unsigned)hw * (unsigned)octets;
   const unsigned omask = (unsigned)octets - 1u;
   const bool pow2 = (octets & (octets - 1)) == 0;
-  const bf16* xb = x + ((long long)b * hw) * c;
-  const bf16* rb = res ? res + ((long long)b * hw) * c : nullptr;
-  bf16* yb = y + ((long long)b * hw) * c;
+  const T* xb = x + ((long long)b * hw) * c;
+  const T* rb = res ? res + ((long long)b * hw) * c : nullptr;
+  T* yb = y + ((long long)b * hw) * c;
   // A thread always lands on the same channel octet (the grid stride is a multiple of the octet
   // count), so its (scale, shift) coefficients are loaded from shared memory ONCE; two independent
   // items per iteration keep all global loads ahead of the math.
@@ -305,9 +320,10 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
 }
 
 // Stem: GroupNorm + ReLU + MaxPool 3x3 s2, TF-SAME pad (0,1): window rows/cols 2o..2o+2, clipped.
+template <typename T>
 __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
-    const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-    const float* __restrict__ beta, bf16* __restrict__ y, int h, int w, int c, int groups) {
+    const T* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, T* __restrict__ y, int h, int w, int c, int groups) {
   grid_dep_wait();
   grid_dep_launch();
   extern __shared__ float coef[];  // [c] scale, [c] shift
@@ -322,8 +338,8 @@ __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
   }
   __syncthreads();
   const unsigned total = (unsigned)oh * (unsigned)ow * (unsigned)octets;
-  const bf16* xb = x + (long long)b * h * w * c;
-  bf16* yb = y + (long long)b * oh * ow * c;
+  const T* xb = x + (long long)b * h * w * c;
+  T* yb = y + (long long)b * oh * ow * c;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const unsigned oct = i % (unsigned)octets;
     const unsigned pix = i / (unsigned)octets;
@@ -359,8 +375,9 @@ __global__ void __launch_bounds__(256) stem_gn_relu_maxpool_kernel(
 // per-element div/mod, no bounds tests, no redundant global loads (the first version issued 8 scalar
 // global loads and ~40 integer ops per 16 output bytes and ran at 1.2 TB/s).
 constexpr int kStemMaxW = 1792;                      // staged rows: 21 x (w + 5) floats <= 151 KiB
+template <typename T>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x,
-                                                          bf16* __restrict__ cols, int b, int h,
+                                                          T* __restrict__ cols, int b, int h,
                                                           int w, int kpad) {
   grid_dep_wait();
   grid_dep_launch();
@@ -383,7 +400,7 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     off[col] = col < 147 ? (ch * 7 + ky) * pitch + kx : -1;
   }
   __syncthreads();
-  bf16* crow = cols + ((long long)bi * oh + oy) * ow * kpad;
+  T* crow = cols + ((long long)bi * oh + oy) * ow * kpad;
   const int total = ow * groups8;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int ox = i / groups8;
@@ -402,7 +419,8 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 // modules/midas/vit.py:131 `patch_embed.proj(x)`): fp32 NCHW -> bf16 [b * gh * gw][3 * p * p], column
 // (c * p + py) * p + px — the row-major flattening of the conv weight [D][3][p][p], so the conv is one GEMM.
 // Thread = (token, 8 consecutive px of one (c, py) row): two float4 loads, one 16-byte store.
-__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, bf16* __restrict__ cols,
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, T* __restrict__ cols,
                                                        int b, int h, int w, int p) {
   grid_dep_wait();
   grid_dep_launch();
@@ -432,10 +450,11 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 // 2x2 output block {2m+1, 2m+2} x {2k+1, 2k+2} from a single set of four loads; m = -1 / k = -1 and
 // m = h-1 / k = w-1 produce the border rows / columns (source index clamped, weight 0 or 1).
 // blockDim = (channel octets, quads along x); no integer division, 32-bit index math.
-__global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restrict__ z,
-                                                             const bf16* __restrict__ res,
-                                                             bf16* __restrict__ out,
-                                                             bf16* __restrict__ out_relu, int h, int w,
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_add_kernel(const T* __restrict__ z,
+                                                             const T* __restrict__ res,
+                                                             T* __restrict__ out,
+                                                             T* __restrict__ out_relu, int h, int w,
                                                              int c) {
   grid_dep_wait();
   grid_dep_launch();
@@ -447,7 +466,7 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
   const int ch = threadIdx.x * 8;
   const float sy = (float)(h - 1) / (float)(oh - 1), sx = (float)(w - 1) / (float)(ow - 1);
   const int ys = min(max(m, 0), h - 2), xs = min(max(k, 0), w - 2);
-  const bf16* zb = z + ((size_t)bi * h + ys) * w * c + (size_t)xs * c + ch;
+  const T* zb = z + ((size_t)bi * h + ys) * w * c + (size_t)xs * c + ch;
   float q00[8], q01[8], q10[8], q11[8];
   load8(zb, q00);
   load8(zb + c, q01);
@@ -487,19 +506,21 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const bf16* __restr
   }
 }
 
-__global__ void write_cls_row_kernel(bf16* __restrict__ tokens, const float* __restrict__ cls,
+template <typename T>
+__global__ void write_cls_row_kernel(T* __restrict__ tokens, const float* __restrict__ cls,
                                      const float* __restrict__ pos0, int tokens_n, int c) {
   grid_dep_wait();
   grid_dep_launch();
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < c; i += blockDim.x)
-    tokens[(long long)b * tokens_n * c + i] = __float2bfloat16_rn(cls[i] + pos0[i]);
+    store1(tokens + (long long)b * tokens_n * c + i, cls[i] + pos0[i]);
 }
 
 // out[b][n] = bias[n] + sum_k w[n][c + k] * tokens[b][0][k];  one warp per (b, n).
-__global__ void __launch_bounds__(256) readout_cls_bias_kernel(const bf16* __restrict__ w,
+template <typename T>
+__global__ void __launch_bounds__(256) readout_cls_bias_kernel(const T* __restrict__ w,
                                                                const float* __restrict__ bias,
-                                                               const bf16* __restrict__ tokens,
+                                                               const T* __restrict__ tokens,
                                                                float* __restrict__ out, int b_n,
                                                                int tokens_n, int c) {
   grid_dep_wait();
@@ -508,8 +529,8 @@ __global__ void __launch_bounds__(256) readout_cls_bias_kernel(const bf16* __res
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)b_n * c) return;
   const int n = (int)(wid % c), b = (int)(wid / c);
-  const bf16* wr = w + (long long)n * 2 * c + c;
-  const bf16* t = tokens + (long long)b * tokens_n * c;
+  const T* wr = w + (long long)n * 2 * c + c;
+  const T* t = tokens + (long long)b * tokens_n * c;
   float acc = 0.f;
   for (int k = lane * 8; k < c; k += 256) {
     float a[8], x[8];
@@ -520,6 +541,18 @@ __global__ void __launch_bounds__(256) readout_cls_bias_kernel(const bf16* __res
   }
   acc = warp_sum(acc);
   if (lane == 0) out[wid] = acc + __ldg(bias + n);
+}
+
+// fp32 -> bf16 copy (the hooked ViT activations: the residual stream is fp32, the readout GEMM reads bf16)
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst,
+                                                            long long n8) {
+  grid_dep_wait();
+  grid_dep_launch();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(src + i * 8, v);
+    store8(dst + i * 8, v);
+  }
 }
 
 // grid.x of a (blocks per image, image) launch: the per-image block count, capped by the share of
@@ -537,24 +570,41 @@ static int per_image_grid(long long items_per_image, int block, int b, int max_b
 
 using namespace odb;
 
-extern "C" int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y,
-                             int64_t rows, int32_t cols, float eps, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!x || !gamma || !beta || !y || rows < 0) return fail(ODB_ERR_INVALID, "layernorm: bad argument");
-  if (rows == 0) return ODB_OK;
+// storage type dispatch: T = bf16 (ODB_DTYPE_BF16) or float (ODB_DTYPE_F32)
+#define ODB_DTYPE_SWITCH(dt, T, what, ...)                                          \
+  do {                                                                              \
+    if ((dt) == ODB_DTYPE_BF16) { using T = bf16; __VA_ARGS__; }                    \
+    else if ((dt) == ODB_DTYPE_F32) { using T = float; __VA_ARGS__; }               \
+    else return fail(ODB_ERR_INVALID, what ": dtype must be ODB_DTYPE_BF16 or ODB_DTYPE_F32"); \
+  } while (0)
+
+template <typename TI, typename TO>
+static int layernorm_launch(const void* x, const float* gamma, const float* beta, void* y, int64_t rows, int32_t cols,
+                            float eps, cudaStream_t stream) {
   const int rpb = 16;   // 8 warps x 2 rows
   const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
-  const bf16* xp = static_cast<const bf16*>(x);
-  bf16* yp = static_cast<bf16*>(y);
+  const TI* xp = static_cast<const TI*>(x);
+  TO* yp = static_cast<TO*>(y);
   switch (cols) {
-    case 256: launch_pdl(layernorm_kernel<1>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
-    case 512: launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
-    case 768: launch_pdl(layernorm_kernel<3>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
-    case 1024: launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
+    case 256: launch_pdl(layernorm_kernel<1, TI, TO>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
+    case 512: launch_pdl(layernorm_kernel<2, TI, TO>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
+    case 768: launch_pdl(layernorm_kernel<3, TI, TO>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
+    case 1024: launch_pdl(layernorm_kernel<4, TI, TO>, dim3(grid), dim3(256), 0, stream, xp, gamma, beta, yp, (long long)rows, eps); break;
     default: return fail(ODB_ERR_UNSUPPORTED, "layernorm: cols must be 256/512/768/1024");
   }
   count_launch();
   return check_launch("layernorm");
+}
+
+extern "C" int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y,
+                             int64_t rows, int32_t cols, float eps, int32_t x_dtype, int32_t y_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !gamma || !beta || !y || rows < 0) return fail(ODB_ERR_INVALID, "layernorm: bad argument");
+  if (rows == 0) return ODB_OK;
+  if (x_dtype == ODB_DTYPE_BF16 && y_dtype == ODB_DTYPE_BF16) return layernorm_launch<bf16, bf16>(x, gamma, beta, y, rows, cols, eps, stream);
+  if (x_dtype == ODB_DTYPE_F32 && y_dtype == ODB_DTYPE_BF16) return layernorm_launch<float, bf16>(x, gamma, beta, y, rows, cols, eps, stream);
+  if (x_dtype == ODB_DTYPE_F32 && y_dtype == ODB_DTYPE_F32) return layernorm_launch<float, float>(x, gamma, beta, y, rows, cols, eps, stream);
+  return fail(ODB_ERR_INVALID, "layernorm: (x, y) dtypes must be (bf16, bf16), (f32, bf16) or (f32, f32)");
 }
 
 static int gn_args_ok(int b, int hw, int c, int groups) {
@@ -580,7 +630,7 @@ extern "C" int64_t odb_groupnorm_scratch_bytes(int32_t b, int32_t hw, int32_t c,
 
 extern "C" int odb_groupnorm_stats(const void* x, float* stats, void* scratch, int64_t scratch_bytes,
                                    int32_t b, int32_t hw, int32_t c, int32_t groups, float eps,
-                                   void* stream_) {
+                                   int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !stats || !scratch || !gn_args_ok(b, hw, c, groups) || c > kGnMaxC)
     return fail(ODB_ERR_INVALID, "groupnorm_stats: bad argument");
@@ -593,8 +643,9 @@ extern "C" int odb_groupnorm_stats(const void* x, float* stats, void* scratch, i
   const size_t part_off = (((size_t)b * 4) + 255) & ~(size_t)255;
   double* partial = reinterpret_cast<double*>(static_cast<char*>(scratch) + part_off);
   dim3 grid(slabs, b);
-  groupnorm_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), stats, partial,
-                                                   counters, hw, c, groups, ppb, eps);
+  ODB_DTYPE_SWITCH(dtype, T, "groupnorm_stats",
+                   groupnorm_stats_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), stats, partial, counters,
+                                                                       hw, c, groups, ppb, eps));
   count_launch();
   return check_launch("groupnorm_stats");
 }
@@ -614,62 +665,73 @@ extern "C" int odb_groupnorm_finalize(const float* partial, float* stats, int32_
 extern "C" int odb_groupnorm_apply(const void* x, const float* stats, const float* gamma,
                                    const float* beta, const void* res, const float* res_stats,
                                    const float* res_gamma, const float* res_beta, void* y, int32_t b,
-                                   int32_t hw, int32_t c, int32_t groups, int32_t relu,
+                                   int32_t hw, int32_t c, int32_t groups, int32_t relu, int32_t dtype,
                                    void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !stats || !gamma || !beta || !y || !gn_args_ok(b, hw, c, groups))
     return fail(ODB_ERR_INVALID, "groupnorm_apply: bad argument");
   if (res_stats && (!res || !res_gamma || !res_beta))
     return fail(ODB_ERR_INVALID, "groupnorm_apply: res_stats needs res, res_gamma, res_beta");
-  // blocks per image: enough for one 16-byte item per thread, capped so that the whole grid
+  // blocks per image: enough for one 8-element item per thread, capped so that the whole grid
   // (gx * b blocks) stays within ~8 resident blocks per SM
   const int gx = per_image_grid((long long)hw * (c / 8), 256, b);
   dim3 grid(gx, b);
-  launch_pdl(groupnorm_apply_kernel, grid, dim3(256), 3 * c * sizeof(float), stream,
-             static_cast<const bf16*>(x), stats, gamma, beta, static_cast<const bf16*>(res), res_stats,
-             res_gamma, res_beta, static_cast<bf16*>(y), hw, c, groups, relu);
+  ODB_DTYPE_SWITCH(dtype, T, "groupnorm_apply",
+                   launch_pdl(groupnorm_apply_kernel<T>, grid, dim3(256), 3 * c * sizeof(float), stream,
+                              static_cast<const T*>(x), stats, gamma, beta, static_cast<const T*>(res), res_stats,
+                              res_gamma, res_beta, static_cast<T*>(y), hw, c, groups, relu));
   count_launch();
   return check_launch("groupnorm_apply");
 }
 
 extern "C" int odb_stem_gn_relu_maxpool(const void* x, const float* stats, const float* gamma,
                                         const float* beta, void* y, int32_t b, int32_t h, int32_t w,
-                                        int32_t c, int32_t groups, void* stream_) {
+                                        int32_t c, int32_t groups, int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !stats || !gamma || !beta || !y || h < 2 || w < 2 || (h & 1) || (w & 1) ||
       !gn_args_ok(b, h * w, c, groups))
     return fail(ODB_ERR_INVALID, "stem_gn_relu_maxpool: bad argument");
   const int gx = per_image_grid((long long)(h / 2) * (w / 2) * (c / 8), 256, b);
   dim3 grid(gx, b);
-  launch_pdl(stem_gn_relu_maxpool_kernel, grid, dim3(256), 2 * c * sizeof(float), stream,
-             static_cast<const bf16*>(x), stats, gamma, beta, static_cast<bf16*>(y), h, w, c, groups);
+  ODB_DTYPE_SWITCH(dtype, T, "stem_gn_relu_maxpool",
+                   launch_pdl(stem_gn_relu_maxpool_kernel<T>, grid, dim3(256), 2 * c * sizeof(float), stream,
+                              static_cast<const T*>(x), stats, gamma, beta, static_cast<T*>(y), h, w, c, groups));
   count_launch();
   return check_launch("stem_gn_relu_maxpool");
 }
 
+template <typename T>
+static int stem_im2col_launch(const float* x, void* cols, int32_t b, int32_t h, int32_t w, int32_t kpad, size_t smem,
+                              cudaStream_t stream) {
+  static bool configured[kMaxDevices] = {};
+  const int dev_ = current_device();
+  if (!configured[dev_]) {
+    cudaError_t e = cudaFuncSetAttribute(stem_im2col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         21 * (kStemMaxW + 5) * (int)sizeof(float) + 4096);
+    if (e != cudaSuccess) return fail_cuda(e, "stem_im2col: cudaFuncSetAttribute");
+    configured[dev_] = true;
+  }
+  launch_pdl(stem_im2col_kernel<T>, dim3(b * (h / 2)), dim3(256), smem, stream, x, static_cast<T*>(cols), b, h, w, kpad);
+  return ODB_OK;
+}
+
 extern "C" int odb_stem_im2col(const float* x, void* cols, int32_t b, int32_t h, int32_t w,
-                               int32_t kpad, void* stream_) {
+                               int32_t kpad, int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !cols || b < 1 || h < 2 || w < 2 || (h & 1) || (w & 1) || kpad < 152 || kpad % 8)
     return fail(ODB_ERR_INVALID, "stem_im2col: bad argument");
   if (w > kStemMaxW) return fail(ODB_ERR_UNSUPPORTED, "stem_im2col: width above 1792 not supported");
   const size_t smem = (size_t)21 * (w + 5) * sizeof(float) + (size_t)kpad * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         21 * (kStemMaxW + 5) * (int)sizeof(float) + 4096);
-    if (e != cudaSuccess) return fail_cuda(e, "stem_im2col: cudaFuncSetAttribute");
-    configured = true;
-  }
   if (kpad > 1024) return fail(ODB_ERR_INVALID, "stem_im2col: kpad too large");
-  launch_pdl(stem_im2col_kernel, dim3(b * (h / 2)), dim3(256), smem, stream, x, static_cast<bf16*>(cols), b, h, w,
-             kpad);
+  int rc = ODB_OK;
+  ODB_DTYPE_SWITCH(dtype, T, "stem_im2col", rc = stem_im2col_launch<T>(x, cols, b, h, w, kpad, smem, stream));
+  if (rc) return rc;
   count_launch();
   return check_launch("stem_im2col");
 }
 
 extern "C" int odb_patchify(const float* x, void* cols, int32_t b, int32_t h, int32_t w, int32_t patch,
-                            void* stream_) {
+                            int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !cols || b < 1 || patch < 8 || patch % 8 || h < patch || w < patch || h % patch || w % patch ||
       (reinterpret_cast<uintptr_t>(x) & 15u) || (w % 4))
@@ -678,14 +740,15 @@ extern "C" int odb_patchify(const float* x, void* cols, int32_t b, int32_t h, in
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  launch_pdl(patchify_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, static_cast<bf16*>(cols), b, h, w,
-             patch);
+  ODB_DTYPE_SWITCH(dtype, T, "patchify",
+                   launch_pdl(patchify_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, stream, x, static_cast<T*>(cols), b,
+                              h, w, patch));
   count_launch();
   return check_launch("patchify");
 }
 
 extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, void* out_relu,
-                                  int32_t b, int32_t h, int32_t w, int32_t c, void* stream_) {
+                                  int32_t b, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!z || !out || b < 1 || h < 1 || w < 1 || c < 8 || c % 8)
     return fail(ODB_ERR_INVALID, "upsample2x_add: bad argument");
@@ -695,32 +758,49 @@ extern "C" int odb_upsample2x_add(const void* z, const void* res, void* out, voi
   const int quads = 256 / octets;                       // source quads along x per block
   dim3 block(octets, quads);
   dim3 grid((w + 1 + quads - 1) / quads, h + 1, b);     // quad columns -1..w-1, quad rows -1..h-1
-  launch_pdl(upsample2x_add_kernel, grid, block, 0, stream, static_cast<const bf16*>(z),
-             static_cast<const bf16*>(res), static_cast<bf16*>(out), static_cast<bf16*>(out_relu), h, w, c);
+  ODB_DTYPE_SWITCH(dtype, T, "upsample2x_add",
+                   launch_pdl(upsample2x_add_kernel<T>, grid, block, 0, stream, static_cast<const T*>(z),
+                              static_cast<const T*>(res), static_cast<T*>(out), static_cast<T*>(out_relu), h, w, c));
   count_launch();
   return check_launch("upsample2x_add");
 }
 
 extern "C" int odb_write_cls_row(void* tokens, const float* cls, const float* pos0, int32_t b,
-                                 int32_t tokens_n, int32_t c, void* stream_) {
+                                 int32_t tokens_n, int32_t c, int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!tokens || !cls || !pos0 || b < 1 || tokens_n < 1 || c < 1)
     return fail(ODB_ERR_INVALID, "write_cls_row: bad argument");
-  launch_pdl(write_cls_row_kernel, dim3(b), dim3(256), 0, stream, static_cast<bf16*>(tokens), cls, pos0,
-             tokens_n, c);
+  ODB_DTYPE_SWITCH(dtype, T, "write_cls_row",
+                   launch_pdl(write_cls_row_kernel<T>, dim3(b), dim3(256), 0, stream, static_cast<T*>(tokens), cls, pos0,
+                              tokens_n, c));
   count_launch();
   return check_launch("write_cls_row");
 }
 
 extern "C" int odb_readout_cls_bias(const void* w, const float* bias, const void* tokens, float* out,
-                                    int32_t b, int32_t tokens_n, int32_t c, void* stream_) {
+                                    int32_t b, int32_t tokens_n, int32_t c, int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!w || !bias || !tokens || !out || b < 1 || tokens_n < 1 || c < 8 || c % 8)
     return fail(ODB_ERR_INVALID, "readout_cls_bias: bad argument");
   const long long warps = (long long)b * c;
   const unsigned grid = (unsigned)((warps + 7) / 8);
-  launch_pdl(readout_cls_bias_kernel, dim3(grid), dim3(256), 0, stream, static_cast<const bf16*>(w), bias,
-             static_cast<const bf16*>(tokens), out, b, tokens_n, c);
+  ODB_DTYPE_SWITCH(dtype, T, "readout_cls_bias",
+                   launch_pdl(readout_cls_bias_kernel<T>, dim3(grid), dim3(256), 0, stream, static_cast<const T*>(w), bias,
+                              static_cast<const T*>(tokens), out, b, tokens_n, c));
   count_launch();
   return check_launch("readout_cls_bias");
+}
+
+extern "C" int odb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst || n < 0 || n % 8 || (reinterpret_cast<uintptr_t>(src) & 15u) || (reinterpret_cast<uintptr_t>(dst) & 15u))
+    return fail(ODB_ERR_INVALID, "cast_f32_bf16: n must be a multiple of 8, pointers 16-byte aligned");
+  if (n == 0) return ODB_OK;
+  long long blocks = (n / 8 + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  launch_pdl(cast_f32_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, src, static_cast<bf16*>(dst),
+             (long long)(n / 8));
+  count_launch();
+  return check_launch("cast_f32_bf16");
 }

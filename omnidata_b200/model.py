@@ -221,7 +221,12 @@ class DPTDepthModel(nn.Module):
         self.use_cuda_graph = False
         self.keep_taps = False                    # tests: keep named intermediate activations
         self.taps: Dict[str, torch.Tensor] = {}
+        # "bf16": tcgen05 tensor-core path (bf16 operands / storage, fp32 accumulation, fp32 ViT residual stream);
+        # "fp32": correctness mode — every operand and activation fp32, contractions on the FP32 pipe with fp64
+        #         combination of partial sums (the reference is fp32-only: requirements.txt:4, no autocast anywhere)
+        self._precision = "bf16"
         self._packed = None
+        self._packed_sig = None
         self._workspaces: Dict[Tuple[int, int, int], _Workspace] = {}
         self._graphs: Dict[Tuple[int, int, int], tuple] = {}
         self._build_parameters()
@@ -259,9 +264,36 @@ class DPTDepthModel(nn.Module):
             parameters = parameters["model"]
         self.load_state_dict(parameters)
 
+    @property
+    def precision(self) -> str:
+        return self._precision
+
+    @precision.setter
+    def precision(self, value: str):
+        if value not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if value != self._precision:
+            self._precision = value
+            self._invalidate()
+            self._workspaces.clear()
+
     def _invalidate(self):
         self._packed = None
+        self._packed_sig = None
         self._graphs.clear()
+
+    def refresh_weights(self):
+        """Re-derive the packed kernel weights (and drop captured CUDA graphs) after the parameters changed.
+        `forward` also detects in-place updates by itself (parameter version counters and storage pointers)."""
+        self._invalidate()
+
+    def _weights_signature(self):
+        # in-place updates (optimizer steps on a flat buffer, broadcast copy_, EMA) bump `_version`;
+        # re-pointed storage (flatten_parameters, .data = ...) changes `data_ptr`
+        sig = 0
+        for p in self.parameters():
+            sig = (sig * 1000003 + p._version * 31 + p.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+        return sig
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -274,7 +306,10 @@ class DPTDepthModel(nn.Module):
     def _prepack(self, device) -> dict:
         sd = {k: v.detach().to(device) for k, v in self.state_dict().items()}
         f32 = lambda k: sd[k].float().contiguous()
-        bf = lambda t: t.to(torch.bfloat16).contiguous()
+        wdt = torch.float32 if self._precision == "fp32" else torch.bfloat16
+        bf = lambda t: t.to(wdt).contiguous()                      # operand storage type of the GEMM weights
+        _pack = ops.pack_conv_weight
+        pack_w = lambda w: _pack(w, wdt)
         pk: dict = {}
         pm = "pretrained.model."
         D, depth = self.arch["embed"], self.arch["depth"]
@@ -290,14 +325,14 @@ class DPTDepthModel(nn.Module):
                     p = f"{bb}stages.{s}.blocks.{b}."
                     e = {"stride": 2 if (b == 0 and s > 0) else 1, "cout": cout, "mid": cout // 4}
                     if b == 0:
-                        e["wd"] = ops.pack_conv_weight(_std_weight(sd[p + "downsample.conv.weight"]))
+                        e["wd"] = pack_w(_std_weight(sd[p + "downsample.conv.weight"]))
                         e["gd"], e["bd"] = f32(p + "downsample.norm.weight"), f32(p + "downsample.norm.bias")
                     for i in (1, 2, 3):
-                        e[f"w{i}"] = ops.pack_conv_weight(_std_weight(sd[p + f"conv{i}.weight"]))
+                        e[f"w{i}"] = pack_w(_std_weight(sd[p + f"conv{i}.weight"]))
                         e[f"g{i}"], e[f"b{i}"] = f32(p + f"norm{i}.weight"), f32(p + f"norm{i}.bias")
                     blocks.append((s, b, e))
             pk["rn_blocks"] = blocks
-            pk["proj_w"] = ops.pack_conv_weight(sd[pm + "patch_embed.proj.weight"])
+            pk["proj_w"] = pack_w(sd[pm + "patch_embed.proj.weight"])
         else:
             # PatchEmbed conv [D,3,16,16]: its row-major flattening is the GEMM weight for odb_patchify's columns
             pk["proj_w"] = bf(sd[pm + "patch_embed.proj.weight"].reshape(D, -1))
@@ -323,9 +358,9 @@ class DPTDepthModel(nn.Module):
             pk[f"ro{n}_wtok"] = wfull[:, :D].contiguous()          # token half of the split Linear
             pk[f"ro{n}_b"] = f32(p + "0.project.0.bias")
             cp = self._rn_pad[n - 1]
-            pk[f"pp{n}_w"] = ops.pack_conv_weight(_pad_to(sd[p + "3.weight"], 0, cp))
+            pk[f"pp{n}_w"] = pack_w(_pad_to(sd[p + "3.weight"], 0, cp))
             pk[f"pp{n}_b"] = _pad_to(f32(p + "3.bias"), 0, cp)
-        pk["pp4s_w"] = ops.pack_conv_weight(sd["pretrained.act_postprocess4.4.weight"])
+        pk["pp4s_w"] = pack_w(sd["pretrained.act_postprocess4.4.weight"])
         pk["pp4s_b"] = f32("pretrained.act_postprocess4.4.bias")
         if not self.arch["hybrid"]:
             # ConvTranspose2d(c, c, k, stride k) (vit.py:216-225, 240-249): k*k independent 1x1 convolutions,
@@ -336,22 +371,22 @@ class DPTDepthModel(nn.Module):
                 pk[f"pp{n}t_w"] = [[bf(w[:, :, dy, dx].t()) for dx in range(k)] for dy in range(k)]
                 pk[f"pp{n}t_b"] = _pad_to(f32(f"pretrained.act_postprocess{n}.4.bias"), 0, cp)
         for n in (1, 2, 3, 4):
-            pk[f"rn{n}_w"] = ops.pack_conv_weight(_pad_to(sd[f"scratch.layer{n}_rn.weight"], 1, self._rn_pad[n - 1]))
+            pk[f"rn{n}_w"] = pack_w(_pad_to(sd[f"scratch.layer{n}_rn.weight"], 1, self._rn_pad[n - 1]))
             p = f"scratch.refinenet{n}."
-            pk[f"ff{n}_out"] = (ops.pack_conv_weight(sd[p + "out_conv.weight"]), f32(p + "out_conv.bias"))
+            pk[f"ff{n}_out"] = (pack_w(sd[p + "out_conv.weight"]), f32(p + "out_conv.bias"))
             for u in (1, 2):
                 pk[f"ff{n}_rcu{u}"] = tuple(
-                    (ops.pack_conv_weight(sd[f"{p}resConfUnit{u}.conv{cv}.weight"]),
+                    (pack_w(sd[f"{p}resConfUnit{u}.conv{cv}.weight"]),
                      f32(f"{p}resConfUnit{u}.conv{cv}.bias")) for cv in (1, 2))
-        pk["head0"] = (ops.pack_conv_weight(sd["scratch.output_conv.0.weight"]), f32("scratch.output_conv.0.bias"))
-        pk["head2"] = (ops.pack_conv_weight(sd["scratch.output_conv.2.weight"]), f32("scratch.output_conv.2.bias"))
+        pk["head0"] = (pack_w(sd["scratch.output_conv.0.weight"]), f32("scratch.output_conv.0.bias"))
+        pk["head2"] = (pack_w(sd["scratch.output_conv.2.weight"]), f32("scratch.output_conv.2.bias"))
         pk["head4"] = (sd["scratch.output_conv.4.weight"].float().reshape(self.num_channels, 32).contiguous(),
                        f32("scratch.output_conv.4.bias"))
         pk["pos_cache"] = {}
         return pk
 
     def _pos_for_grid(self, pk, gh: int, gw: int):
-        """(pos0 fp32 [D], grid bf16 [1,1,gh*gw,D]); bilinear resize as vit.py:102-116 if needed."""
+        """(pos0 fp32 [D], grid fp32 [gh*gw, D]); bilinear resize as vit.py:102-116 if needed."""
         key = (gh, gw)
         if key not in pk["pos_cache"]:
             pos = pk["pos"]
@@ -360,8 +395,7 @@ class DPTDepthModel(nn.Module):
                 g = grid.reshape(1, 24, 24, -1).permute(0, 3, 1, 2)
                 g = F.interpolate(g, size=(gh, gw), mode="bilinear")
                 grid = g.permute(0, 2, 3, 1).reshape(gh * gw, -1)
-            pk["pos_cache"][key] = (pos[0, 0].contiguous(),
-                                    grid.to(torch.bfloat16).contiguous().view(1, 1, gh * gw, self.arch["embed"]))
+            pk["pos_cache"][key] = (pos[0, 0].contiguous(), grid.float().contiguous())
         return pk["pos_cache"][key]
 
     # ------------------------------------------------------------------ forward
@@ -374,14 +408,27 @@ class DPTDepthModel(nn.Module):
         B, _, H, W = x.shape
         if H % 32 or W % 32 or (H // 16) * (W // 16) + 1 > 640:
             raise ValueError("H and W must be multiples of 32 with at most 639 patches (384x384 in scope)")
+        if self.training and torch.is_grad_enabled():
+            # train() mode under autograd: the differentiable forward (activations kept for the backward kernels);
+            # eval() mode, or any call under torch.no_grad(), is the inference path below and returns a tensor
+            # that is not attached to an autograd graph
+            return self._forward_autograd(x)
         x = x.detach().float().contiguous()
-        if self._packed is None:
+        sig = self._weights_signature()
+        if self._packed is None or sig != self._packed_sig:
+            self._invalidate()
             self._packed = self._prepack(x.device)
+            self._packed_sig = sig
         if self.use_cuda_graph and not self.keep_taps:
             out = self._forward_graph(x)
         else:
             out = self._forward_impl(x)
         return out.squeeze(dim=1)                     # dpt_depth.py:107
+
+    def _forward_autograd(self, x: torch.Tensor) -> torch.Tensor:
+        """Differentiable forward (train_depth.py:183-190 training_step): implemented by omnidata_b200.train."""
+        from . import train
+        return train.differentiable_forward(self, x)
 
     def _forward_graph(self, x: torch.Tensor) -> torch.Tensor:
         key = tuple(x.shape[i] for i in (0, 2, 3))
@@ -407,7 +454,9 @@ class DPTDepthModel(nn.Module):
     def _resnet_features(self, x, pk, ws, taps):
         """ResNetV2 stem + stages of the hybrid encoder -> (layer_1, layer_2, stage-2 features)."""
         B, _, H, W = x.shape
-        buf = ws.get
+        fp32 = self._precision == "fp32"
+        adt = torch.float32 if fp32 else torch.bfloat16
+        buf = lambda name, shape, dtype=None: ws.get(name, shape, adt if dtype is None else dtype)
         # ---------------- ResNetV2 stem + stages (timm; hooks at vit.py:363-368)
         h2, w2 = H // 2, W // 2
         n_gn = 1 + sum(3 * d + 1 for _, d in _STAGES)
@@ -416,25 +465,25 @@ class DPTDepthModel(nn.Module):
         if gn_scratch is None:                         # zeroed once; the kernel leaves it zeroed
             gn_scratch = ws.bufs["gn_scratch"] = torch.zeros(4 << 20, dtype=torch.uint8, device=x.device)
         stat_i = iter(range(n_gn))
-
-        def gn_stats(t):                                  # standalone statistics pass (stem only)
-            st = stats_pool[next(stat_i)]
-            ops.groupnorm_stats(t, st, scratch=gn_scratch)
-            return st
-
         # fused statistics: the conv epilogue writes per-warp partial sums here (largest layer:
         # stage 0 at 96x96 -> 72 tiles x 4 quadrants x 32 groups x 2 per image)
         gn_part = buf("gn_partial", (B * ((H // 4) * (W // 4) // 32 + 64) * 4 * 32 * 2,), torch.float32)
 
-        def gn_fused():
-            return (gn_part, stats_pool[next(stat_i)])
+        def conv_stats(fn, *args, out, **kw):
+            """conv + GroupNorm statistics of its (unrounded) output.  Tensor-core path: partial sums in the conv
+            epilogue + finalize; fp32 mode: the deterministic standalone statistics kernel."""
+            st = stats_pool[next(stat_i)]
+            if fp32:
+                fn(*args, out, **kw)
+                ops.groupnorm_stats(out, st, scratch=gn_scratch)
+            else:
+                fn(*args, out, gn_stats=(gn_part, st), **kw)
+            return st
 
         cols = buf("stem_cols", (B * h2 * w2, 160))
         ops.stem_im2col(x, cols)
         s0 = buf("stem_conv", (B, h2, w2, 64))
-        gs = gn_fused()
-        ops.conv1x1(cols.view(B, h2, w2, 160), pk["stem_w"], s0, gn_stats=gs)
-        st = gs[1]
+        st = conv_stats(ops.conv1x1, cols.view(B, h2, w2, 160), pk["stem_w"], out=s0)
         t = buf("stem_pool", (B, h2 // 2, w2 // 2, 64))
         ops.stem_gn_relu_maxpool(s0, st, pk["stem_g"], pk["stem_b"], t)
         if taps is not None:
@@ -448,29 +497,21 @@ class DPTDepthModel(nn.Module):
             shortcut, sc_stats = t, None
             if b == 0:
                 d = buf(tag + "_ds", (B, ho, wo, cout))
-                gs = gn_fused()
-                ops.conv1x1(t[:, ::stride, ::stride, :] if stride > 1 else t, e["wd"], d, gn_stats=gs)
-                sc_stats = gs[1]
+                sc_stats = conv_stats(ops.conv1x1, t[:, ::stride, ::stride, :] if stride > 1 else t, e["wd"], out=d)
                 shortcut = d
             y1 = buf(tag + "_y1", (B, hh, ww, mid))
-            gs = gn_fused()
-            ops.conv1x1(t, e["w1"], y1, gn_stats=gs)
-            st1 = gs[1]
+            st1 = conv_stats(ops.conv1x1, t, e["w1"], out=y1)
             a1 = buf(tag + "_a1", (B, hh, ww, mid))
             ops.groupnorm_apply(y1, st1, e["g1"], e["b1"], a1, relu=True)
             y2 = buf(tag + "_y2", (B, ho, wo, mid))
-            gs = gn_fused()
             if stride == 1:
-                ops.conv3x3(a1, e["w2"], y2, gn_stats=gs)
+                st2 = conv_stats(ops.conv3x3, a1, e["w2"], out=y2)
             else:
-                ops.conv3x3_s2(a1, e["w2"], y2, "same", gn_stats=gs)
-            st2 = gs[1]
+                st2 = conv_stats(lambda a, w_, o, **kw: ops.conv3x3_s2(a, w_, o, "same", **kw), a1, e["w2"], out=y2)
             a2 = buf(tag + "_a2", (B, ho, wo, mid))
             ops.groupnorm_apply(y2, st2, e["g2"], e["b2"], a2, relu=True)
             y3 = buf(tag + "_y3", (B, ho, wo, cout))
-            gs = gn_fused()
-            ops.conv1x1(a2, e["w3"], y3, gn_stats=gs)
-            st3 = gs[1]
+            st3 = conv_stats(ops.conv1x1, a2, e["w3"], out=y3)
             out = buf(tag + "_out", (B, ho, wo, cout))
             if b == 0:
                 ops.groupnorm_apply(y3, st3, e["g3"], e["b3"], out, relu=True, res=shortcut,
@@ -495,7 +536,9 @@ class DPTDepthModel(nn.Module):
         taps = self.taps if self.keep_taps else None
         if taps is not None:
             taps.clear()
-        buf = ws.get
+        fp32 = self._precision == "fp32"
+        adt = torch.float32 if fp32 else torch.bfloat16            # activation storage type
+        buf = lambda name, shape, dtype=None: ws.get(name, shape, adt if dtype is None else dtype)
 
         D, heads = self.arch["embed"], self.arch["heads"]
         hooks = self.arch["hooks"]
@@ -506,18 +549,23 @@ class DPTDepthModel(nn.Module):
             gh, gw = H // 16, W // 16
         ntok = gh * gw + 1
 
-        # ---------------- tokens: patch proj + cls + pos (vit.py:131-147)
+        # ---------------- tokens: patch proj + cls + pos (vit.py:131-147).  The residual stream is fp32 in BOTH
+        # precisions (timm Block.forward adds every branch to an fp32 `x`): the proj / fc2 epilogues
+        # read and write fp32, LayerNorm reads fp32.
         pos0, pos_grid = self._pos_for_grid(pk, gh, gw)
-        tok_bufs = [buf(f"tok_{i}", (B, ntok, D)) for i in range(len(hooks))]
+        pos_b = pk["pos_cache"].get((gh, gw, B))           # derived from the weights: lives with the packed weights
+        if pos_b is None:                                  # pos[1:] replicated per image: the GEMM's fp32 residual operand
+            pos_b = pk["pos_cache"][(gh, gw, B)] = pos_grid.unsqueeze(0).expand(B, -1, -1).contiguous()
+        tok_bufs = [buf(f"tok_{i}", (B, ntok, D), torch.float32) for i in range(len(hooks))]
         tok = tok_bufs[0]
         ops.write_cls_row(tok, pk["cls"], pos0)
         if self.arch["hybrid"]:
             ops.linear(f3.view(B, 1, gh * gw, 1024), pk["proj_w"], tok[:, 1:, :].unsqueeze(1), bias=pk["proj_b"],
-                       residual=pos_grid)
+                       residual=pos_b.unsqueeze(1))
         else:
             cols = buf("patch_cols", (B, 1, gh * gw, 3 * 16 * 16))
             ops.patchify(x, cols.view(B * gh * gw, -1), 16)
-            ops.linear(cols, pk["proj_w"], tok[:, 1:, :].unsqueeze(1), bias=pk["proj_b"], residual=pos_grid)
+            ops.linear(cols, pk["proj_w"], tok[:, 1:, :].unsqueeze(1), bias=pk["proj_b"], residual=pos_b.unsqueeze(1))
 
         if taps is not None:
             taps["tokens_in"] = tok.clone()
@@ -551,6 +599,10 @@ class DPTDepthModel(nn.Module):
 
         # ---------------- reassemble (vit.py:66-97, 185-290 / 431-462)
         def readout(tk, n, cout):
+            if not fp32:                                   # the hooked activation leaves the fp32 stream as a bf16 operand
+                tk16 = buf(f"ro{n}_tok", (B, ntok, D))
+                ops.cast_f32_bf16(tk, tk16)
+                tk = tk16
             cb = buf(f"ro{n}_cb", (B, D), torch.float32)
             ops.readout_cls_bias(pk[f"ro{n}_wfull"], pk[f"ro{n}_b"], tk, cb)
             r = buf(f"ro{n}_r", (B, 1, gh * gw, D))
@@ -633,7 +685,16 @@ class DPTDepthModel(nn.Module):
         out = buf("out", (B, self.num_channels, H, W), torch.float32)
         w2, b2 = pk["head2"]
         w4, b4 = pk["head4"]
-        ops.conv3x3(h1u, w2, None, bias=b2, head=(w4, b4, out, self.non_negative))
+        if fp32:
+            # correctness mode: the 128 -> 32 conv (+ReLU) on the FP32 pipe, then the 1x1 conv (+ReLU) to NCHW
+            h2 = buf("head_h2", (B, H, W, 32))
+            ops.conv3x3(h1u, w2, h2, bias=b2, act=ops.ACT_RELU)
+            pre = buf("head_pre", (B, self.num_channels, H, W), torch.float32) if taps is not None else None
+            ops.head_tail_f32(h2, w4, b4, out, relu=self.non_negative, pre=pre)
+            if taps is not None:
+                taps["head_pre_relu"] = pre
+        else:
+            ops.conv3x3(h1u, w2, None, bias=b2, head=(w4, b4, out, self.non_negative))
 
         if taps is not None:
             for hk, tk in zip(hooks, hooked):
@@ -646,7 +707,6 @@ class DPTDepthModel(nn.Module):
 
     @staticmethod
     def _debug_upsample(z: torch.Tensor) -> torch.Tensor:
-        o = torch.empty((z.shape[0], 2 * z.shape[1], 2 * z.shape[2], z.shape[3]), device=z.device,
-                        dtype=torch.bfloat16)
+        o = torch.empty((z.shape[0], 2 * z.shape[1], 2 * z.shape[2], z.shape[3]), device=z.device, dtype=z.dtype)
         ops.upsample2x_add(z, o)
         return o

@@ -12,17 +12,38 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _capi
-from ._capi import ACT_GELU, ACT_NONE, ACT_RELU, ConvGemmDesc, View, check, lib
+from ._capi import ACT_GELU, ACT_NONE, ACT_RELU, DTYPE_BF16, DTYPE_F32, ConvGemmDesc, View, check, lib
 
 __all__ = [
     "ACT_NONE", "ACT_RELU", "ACT_GELU", "conv_gemm", "linear", "conv1x1", "conv3x3", "conv3x3_s2",
     "layernorm", "attention", "groupnorm_stats", "groupnorm_apply", "stem_gn_relu_maxpool",
     "stem_im2col", "patchify", "upsample2x_add", "write_cls_row", "readout_cls_bias", "pack_conv_weight",
+    "cast_f32_bf16", "head_tail_f32",
 ]
 
+_DTYPES = {torch.bfloat16: DTYPE_BF16, torch.float32: DTYPE_F32}
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+
+def _dt(t: torch.Tensor, name: str = "tensor") -> int:
+    """odb_dtype of an activation tensor (bf16 in production, fp32 for the residual stream / correctness mode)."""
+    if not t.is_cuda:
+        raise _capi.OdbError(f"{name}: tensor must live on a CUDA device (no CPU path exists)")
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise _capi.OdbError(f"{name}: expected bfloat16 or float32 storage, got {t.dtype}") from None
+
+
+def _same_device(*ts):
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _capi.OdbError(f"tensors live on different devices ({dev} and {t.device})")
+    return dev
 
 
 class LaunchTimer:
@@ -47,14 +68,23 @@ class LaunchTimer:
         return [(n, i, s.elapsed_time(e)) for n, i, s, e in self.records]
 
 
-def _call(name: str, info: dict, fn, *args):
+def _call(name: str, info: dict, fn, dev, *args):
+    """Enqueue one C-ABI call on the current stream of `dev` — the device the tensors live on, made current for the
+    duration of the call (kernel attributes, SM counts and TMA descriptors are per device).  The stream is appended
+    as the last argument."""
+    if dev is None or dev.type != "cuda":
+        raise _capi.OdbError(f"{name}: tensors must live on a CUDA device (no CPU path exists)")
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _call(name, info, fn, dev, *args)
+    stream = torch.cuda.current_stream(dev).cuda_stream
     t = LaunchTimer.active
     if t is None:
-        check(fn(*args), name)
+        check(fn(*args, stream), name)
         return
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    check(fn(*args), name)
+    check(fn(*args, stream), name)
     e.record()
     t.records.append((name, info, s, e))
 
@@ -70,9 +100,9 @@ def _need(t: torch.Tensor, dtype, name: str):
         raise _capi.OdbError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
-def _view4(t: torch.Tensor, name: str) -> View:
-    """[B,H,W,C] (or [rows,C] -> B=H=1) bf16 tensor with unit channel stride -> odb_view."""
-    _need(t, torch.bfloat16, name)
+def _view4(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> View:
+    """[B,H,W,C] (or [rows,C] -> B=H=1) tensor with unit channel stride -> odb_view."""
+    _need(t, dtype, name)
     if t.dim() == 2:
         t = t.unsqueeze(0).unsqueeze(0)
     if t.dim() != 4 or t.stride(3) != 1:
@@ -91,21 +121,26 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
               out_extent: Optional[Tuple[int, int, int]] = None) -> None:
     """taps: (view index, dx, dy).  head = (w[head_c,32] f32, b[head_c] f32, out[B,head_c,H,W] f32, relu)."""
     d = ConvGemmDesc()
+    dev = _same_device(*views, weight, out, out2, bias, residual)
+    in_t = views[0].dtype
+    d.in_dtype = _dt(views[0], "view0")
     d.num_views = len(views)
     for i, v in enumerate(views):
-        d.views[i] = _view4(v, f"view{i}")
+        d.views[i] = _view4(v, f"view{i}", in_t)
     d.num_taps = len(taps)
     for i, (vi, dx, dy) in enumerate(taps):
         d.tap_view[i], d.tap_dx[i], d.tap_dy[i] = vi, dx, dy
-    _need(weight, torch.bfloat16, "weight")
+    _need(weight, in_t, "weight")
     if not weight.is_contiguous():
         raise _capi.OdbError("weight must be contiguous [n][taps*C]")
     d.weight = weight.data_ptr()
     d.n = weight.shape[0]
+    out_t = in_t if out is None else out.dtype
+    d.out_dtype = _DTYPES.get(out_t, -1)
     if out is not None:
-        d.out = _view4(out, "out")
+        d.out = _view4(out, "out", out_t)
     if out2 is not None:
-        d.out2 = _view4(out2, "out2")
+        d.out2 = _view4(out2, "out2", out_t)
     if bias is not None:
         _need(bias, torch.float32, "bias")
         d.bias = bias.data_ptr()
@@ -114,7 +149,7 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
         r = residual
         if r.dim() == 3:  # [rows_per_image, C] broadcast over batch is passed as [1,H,W,C] with sb=0
             r = r.unsqueeze(0)
-        rv = _view4(r, "residual")
+        rv = _view4(r, "residual", out_t)
         if residual.dim() == 4 and residual.shape[0] == 1 and out is not None and out.dim() == 4 and out.shape[0] > 1:
             rv.sb = 0
         d.residual = rv
@@ -134,9 +169,10 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
         b, _, h, w = hout.shape
         d.out = View(None, 32, w, h, b, 0, 0, 0)
     rows = d.out.w * d.out.h * d.out.b
-    info = {"m": rows, "n": d.n, "k": d.num_taps * d.views[0].c, "taps": d.num_taps, "w": d.out.w, "h": d.out.h}
+    info = {"m": rows, "n": d.n, "k": d.num_taps * d.views[0].c, "taps": d.num_taps, "w": d.out.w, "h": d.out.h,
+            "f32": d.in_dtype == DTYPE_F32}
     if gn_stats is None:
-        _call("odb_conv_gemm", info, lib().odb_conv_gemm, C.byref(d), _stream())
+        _call("odb_conv_gemm", info, lib().odb_conv_gemm, dev, C.byref(d))
         return
     # fused GroupNorm statistics: the epilogue writes per-warp partial sums, a tiny kernel reduces them
     partial, stats = gn_stats
@@ -148,20 +184,20 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
         raise _capi.OdbError("conv_gemm: gn partial buffer too small")
     d.gn_partial = partial.data_ptr()
     d.gn_groups = gn_groups
-    _call("odb_conv_gemm", info, lib().odb_conv_gemm, C.byref(d), _stream())
+    _call("odb_conv_gemm", info, lib().odb_conv_gemm, dev, C.byref(d))
     count = float(d.out.w) * float(d.out.h) * (d.n // gn_groups)
-    _call("odb_groupnorm_finalize", {}, lib().odb_groupnorm_finalize, partial.data_ptr(), stats.data_ptr(),
-          d.out.b, part_rows, gn_groups, count, gn_eps, _stream())
+    _call("odb_groupnorm_finalize", {}, lib().odb_groupnorm_finalize, dev, partial.data_ptr(), stats.data_ptr(),
+          d.out.b, part_rows, gn_groups, count, gn_eps)
 
 
 TAPS_1 = [(0, 0, 0)]
 TAPS_3X3 = [(0, kx - 1, ky - 1) for ky in range(3) for kx in range(3)]
 
 
-def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
-    """[N, Cin, kh, kw] (any float dtype) -> bf16 [N, kh*kw*Cin], tap-major / channel-minor."""
+def pack_conv_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """[N, Cin, kh, kw] (any float dtype) -> `dtype` [N, kh*kw*Cin], tap-major / channel-minor."""
     n = w.shape[0]
-    return w.permute(0, 2, 3, 1).reshape(n, -1).to(torch.bfloat16).contiguous()
+    return w.permute(0, 2, 3, 1).reshape(n, -1).to(dtype).contiguous()
 
 
 def linear(x, weight, out, **kw):
@@ -200,28 +236,29 @@ def conv3x3_s2(x, weight, out, mode: str, **kw):
 
 
 def layernorm(x, gamma, beta, out, eps: float = 1e-6):
-    _need(x, torch.bfloat16, "x"); _need(out, torch.bfloat16, "out")
+    """x bf16 or fp32 (the fp32 residual stream), out bf16 (fp32 only together with an fp32 x)."""
     _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
     if not (x.is_contiguous() and out.is_contiguous()):
         raise _capi.OdbError("layernorm: contiguous tensors required")
     rows = x.numel() // x.shape[-1]
-    _call("odb_layernorm", {"bytes": 4 * x.numel()}, lib().odb_layernorm, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows,
-                              x.shape[-1], eps, _stream())
+    _call("odb_layernorm", {"bytes": x.element_size() * x.numel() + out.element_size() * out.numel()},
+          lib().odb_layernorm, _same_device(x, gamma, beta, out), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+          out.data_ptr(), rows, x.shape[-1], eps, _dt(x, "x"), _dt(out, "out"))
 
 
-import os as _os
-
-ATTENTION_IMPL = _os.environ.get("ODB_ATTENTION", "tc")   # "tc" | "pp" (ping-pong) | "mma" (legacy)
-
-
-def attention(qkv, out, heads: int = 12, scale: float = 0.125, impl: Optional[str] = None):
-    impl = impl or ATTENTION_IMPL
-    _need(qkv, torch.bfloat16, "qkv"); _need(out, torch.bfloat16, "out")
+def attention(qkv, out, heads: int = 12, scale: float = 0.125):
     b, n, c3 = qkv.shape
     if not (qkv.is_contiguous() and out.is_contiguous()) or c3 != 3 * heads * 64:
         raise _capi.OdbError("attention: qkv must be contiguous [B, tokens, 3*heads*64]")
-    _call("odb_attention", {"flops": 4.0 * b * heads * n * n * 64, "bytes": 2 * (qkv.numel() + out.numel())}, {"tc": lib().odb_attention, "pp": lib().odb_attention_pp, "mma": lib().odb_attention_mma}[impl], qkv.data_ptr(), out.data_ptr(), b, n,
-          heads, scale, _stream())
+    info = {"flops": 4.0 * b * heads * n * n * 64, "bytes": qkv.element_size() * (qkv.numel() + out.numel())}
+    if qkv.dtype == torch.float32:
+        _need(out, torch.float32, "out")
+        _call("odb_attention_f32", info, lib().odb_attention_f32, _same_device(qkv, out), qkv.data_ptr(), out.data_ptr(),
+              b, n, heads, scale)
+        return
+    _need(qkv, torch.bfloat16, "qkv"); _need(out, torch.bfloat16, "out")
+    _call("odb_attention", info, lib().odb_attention, _same_device(qkv, out), qkv.data_ptr(), out.data_ptr(), b, n,
+          heads, scale)
 
 
 _GN_SCRATCH = {}
@@ -239,7 +276,7 @@ def groupnorm_scratch(device, nbytes: int) -> torch.Tensor:
 
 def groupnorm_stats(x, stats, groups: int = 32, eps: float = 1e-5, scratch: Optional[torch.Tensor] = None):
     """stats[b, g] = (mean, rstd).  Deterministic; `scratch` must stay zeroed between calls (it does)."""
-    _need(x, torch.bfloat16, "x"); _need(stats, torch.float32, "stats")
+    _need(stats, torch.float32, "stats")
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
     need = int(lib().odb_groupnorm_scratch_bytes(b, hw, c, groups))
@@ -247,57 +284,91 @@ def groupnorm_stats(x, stats, groups: int = 32, eps: float = 1e-5, scratch: Opti
         raise _capi.OdbError("groupnorm_stats: unsupported shape")
     if scratch is None:
         scratch = groupnorm_scratch(x.device, need)
-    _call("odb_groupnorm_stats", {"bytes": 2 * x.numel()}, lib().odb_groupnorm_stats, x.data_ptr(), stats.data_ptr(),
-          scratch.data_ptr(), scratch.numel(), b, hw, c, groups, eps, _stream())
+    _call("odb_groupnorm_stats", {"bytes": x.element_size() * x.numel()}, lib().odb_groupnorm_stats,
+          _same_device(x, stats, scratch), x.data_ptr(), stats.data_ptr(), scratch.data_ptr(), scratch.numel(), b, hw, c,
+          groups, eps, _dt(x, "x"))
 
 
 def groupnorm_apply(x, stats, gamma, beta, out, *, relu: bool, res=None, res_stats=None, res_gamma=None,
                     res_beta=None, groups: int = 32):
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
-    _call("odb_groupnorm_apply", {"bytes": 2 * x.numel() * (2 + (res is not None))}, lib().odb_groupnorm_apply,
+    if out.dtype != x.dtype or (res is not None and res.dtype != x.dtype):
+        raise _capi.OdbError("groupnorm_apply: x, res and out must share one storage type")
+    _call("odb_groupnorm_apply", {"bytes": x.element_size() * x.numel() * (2 + (res is not None))},
+          lib().odb_groupnorm_apply, _same_device(x, stats, gamma, beta, res, out),
           x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(res), _ptr(res_stats),
-          _ptr(res_gamma), _ptr(res_beta), out.data_ptr(), b, hw, c, groups, 1 if relu else 0, _stream())
+          _ptr(res_gamma), _ptr(res_beta), out.data_ptr(), b, hw, c, groups, 1 if relu else 0, _dt(x, "x"))
 
 
 def stem_gn_relu_maxpool(x, stats, gamma, beta, out, groups: int = 32):
     b, h, w, c = x.shape
-    _call("odb_stem_gn_relu_maxpool", {"bytes": int(2.5 * x.numel())}, lib().odb_stem_gn_relu_maxpool, x.data_ptr(),
-          stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), b, h, w, c, groups, _stream())
+    if out.dtype != x.dtype:
+        raise _capi.OdbError("stem_gn_relu_maxpool: x and out must share one storage type")
+    _call("odb_stem_gn_relu_maxpool", {"bytes": int(1.25 * x.element_size() * x.numel())}, lib().odb_stem_gn_relu_maxpool,
+          _same_device(x, stats, gamma, beta, out), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+          out.data_ptr(), b, h, w, c, groups, _dt(x, "x"))
 
 
 def stem_im2col(x, cols):
-    _need(x, torch.float32, "x"); _need(cols, torch.bfloat16, "cols")
+    _need(x, torch.float32, "x")
     b, ch, h, w = x.shape
     if ch != 3 or not x.is_contiguous():
         raise _capi.OdbError("stem_im2col: contiguous [B,3,H,W] fp32 input required")
-    _call("odb_stem_im2col", {}, lib().odb_stem_im2col, x.data_ptr(), cols.data_ptr(), b, h, w, cols.shape[-1], _stream())
+    _call("odb_stem_im2col", {}, lib().odb_stem_im2col, _same_device(x, cols), x.data_ptr(), cols.data_ptr(), b, h, w,
+          cols.shape[-1], _dt(cols, "cols"))
 
 
 def patchify(x, cols, patch: int = 16):
-    """x fp32 [B,3,H,W] -> cols bf16 [B*(H/p)*(W/p), 3*p*p] (the im2col of a stride-p, kernel-p convolution)."""
-    _need(x, torch.float32, "x"); _need(cols, torch.bfloat16, "cols")
+    """x fp32 [B,3,H,W] -> cols [B*(H/p)*(W/p), 3*p*p] (the im2col of a stride-p, kernel-p convolution)."""
+    _need(x, torch.float32, "x")
     b, c, h, w = x.shape
     if c != 3 or not x.is_contiguous() or not cols.is_contiguous() or cols.numel() != b * (h // patch) * (w // patch) * 3 * patch * patch:
         raise _capi.OdbError("patchify: x [B,3,H,W] contiguous, cols [B*gh*gw, 3*p*p]")
-    _call("odb_patchify", {"bytes": x.numel() * 4 + cols.numel() * 2}, lib().odb_patchify, x.data_ptr(), cols.data_ptr(),
-          b, h, w, patch, _stream())
+    _call("odb_patchify", {"bytes": x.numel() * 4 + cols.numel() * cols.element_size()}, lib().odb_patchify,
+          _same_device(x, cols), x.data_ptr(), cols.data_ptr(), b, h, w, patch, _dt(cols, "cols"))
 
 
 def upsample2x_add(z, out, res=None, out_relu=None):
     b, h, w, c = z.shape
-    n_in = b * h * w * c * 2
+    for t in (out, res, out_relu):
+        if t is not None and t.dtype != z.dtype:
+            raise _capi.OdbError("upsample2x_add: all tensors must share one storage type")
+    n_in = b * h * w * c * z.element_size()
     info = {"bytes": n_in + 4 * n_in * (1 + (res is not None) + (out_relu is not None)), "h": h, "c": c}
-    _call("odb_upsample2x_add", info, lib().odb_upsample2x_add, z.data_ptr(), _ptr(res), out.data_ptr(), _ptr(out_relu), b, h, w, c,
-                                   _stream())
+    _call("odb_upsample2x_add", info, lib().odb_upsample2x_add, _same_device(z, out, res, out_relu), z.data_ptr(),
+          _ptr(res), out.data_ptr(), _ptr(out_relu), b, h, w, c, _dt(z, "z"))
 
 
 def write_cls_row(tokens, cls, pos0):
     b, n, c = tokens.shape
-    _call("odb_write_cls_row", {}, lib().odb_write_cls_row, tokens.data_ptr(), cls.data_ptr(), pos0.data_ptr(), b, n, c, _stream())
+    _call("odb_write_cls_row", {}, lib().odb_write_cls_row, _same_device(tokens, cls, pos0), tokens.data_ptr(),
+          cls.data_ptr(), pos0.data_ptr(), b, n, c, _dt(tokens, "tokens"))
 
 
 def readout_cls_bias(w, bias, tokens, out):
     b, n, c = tokens.shape
-    _call("odb_readout_cls_bias", {}, lib().odb_readout_cls_bias, w.data_ptr(), bias.data_ptr(), tokens.data_ptr(), out.data_ptr(), b, n,
-                                     c, _stream())
+    if w.dtype != tokens.dtype:
+        raise _capi.OdbError("readout_cls_bias: w and tokens must share one storage type")
+    _call("odb_readout_cls_bias", {}, lib().odb_readout_cls_bias, _same_device(w, bias, tokens, out), w.data_ptr(),
+          bias.data_ptr(), tokens.data_ptr(), out.data_ptr(), b, n, c, _dt(tokens, "tokens"))
+
+
+def cast_f32_bf16(src, dst):
+    """dst (bf16) = round(src (fp32)); contiguous, numel a multiple of 8."""
+    _need(src, torch.float32, "src"); _need(dst, torch.bfloat16, "dst")
+    if not (src.is_contiguous() and dst.is_contiguous()) or src.numel() != dst.numel():
+        raise _capi.OdbError("cast_f32_bf16: contiguous tensors of equal size required")
+    _call("odb_cast_f32_bf16", {"bytes": 6 * src.numel()}, lib().odb_cast_f32_bf16, _same_device(src, dst),
+          src.data_ptr(), dst.data_ptr(), src.numel())
+
+
+def head_tail_f32(x, w, bias, out, relu: bool, pre=None):
+    """fp32 correctness mode: out[b,k,y,x] = relu?(bias[k] + sum_j w[k,j] x[b,y,x,j]), x fp32 [B,H,W,32]."""
+    for t_, n_ in ((x, "x"), (w, "w"), (bias, "bias"), (out, "out")):
+        _need(t_, torch.float32, n_)
+    b, h, wd, c = x.shape
+    if c != 32 or not x.is_contiguous() or not out.is_contiguous():
+        raise _capi.OdbError("head_tail_f32: x must be contiguous [B,H,W,32]")
+    _call("odb_head_tail_f32", {}, lib().odb_head_tail_f32, _same_device(x, w, bias, out, pre), x.data_ptr(),
+          w.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(pre), b, h, wd, w.shape[0], 1 if relu else 0)

@@ -8,7 +8,8 @@ and is what the GPU tests compare taps against on the GPU box, where /root/refer
 
 `forward_bf16(sd, x)` is the same arithmetic with the product's rounding points: operands are
 bf16, accumulation and elementwise math are fp32, and a value is rounded to bf16 exactly where
-the CUDA pipeline stores it to HBM (DESIGN.md "rounding points").  It also applies the two
+the CUDA pipeline stores it to HBM (DESIGN.md "rounding points"); the ViT residual stream stays fp32
+and GroupNorm statistics are taken from the unrounded conv output, as in the product.  It also applies the two
 algebraic re-orderings the product uses (1x1 out_conv before the bilinear upsample; ProjectReadout
 weight split), which are exact in real arithmetic.
 """
@@ -207,15 +208,27 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
     B = x.shape[0]
 
     def sconv(t, key, stride=1):
+        """-> (conv output rounded to bf16 as stored, GroupNorm statistics of the UNROUNDED fp32 output: the conv
+        epilogue sums its fp32 accumulators, like timm GroupNormAct which normalises the fp32 conv output)."""
         w = wq(std_weight(g(key)))
-        return r(F.conv2d(same_pad(t, w.shape[-1], stride), w, None, stride))
+        y = F.conv2d(same_pad(t, w.shape[-1], stride), w, None, stride)
+        yg = y.double().reshape(y.shape[0], 32, -1)
+        mean = yg.mean(dim=2)
+        var = (yg * yg).mean(dim=2) - mean * mean
+        rstd = 1.0 / torch.sqrt(var.clamp_min(0) + 1e-5)
+        return r(y), (mean.float(), rstd.float())
 
-    def gn_raw(t, prefix):
-        return F.group_norm(t, 32, g(prefix + ".weight"), g(prefix + ".bias"), 1e-5)
+    def gn_raw(ys, prefix):
+        y, (mean, rstd) = ys
+        Bn, Cn = y.shape[:2]
+        cpg = Cn // 32
+        a = rstd.repeat_interleave(cpg, dim=1) * g(prefix + ".weight")[None]                 # [B, C]
+        sh = g(prefix + ".bias")[None] - mean.repeat_interleave(cpg, dim=1) * a
+        return y * a[:, :, None, None] + sh[:, :, None, None]
 
     xin = r(x.float())                                    # im2col stores the image as bf16
     s0 = sconv(xin, BB + "stem.conv.weight", 2)
-    taps["stem_conv"] = s0
+    taps["stem_conv"] = s0[0]
     t = F.relu(gn_raw(s0, BB + "stem.norm"))
     t = r(F.max_pool2d(same_pad(t, 3, 2, float("-inf")), 3, 2))
     taps["stem_pool"] = t
@@ -240,10 +253,11 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
         grid = pos[0, 1:].reshape(1, 24, 24, -1).permute(0, 3, 1, 2)
         grid = F.interpolate(grid, size=(gh, gw), mode="bilinear")
         pos = torch.cat([pos[:, :1], grid.permute(0, 2, 3, 1).reshape(1, gh * gw, -1)], dim=1)
+    # the residual stream is fp32 (proj / fc2 epilogues add into fp32 storage; LayerNorm reads fp32): no rounding
     tok = F.conv2d(feats[2], wq(g(P + "patch_embed.proj.weight")), g(P + "patch_embed.proj.bias"))
-    tok = tok.flatten(2).transpose(1, 2) + r(pos[:, 1:])
+    tok = tok.flatten(2).transpose(1, 2) + pos[:, 1:]
     cls = (g(P + "cls_token") + pos[:, :1]).expand(B, -1, -1)
-    tok = r(torch.cat((cls, tok), dim=1))
+    tok = torch.cat((cls, tok), dim=1)
     taps["tokens_in"] = tok
     hooked = {}
     for i in range(12):
@@ -254,16 +268,17 @@ def forward_bf16(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[di
         q, k, v = qkv.reshape(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4)
         a = _attention_bf16(q, k, v)
         a = r(a.transpose(1, 2).reshape(B, N, 768))
-        tok = r(tok + F.linear(a, wq(g(p + "attn.proj.weight")), g(p + "attn.proj.bias")))
+        tok = tok + F.linear(a, wq(g(p + "attn.proj.weight")), g(p + "attn.proj.bias"))
         h = r(F.layer_norm(tok, (768,), g(p + "norm2.weight"), g(p + "norm2.bias"), 1e-6))
         h = r(F.gelu(F.linear(h, wq(g(p + "mlp.fc1.weight")), g(p + "mlp.fc1.bias"))))
-        tok = r(tok + F.linear(h, wq(g(p + "mlp.fc2.weight")), g(p + "mlp.fc2.bias")))
+        tok = tok + F.linear(h, wq(g(p + "mlp.fc2.weight")), g(p + "mlp.fc2.bias"))
         taps[f"tokens_{i}"] = tok
         if i in (8, 11):
             hooked[i] = tok
 
     def readout(tk, n):
         pp = f"pretrained.act_postprocess{n}."
+        tk = r(tk)                       # the hooked activation leaves the fp32 stream as a bf16 GEMM operand
         w = wq(g(pp + "0.project.0.weight"))
         cls_term = F.linear(tk[:, 0], w[:, 768:], g(pp + "0.project.0.bias"))       # fp32 [B,768]
         f = r(F.gelu(F.linear(tk[:, 1:], w[:, :768]) + cls_term[:, None, :]))

@@ -26,6 +26,7 @@ int main(void) {
   F(odb_conv_gemm_desc, cta_pair) F(odb_conv_gemm_desc, halo) F(odb_conv_gemm_desc, head_w) F(odb_conv_gemm_desc, head_b)
   F(odb_conv_gemm_desc, head_c) F(odb_conv_gemm_desc, head_relu) F(odb_conv_gemm_desc, head_out)
   F(odb_conv_gemm_desc, gn_partial) F(odb_conv_gemm_desc, gn_groups) F(odb_conv_gemm_desc, epilogue)
+  F(odb_conv_gemm_desc, in_dtype) F(odb_conv_gemm_desc, out_dtype)
   printf("abi %d\n", ODB_ABI_VERSION);
   return 0;
 }
