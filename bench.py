@@ -4,7 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path
 
-A "step" is one forward pass of the depth model over one batch of synthetic 384x384 RGB images.
+A "step" is one forward pass over one batch of synthetic 384x384 RGB images (`--config` picks the BASELINE.json
+configuration: 1 = depth b32 (default, the metric's own), 2 = dual depth+normal b64, 3 = 512 images strong scaling,
+4 = the train_depth.py step).
 N=1 workload = BASELINE.json configs[1] (depth head, bf16, batch 32, one B200).  For N>1 (launched
 by torch.distributed.run, one rank per GPU) every rank runs the same per-GPU batch on its own
 images — independent units, no data-path collective ("weak" scaling); weights are NCCL-broadcast
@@ -100,28 +102,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def pick_threads() -> int:
-    """All host threads the CPU path can USE: intra-op oversubscription on a 100+-core box makes the
-    convolutions slower, so time one image at a few thread counts and keep the fastest."""
-    import torch
-    from oracle import dpt_oracle, make_golden, weights
-    cores = os.cpu_count() or 1
-    cands = sorted({min(cores, c) for c in (16, 32, 64, cores)})
-    sd = weights.make_state_dict(0, 1)
-    x = make_golden.golden_input(1, seed=0)
-    best, best_t = cands[0], float("inf")
-    with torch.no_grad():
-        for c in cands:
-            torch.set_num_threads(c)
-            dpt_oracle.forward_fp32(sd, x)
-            t0 = time.perf_counter()
-            dpt_oracle.forward_fp32(sd, x)
-            dt = time.perf_counter() - t0
-            if dt < best_t:
-                best, best_t = c, dt
-    return best
-
-
 def cpu_forward_timer(batch: int, reps: int, threads: int):
     """Times the oracle (reference CPU PyTorch arithmetic, fp32) on `batch` images; returns img/s."""
     import torch
@@ -153,37 +133,54 @@ def run_reference_arm(args, rank: int, world: int):
     """--impl reference: the reference's CPU implementation of the path on the host cores.
     /root/reference is absent on the GPU box and the reference is pure Python over the un-vendored
     timm, so the oracle port (bit-identical to the reference module in the build container,
-    tests/test_oracle_cpu.py) is what runs; kind = "port"."""
+    tests/test_oracle_cpu.py) is what runs; kind = "port".  Fixed policy: batch 8 per step,
+    torch.set_num_threads(min(host cores, 32)) — on the 128-thread hosts of this pool more intra-op threads are
+    slower — K timed steps after W warm-up steps; the best single step is reported beside the mean."""
     if rank != 0:
         return
     import torch
     from oracle import dpt_oracle, make_golden, weights
-    cores = pick_threads()
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     batch = args.cpu_batch
-    sd = weights.make_state_dict(0, 1)
+    dual = args.config == 2
+    sds = [weights.make_state_dict(0, 1)] + ([weights.make_state_dict(0, 3)] if dual else [])
     x = make_golden.golden_input(batch, seed=0)
+    xs = [x] + ([(x + 1) / 2] if dual else [])
+    times = []
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 2))):
-            dpt_oracle.forward_fp32(sd, x)
-        t0 = time.perf_counter()
+            for sd, xi in zip(sds, xs):
+                dpt_oracle.forward_fp32(sd, xi)
         for _ in range(args.steps):
-            dpt_oracle.forward_fp32(sd, x)
-        dt = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for sd, xi in zip(sds, xs):
+                dpt_oracle.forward_fp32(sd, xi)
+            times.append(time.perf_counter() - t0)
+    dt = sum(times)
     value = batch * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DPT-Hybrid-384 depth forward, reference CPU PyTorch arithmetic, {batch} images/step "
-                               f"(bounded sample of configs[1])", "global_batch": batch},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "host_cores": os.cpu_count(),
-                         "kind": "port", "cpu": cpu_model_name(), "sample": f"{args.steps} steps x {batch} images, fp32, "
-                                                             f"torch.set_num_threads({cores})"},
+        "config": {"workload": f"{WORKLOADS[args.config]} — reference CPU PyTorch arithmetic, {batch} images/step "
+                               f"(bounded sample)", "global_batch": batch},
+        "cpu_baseline": {"value": value, "best_step_value": batch / min(times), "unit": "images/s", "cores": cores,
+                         "host_cores": os.cpu_count(), "kind": "port", "cpu": cpu_model_name(),
+                         "sample": f"{args.steps} steps x {batch} images, fp32, torch.set_num_threads({cores})"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+WORKLOADS = {
+    1: "configs[1]: DPT-Hybrid-384 depth head, bf16, batch 32 per GPU, synthetic 384x384 RGB",
+    2: "configs[2]: DPT-Hybrid-384 dual depth + normal networks on the same images, bf16, batch 64 per GPU",
+    3: "configs[3]: DPT-Hybrid-384 depth, global batch 512 sharded 512/N per GPU (strong scaling)",
+    4: "configs[4]: train_depth.py step — DPT forward + MiDaS SSI + virtual-normal loss + backward + gradient "
+       "all-reduce + clip + Adam, batch 16 per GPU (128 at 8 GPUs)",
+}
 
 
 def classify_gemm(info: dict, batch: int, ntok: int) -> str:
@@ -193,15 +190,55 @@ def classify_gemm(info: dict, batch: int, ntok: int) -> str:
     return "other_gemm"
 
 
+def gpu_eager_baseline(batch: int, dev):
+    """The GPU yardstick BASELINE.md 3.5 asks for: the reference network (oracle restatement = the reference module's
+    arithmetic, torch library kernels: cuDNN / cuBLAS) in eager PyTorch on the SAME B200, fp32 (TF32 off) and under
+    torch.autocast(bf16).  Baseline leg only — never on the product path."""
+    import torch
+    from oracle import dpt_oracle, make_golden, weights
+    sd = {k: v.to(dev) for k, v in weights.make_state_dict(0, 1).items()}
+    x = make_golden.golden_input(batch, seed=3).to(dev)
+    out = {}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for name in ("fp32", "autocast_bf16"):
+            def run():
+                if name == "fp32":
+                    return dpt_oracle.forward_fp32(sd, x)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return dpt_oracle.forward_fp32(sd, x)
+            with torch.no_grad():
+                run(); run()
+                torch.cuda.synchronize()
+                best = float("inf")
+                for _ in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); run(); e1.record()
+                    torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+            out[name] = {"images_per_s": round(batch / (best * 1e-3), 1), "ms_per_step": round(best, 3)}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    out["what"] = (f"reference network in eager torch {torch.__version__} (cuDNN/cuBLAS library kernels) on this GPU, "
+                   f"batch {batch}, device-resident input, best of 3 after 2 warm-up passes, CUDA events")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (configs[1]: 32)")
-    ap.add_argument("--cpu-batch", type=int, default=2, help="images per CPU step (reference arm / cpu_baseline)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs index: 1 depth b32 (default, the metric's config), 2 dual depth+normal "
+                         "b64, 3 global batch 512 strong scaling, 4 train step")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0 = the config's own)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU step (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -212,8 +249,13 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
-    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-    os.environ["NCCL_DEBUG"] = os.environ.get("ODB_NCCL_DEBUG", "WARN")
+    # stdout carries exactly one JSON line: whatever NCCL_DEBUG level the caller asked for goes to stderr
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+    if args.config == 4:
+        from omnidata_b200 import train_bench
+        train_bench.main(args)
+        return
     import torch
     from omnidata_b200 import _capi, ops, parallel
     from omnidata_b200.model import DPTDepthModel
@@ -223,39 +265,67 @@ def main():
     rank, world, local = parallel.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B = args.batch
+    dual = args.config == 2
+    strong = args.config == 3
+    if args.batch:
+        B = args.batch
+    elif strong:
+        if 512 % world:
+            raise SystemExit("config 3: 512 images must divide over the ranks")
+        B = 512 // world                      # images per GPU per step (the whole global batch is one step)
+    else:
+        B = 64 if dual else 32
+    chunk = min(B, 128) if strong else B      # config 3: the per-GPU share runs as forwards of <= 128 images
+    if B % chunk:
+        raise SystemExit("per-GPU batch must be a multiple of the chunk size")
+    n_chunks = B // chunk
     peaks = load_peaks()
 
-    # ---- model: rank 0 owns the seeded weights, the others receive them over NCCL
+    # ---- models: rank 0 owns the seeded weights and packs them; the PACKED (bf16) form is NCCL-broadcast
     from omnidata_b200 import synthetic
-    model = DPTDepthModel(backbone="vitb_rn50_384")
-    if rank == 0:
-        model.load_state_dict(synthetic.make_state_dict(0, 1), strict=True)
-    model = model.to(dev).eval()
-    t0 = time.perf_counter()
-    bcast_bytes = parallel.broadcast_state_dict(model, src=0)
-    torch.cuda.synchronize()
-    bcast_ms = 1e3 * (time.perf_counter() - t0)
-    model._invalidate()
-    model.use_cuda_graph = not args.no_graph
+    chans = (1, 3) if dual else (1,)
+    models = []
+    bcast_bytes, bcast_ms = 0, 0.0
+    for c in chans:
+        m = DPTDepthModel(backbone="vitb_rn50_384", num_channels=c)
+        if rank == 0:
+            m.load_state_dict(synthetic.make_state_dict(0, c), strict=True)
+        m = m.to(dev).eval()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bcast_bytes += parallel.broadcast_packed_weights(m, dev, src=0)
+        torch.cuda.synchronize()
+        bcast_ms += 1e3 * (time.perf_counter() - t0)
+        m.use_cuda_graph = not args.no_graph
+        models.append(m)
+
+    def forward_all(x):
+        """one chunk of images through every network of the config (config 2: depth on [-1,1], normal on [0,1])."""
+        outs = [models[0](x)]
+        if dual:
+            outs.append(models[1](x * 0.5 + 0.5))      # demo.py:74-76 / 92-95: the normal net takes RGB in [0,1]
+        return outs
 
     # ---- synthetic inputs: 4 distinct batches rotate so that no step re-reads a hot input; the
     # activations streamed per step (several GB) exceed the 126 MB L2 many times over anyway.
     gen = torch.Generator(device="cpu").manual_seed(1000 + rank)
-    host_inputs = [(torch.rand(B, 3, IMG, IMG, generator=gen) * 2 - 1).pin_memory() for _ in range(4)]
+    n_rot = 4 if chunk <= 64 else 2
+    host_inputs = [(torch.rand(chunk, 3, IMG, IMG, generator=gen) * 2 - 1).pin_memory() for _ in range(n_rot)]
     dev_inputs = [h.to(dev) for h in host_inputs]
 
     with torch.no_grad():
         # launches per forward (eager, counted by the library itself)
-        model.use_cuda_graph = False
+        for m in models:
+            m.use_cuda_graph = False
         n0 = _capi.launch_count()
-        model(dev_inputs[0])
+        forward_all(dev_inputs[0])
         torch.cuda.synchronize()
-        launches_per_fwd = _capi.launch_count() - n0
-        model.use_cuda_graph = not args.no_graph
+        launches_per_chunk = _capi.launch_count() - n0
+        for m in models:
+            m.use_cuda_graph = not args.no_graph
 
         for i in range(args.warmup):
-            model(dev_inputs[i % 4])
+            forward_all(dev_inputs[i % n_rot])
         torch.cuda.synchronize()
 
         # ---------------- timed region 1: device-resident inputs
@@ -266,8 +336,8 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            y = model(dev_inputs[i % 4])
+        for i in range(args.steps * n_chunks):
+            y = forward_all(dev_inputs[i % n_rot])
         e1.record()
         torch.cuda.synchronize()
         parallel.barrier()
@@ -276,47 +346,49 @@ def main():
 
         # ---------------- timed region 2: end to end through the public API, host buffers
         # StreamingPredictor.run = DPTDepthModel.forward per batch, with the pinned-host -> device copy
-        # of the next batch and the device -> host read of the previous depth maps on copy streams.
+        # of the next batch and the device -> host read of the previous outputs on copy streams.
         from omnidata_b200.pipeline import StreamingPredictor
-        predictor = StreamingPredictor(model, dev)
-        host_outs = [torch.empty((B, IMG, IMG), dtype=torch.float32).pin_memory() for _ in range(2)]
-        predictor.run((host_inputs[i % 4] for i in range(3)), host_outs)
+        predictor = StreamingPredictor(forward_all, dev)
+        out_shapes = [(chunk, IMG, IMG)] + ([(chunk, 3, IMG, IMG)] if dual else [])
+        host_outs = [[torch.empty(s, dtype=torch.float32).pin_memory() for s in out_shapes] for _ in range(2)]
+        predictor.run((host_inputs[i % n_rot] for i in range(3)), host_outs)
         torch.cuda.synchronize()
         parallel.barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        predictor.run((host_inputs[i % 4] for i in range(args.steps)), host_outs)
+        predictor.run((host_inputs[i % n_rot] for i in range(args.steps * n_chunks)), host_outs)
         e3.record()
         torch.cuda.synchronize()
         parallel.barrier()
         ms_e2e = parallel.reduce_max(e2.elapsed_time(e3), dev)
 
         # ---------------- instrumented pass: per-launch CUDA events (roofline)
-        roof = None
-        roof_hbm = None
+        roof = roof_vit = roof_hbm = None
         detail = {}
         if rank == 0:
-            model.use_cuda_graph = False
+            for m in models:
+                m.use_cuda_graph = False
             with ops.LaunchTimer() as lt:
                 for i in range(3):
-                    model(dev_inputs[i % 4])
+                    forward_all(dev_inputs[i % n_rot])
             recs = lt.results()
             per_fwd = len(recs) // 3
             recs = recs[per_fwd:]                                        # drop the first pass
             ntok = (IMG // 16) ** 2 + 1
             agg = {}
             for name, info, t_ms in recs:
-                key = name
+                keys = [name]
                 if name == "odb_conv_gemm":
-                    key = classify_gemm(info, B, ntok)
-                a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
-                a["ms"] += t_ms / 2
-                a["launches"] += 0.5
-                if name == "odb_conv_gemm":
-                    a["flops"] += 2.0 * info["m"] * info["n"] * info["k"] / 2
-                a["flops"] += info.get("flops", 0.0) / 2
-                a["bytes"] += info.get("bytes", 0.0) / 2
-            total_ms = sum(a["ms"] for a in agg.values())
+                    keys = ["conv_gemm_all", classify_gemm(info, chunk, ntok)]
+                for key in keys:
+                    a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+                    a["ms"] += t_ms / 2
+                    a["launches"] += 0.5
+                    if name == "odb_conv_gemm":
+                        a["flops"] += 2.0 * info["m"] * info["n"] * info["k"] / 2
+                    a["flops"] += info.get("flops", 0.0) / 2
+                    a["bytes"] += info.get("bytes", 0.0) / 2
+            total_ms = sum(a["ms"] for k, a in agg.items() if k != "conv_gemm_all")
             for k, a in agg.items():
                 d = {"ms_per_step": round(a["ms"], 4), "launches": int(a["launches"]),
                      "share": round(a["ms"] / total_ms, 4)}
@@ -325,21 +397,26 @@ def main():
                 if a["bytes"]:
                     d["gbs"] = round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1)
                 detail[k] = d
-            v = agg.get("vit_gemm")
-            if v:
-                achieved = VIT_GEMM_GFLOP_PER_IMAGE * 1e9 * B / (v["ms"] * 1e-3) / 1e12
-                peak = peaks["tflops_sustained"]
-                roof = {"kernel": "conv_gemm_kernel (tcgen05) — the 48 ViT-block GEMM launches",
+            peak = peaks["tflops_sustained"]
+            how = ("CUDA events around every launch on the launching stream, eager instrumented pass after the timed "
+                   "region (2 forwards averaged)")
+            g = agg.get("conv_gemm_all")
+            if g:
+                achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12
+                roof = {"kernel": f"conv_gemm_kernel (tcgen05 implicit GEMM) — ALL {int(g['launches'])} launches of a "
+                                  f"forward: every conv / linear layer of the network",
                         "bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
                         "frac": round(achieved / peak, 4),
-                        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four ViT GEMM
-                        # shapes, from the committed `ncu --set full` capture (profiles/r01d_vit_gemm_*.csv);
-                        # algorithmic bytes per launch (operands + output + residual, bf16): 131 MB
-                        "traffic": 92.8e6, "traffic_unit": "bytes/launch (ncu, profiles/r01d)",
-                        "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
-                        "avg_launch_ms": round(v["ms"] / v["launches"], 4),
-                        "how": "CUDA events around every launch on the launching stream, eager instrumented pass "
-                               "after the timed region (2 forwards averaged)"}
+                        "algorithmic_gflop_per_step": round(g["flops"] / 1e9, 1),
+                        "avg_launch_ms": round(g["ms"] / g["launches"], 4), "share_of_step": detail["conv_gemm_all"]["share"],
+                        "traffic": NCU_TRAFFIC.get("conv_gemm_all"), "traffic_unit": NCU_TRAFFIC.get("unit"),
+                        "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)", "how": how}
+            v = agg.get("vit_gemm")
+            if v:
+                achieved = VIT_GEMM_GFLOP_PER_IMAGE * 1e9 * chunk * len(models) / (v["ms"] * 1e-3) / 1e12
+                roof_vit = {"kernel": "conv_gemm_kernel — the 48 ViT-block GEMM launches only (qkv, proj, fc1, fc2)",
+                            "bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
+                            "frac": round(achieved / peak, 4), "avg_launch_ms": round(v["ms"] / v["launches"], 4)}
             u = agg.get("odb_upsample2x_add")
             if u and u["bytes"]:
                 gbs = u["bytes"] / (u["ms"] * 1e-3) / 1e9
@@ -347,49 +424,64 @@ def main():
                                       "kernel of the FeatureFusionBlock decoder and head (5 launches)",
                             "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": round(gbs / peaks["hbm_gbs"], 4),
-                            "traffic": 1.45e9, "traffic_unit": "bytes, largest launch (ncu, profiles/r01c): equals its "
-                                                               "algorithmic 0.30 GB read + 1.21 GB write",
                             "peak_source": f"{peaks['source']} copy bandwidth (MEASURED_PEAKS.json)"}
-            model.use_cuda_graph = not args.no_graph
+            for m in models:
+                m.use_cuda_graph = not args.no_graph
 
     images = B * world * args.steps
     value = images / (ms * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)
 
     if rank == 0:
+        nets = len(models)
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if not dual else "384x384 images/sec (DPT-Hybrid-384 depth + normal forward)",
+            "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: DPT-Hybrid-384 depth head, bf16, batch 32 per GPU, synthetic 384x384 RGB",
-                       "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world} (independent images)",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "index": args.config,
+                       "global_batch": B * world, "per_gpu_batch": B,
+                       "forward_chunk": chunk, "chunks_per_step": n_chunks, "networks": nets,
+                       "parallelism": f"dp{world} (independent images)",
                        "cuda_graph": not args.no_graph,
-                       "l2": "4 rotating input batches; per-step activation traffic >> 126 MB L2",
-                       "weights": "seeded synthetic (no checkpoint offline), NCCL-broadcast from rank 0"},
+                       "l2": f"{n_rot} rotating input batches; per-step activation traffic >> 126 MB L2",
+                       "residual_stream": "fp32 (ViT tokens), other activations bf16",
+                       "weights": "seeded synthetic (no checkpoint offline); packed bf16 form NCCL-broadcast from rank 0"},
             "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 4),
-                    "h2d_bytes_per_step": B * 3 * IMG * IMG * 4, "d2h_bytes_per_step": B * IMG * IMG * 4},
-            "gpu_launches": int(launches_per_fwd * args.steps),
-            "launches_per_step": int(launches_per_fwd),
+                    "h2d_bytes_per_step": B * 3 * IMG * IMG * 4,
+                    "d2h_bytes_per_step": B * IMG * IMG * 4 * (4 if dual else 1)},
+            "gpu_launches": int(launches_per_chunk * n_chunks * args.steps),
+            "launches_per_step": int(launches_per_chunk * n_chunks),
             "clocks": clocks,
-            "model_tflops": round(GFLOP_PER_IMAGE * 1e9 * value / 1e12, 2),
-            "model_frac_of_sustained_peak": round(GFLOP_PER_IMAGE * 1e9 * value / world / 1e12 / peaks["tflops_sustained"], 4),
-            "weight_broadcast": {"bytes": bcast_bytes, "ms": round(bcast_ms, 2)},
+            "model_tflops": round(GFLOP_PER_IMAGE * nets * 1e9 * value / 1e12, 2),
+            "model_frac_of_sustained_peak": round(GFLOP_PER_IMAGE * nets * 1e9 * value / world / 1e12 / peaks["tflops_sustained"], 4),
+            "weight_broadcast": {"bytes": bcast_bytes, "ms": round(bcast_ms, 2), "what": "packed bf16 kernel operands"},
             "roofline": roof,
+            "roofline_vit_blocks": roof_vit,
             "roofline_hbm": roof_hbm,
             "roofline_detail": detail,
         }
+        if world == 1 and not args.no_gpu_baseline and args.config == 1:
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_baseline(B, dev)
         if world == 1 and not args.no_cpu_baseline:
-            cores = pick_threads()
+            cores = min(os.cpu_count() or 1, 32)
             v, secs = cpu_forward_timer(args.cpu_batch, reps=3, threads=cores)
-            line["cpu_baseline"] = {"value": round(v, 3), "unit": "images/s", "cores": cores,
+            line["cpu_baseline"] = {"value": round(v / nets, 3), "unit": "images/s", "cores": cores,
                                     "host_cores": os.cpu_count(), "kind": "port",
                                     "cpu": cpu_model_name(),
                                     "sample": f"oracle fp32 forward (bit-identical to the reference module in the build "
                                               f"container), {args.cpu_batch} images, best of 3 after warm-up, "
-                                              f"{secs:.2f} s per pass"}
+                                              f"{secs:.2f} s per pass" + (" (one network timed, halved for two)" if dual else "")}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this round
+# (profiles/r02_*): filled by hand from the capture; None until a capture of the current build exists
+NCU_TRAFFIC = {"unit": "bytes per launch, mean over the launches captured (ncu --set full, profiles/r02_conv_gemm_ncu.csv)",
+               "conv_gemm_all": None}
 
 
 if __name__ == "__main__":

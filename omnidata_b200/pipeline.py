@@ -14,7 +14,11 @@ import torch
 
 
 class StreamingPredictor:
-    def __init__(self, model: torch.nn.Module, device: torch.device):
+    """`model`: a DPTDepthModel, or any callable mapping a device batch to one tensor or a list of tensors (e.g. the
+    depth and the normal network on the same images); `host_outputs[i % len]` is then a pinned tensor or a matching
+    list of pinned tensors."""
+
+    def __init__(self, model, device: torch.device):
         self.model = model
         self.device = device
         self.copy_in = torch.cuda.Stream(device)
@@ -54,8 +58,14 @@ class StreamingPredictor:
             consumed[k] = done
             with torch.cuda.stream(self.copy_out):
                 self.copy_out.wait_event(done)
-                host_outputs[i % len(host_outputs)].copy_(y, non_blocking=True)
-                y.record_stream(self.copy_out)
+                dst = host_outputs[i % len(host_outputs)]
+                if torch.is_tensor(y):
+                    ys, dsts = [y], [dst]
+                else:
+                    ys, dsts = list(y), list(dst)
+                for yy, dd in zip(ys, dsts):
+                    dd.copy_(yy, non_blocking=True)
+                    yy.record_stream(self.copy_out)
                 last_out = torch.cuda.Event()
                 last_out.record(self.copy_out)
             n += 1

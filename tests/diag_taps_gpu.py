@@ -57,5 +57,44 @@ for c in (1, 3):
     out[f"c{c}"] = rec
     for k, v in rec.items():
         print(c, k, {a: (f"{b:.3e}" if b is not None else None) for a, b in v.items()})
+
+# ---- golden-vector comparisons (what tests/test_model_gpu.py / test_model_large_gpu.py assert): sampled values
+GOLDEN = ROOT / "tests" / "golden"
+for c in (1, 3):
+    sd = weights.make_state_dict(0, c)
+    model = DPTDepthModel(num_channels=c); model.load_state_dict(sd); model = model.to(dev).eval(); model.keep_taps = True
+    with torch.no_grad():
+        y = model(make_golden.golden_input(1, seed=0).to(dev)).float().cpu()
+    got = {k: nchw(k, v) for k, v in model.taps.items()}
+    rec = torch.load(GOLDEN / f"dpt_fp32_seed0_c{c}.pt")
+    g = {"output_sub8": rel(y[..., ::8, ::8], rec["output_sub8"])}
+    for name, gv in rec["taps"].items():
+        if name in got:
+            t = got[name].reshape(-1)
+            g[name] = rel(t[make_golden.sample_indices(t.numel(), name)], gv["samples"])
+    out[f"c{c}"]["golden"] = g
+    print(c, "golden", {k: f"{v:.3e}" for k, v in g.items()})
+
+from omnidata_b200 import synthetic  # noqa
+from omnidata_b200.model import state_dict_spec  # noqa
+for backbone, fn in (("vitl16_384", "dpt_large_fp32_seed0_c1.pt"), ("vitb16_384", "dpt_vitb16_fp32_seed0_c1.pt")):
+    rec = torch.load(GOLDEN / fn)
+    model = DPTDepthModel(backbone=backbone)
+    model.load_state_dict(synthetic.make_state_dict(0, 1, spec=state_dict_spec(1, backbone=backbone)), strict=True)
+    model = model.to(dev).eval(); model.keep_taps = True
+    with torch.no_grad():
+        y = model(make_golden.golden_input(1, seed=0).to(dev)).float().cpu()
+    got = {k: nchw(k, v) for k, v in model.taps.items()}
+    g = {"output_sub8": rel(y[..., ::8, ::8], rec["output_sub8"])}
+    make_golden.N_SAMPLES = 4096
+    for name, gv in rec["taps"].items():
+        if name in got:
+            t = got[name].reshape(-1)
+            g[name] = rel(t[make_golden.sample_indices(t.numel(), name)], gv["samples"])
+    make_golden.N_SAMPLES = 256
+    out[backbone] = {"golden": g, "reference_bf16_drift": {k: float(v) for k, v in rec["bf16_drift"].items()},
+                     "reference_bf16_output_drift": float(rec["bf16_output_drift"])}
+    print(backbone, "golden", {k: f"{v:.3e}" for k, v in g.items()})
+    print(backbone, "reference's own bf16 drift", {k: f"{float(v):.3e}" for k, v in rec["bf16_drift"].items()})
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
 (ROOT / "gpurun_out" / "diag_taps.json").write_text(json.dumps(out, indent=1))

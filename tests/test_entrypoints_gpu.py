@@ -9,6 +9,10 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+# rel-L2 of the final (post-ReLU) map of the bf16 path against the fp32 oracle: fixed bound, seeds / sizes vary here
+# (tests/golden/bf16_ceilings.json holds the per-tap numbers for the golden input: 3.7e-2 depth, 2.1e-2 normal)
+BF16_OUTPUT_CEILING = 6e-2
 ROOT = Path(__file__).resolve().parents[1]
 
 
@@ -59,11 +63,16 @@ def test_depth_and_normal_models_side_by_side(lib_built):
     assert torch.equal(d1, d2) and torch.equal(n1, n2)
     with torch.no_grad():
         rd = dpt_oracle.forward_fp32(sds["depth"], x)
-        rd16 = dpt_oracle.forward_bf16(sds["depth"], x)
         rn = dpt_oracle.forward_fp32(sds["normal"], (x + 1) / 2)
-        rn16 = dpt_oracle.forward_bf16(sds["normal"], (x + 1) / 2)
-    assert rel(d1.float().cpu(), rd) <= 1.5 * rel(rd16, rd) + 1e-3
-    assert rel(n1.float().cpu(), rn) <= 1.5 * rel(rn16, rn) + 1e-3
+    # absolute bounds: bf16 production path (operand rounding; stock autocast shows 2-4e-2 on this architecture) ...
+    assert rel(d1.float().cpu(), rd) <= BF16_OUTPUT_CEILING
+    assert rel(n1.float().cpu(), rn) <= BF16_OUTPUT_CEILING
+    # ... and the fp32 correctness mode of the same two instances: the north star's 1e-5
+    for m in models.values():
+        m.precision = "fp32"
+    with torch.no_grad():
+        d3, n3 = models["depth"](xd), models["normal"](xn)
+    assert rel(d3.float().cpu(), rd) <= 1e-5 and rel(n3.float().cpu(), rn) <= 1e-5
 
 
 @pytest.mark.parametrize("size", [(256, 256), (320, 384)])
@@ -80,7 +89,9 @@ def test_other_input_sizes(lib_built, size):
     x = torch.rand(2, 3, *size, generator=g) * 2 - 1
     with torch.no_grad():
         y = m(x.cuda()).float().cpu()
+        m.precision = "fp32"
+        y_fp32 = m(x.cuda()).float().cpu()
         r32 = dpt_oracle.forward_fp32(sd, x)
-        r16 = dpt_oracle.forward_bf16(sd, x)
     assert y.shape == (2, *size)
-    assert rel(y, r32) <= 1.5 * rel(r16, r32) + 1e-3
+    assert rel(y, r32) <= BF16_OUTPUT_CEILING
+    assert rel(y_fp32, r32) <= 1e-5

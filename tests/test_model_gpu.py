@@ -1,17 +1,19 @@
-"""Whole-model parity of the CUDA path (through the C ABI) on the GPU box.
+"""Whole-model parity of the bf16 production path (through the C ABI) on the GPU box.
 
-/root/reference does not exist there; the checker is the oracle (pinned against the unmodified
-reference in the build container) plus the committed golden vectors.
+/root/reference does not exist there; the checkers are the oracle (pinned against the unmodified reference in the
+build container) and the committed golden vectors made by the unmodified reference.
 
-Tolerances (rel-L2 = ||a-b|| / ||b||), see DESIGN.md §4:
-  * first kernels of the chain (stem conv, stem pool) vs the bf16-rounding oracle: <= 2e-4 — the kernels are
-    exact up to rounding flips (tests/test_kernels_gpu.py shows the same for every kernel in isolation);
-  * deeper taps: two bf16 pipelines that differ by ANY fp32 summation order de-correlate: a perturbation e
-    before a bf16 rounding (ulp u) becomes sqrt(e*u) after it, so the mismatch converges towards the size of
-    independent rounding noise within a few layers.  The meaningful bounds are therefore relative to the
-    drift D the bf16-rounding oracle itself shows against fp32:  mismatch(kernel, bf16-oracle) <= D and
-    drift(kernel, fp32 oracle / reference golden) <= DRIFT_FACTOR x D.
-"""
+Every bound here is an ABSOLUTE, COMMITTED number: tests/golden/bf16_ceilings.json holds, per tap, the rel-L2
+(||a-b|| / ||b||) measured on a B200 by tests/diag_taps_gpu.py, times 1.2 (tests/make_ceilings.py).  Nothing is
+relative to a yardstick computed at test time, so a regression cannot hide inside a floating envelope:
+  * vs_fp32         production output vs the fp32 oracle (== the reference module's arithmetic);
+  * vs_bf16_oracle  production output vs oracle/dpt_oracle.py::forward_bf16 (same rounding points, different
+                    summation order — DESIGN.md section 4 explains why this cannot reach 1e-3 past the first layers);
+  * golden          production output vs the sampled values recorded from the UNMODIFIED reference.
+For orientation the file also records what stock `torch.autocast(bfloat16)` of the same network gives on the same
+GPU and weights (torch_autocast_vs_fp32); test_not_worse_than_stock_autocast re-measures that live.
+The fp32 correctness mode (1e-5) is tested in tests/test_fp32_mode_gpu.py."""
+import json
 from pathlib import Path
 
 import pytest
@@ -20,8 +22,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = Path(__file__).parent / "golden"
-FIRST_KERNELS_TOL = 2e-4
-DRIFT_FACTOR = 1.5
+CEIL = json.loads((GOLDEN / "bf16_ceilings.json").read_text())
 TAPS = ["layer_1", "layer_2", "tokens_8", "tokens_11", "layer_3", "layer_4", "layer_1_rn", "layer_2_rn",
         "layer_3_rn", "layer_4_rn", "path_4", "path_3", "path_2", "path_1"]
 
@@ -60,54 +61,65 @@ def setup(lib_built):
         with torch.no_grad():
             y32 = dpt_oracle.forward_fp32(sd, x, t32)
             y16 = dpt_oracle.forward_bf16(sd, x, t16)
-        res[c] = dict(model=model, x=x, y=y.float().cpu(), taps=got, y32=y32, y16=y16, t32=t32, t16=t16)
+        res[c] = dict(model=model, sd=sd, x=x, y=y.float().cpu(), taps=got, y32=y32, y16=y16, t32=t32, t16=t16)
     return res
 
 
 @pytest.mark.parametrize("c", [1, 3])
-def test_taps_match_bf16_rounding_oracle(setup, c):
-    r = setup[c]
-    report = []
-    for k in TAPS:
-        e16 = rel(r["taps"][k], r["t16"][k])
-        report.append(f"{k}: vs bf16-oracle {e16:.2e} (oracle drift vs fp32 {rel(r['t16'][k], r['t32'][k]):.2e})")
-    print("\n".join(report))
-    for k in ("stem_conv", "stem_pool"):
-        assert rel(r["taps"][k], r["t16"][k]) <= FIRST_KERNELS_TOL, (k, rel(r["taps"][k], r["t16"][k]))
-    for k in TAPS:
-        assert rel(r["taps"][k], r["t16"][k]) <= rel(r["t16"][k], r["t32"][k]), (k, report)
-    assert rel(r["y"], r["y16"]) <= rel(r["y16"], r["y32"]), ("output", rel(r["y"], r["y16"]))
+def test_taps_within_committed_ceilings_vs_fp32_oracle(setup, c):
+    r, ceil = setup[c], CEIL[f"hybrid_c{c}"]["vs_fp32"]
+    report = {k: rel(r["taps"][k], r["t32"][k]) for k in TAPS}
+    report["output"] = rel(r["y"], r["y32"])
+    print("\n".join(f"{k}: {v:.3e} (ceiling {ceil[k]:.3e})" for k, v in report.items()))
+    for k, v in report.items():
+        assert v <= ceil[k], (k, v, ceil[k])
+    assert tuple(r["y"].shape) == ((2, 384, 384) if c == 1 else (2, 3, 384, 384))
+    assert float(r["y"].min()) >= 0.0                       # final ReLU (non_negative=True)
 
 
 @pytest.mark.parametrize("c", [1, 3])
-def test_drift_vs_fp32_reference_is_stock_bf16_like(setup, c):
-    r = setup[c]
-    for k in TAPS:
-        mine = rel(r["taps"][k], r["t32"][k])
-        yard = rel(r["t16"][k], r["t32"][k])
-        assert mine <= DRIFT_FACTOR * yard + 1e-3, (k, mine, yard)
-    assert tuple(r["y"].shape) == ((2, 384, 384) if c == 1 else (2, 3, 384, 384))
-    assert float(r["y"].min()) >= 0.0                       # final ReLU (non_negative=True)
-    assert rel(r["y"], r["y32"]) <= DRIFT_FACTOR * rel(r["y16"], r["y32"]) + 1e-3
+def test_taps_within_committed_ceilings_vs_bf16_rounding_oracle(setup, c):
+    r, ceil = setup[c], CEIL[f"hybrid_c{c}"]["vs_bf16_oracle"]
+    report = {k: rel(r["taps"][k], r["t16"][k]) for k in TAPS + ["stem_conv", "stem_pool"]}
+    report["output"] = rel(r["y"], r["y16"])
+    for k, v in report.items():
+        assert v <= ceil[k], (k, v, ceil[k])
+    # the first kernels of the chain are exact up to rounding flips
+    assert report["stem_conv"] <= 2e-4 and report["stem_pool"] <= 2e-4
 
 
 @pytest.mark.parametrize("c", [1, 3])
 def test_against_reference_golden_vectors(setup, c):
     """Image 0 is the golden input: compare with what the UNMODIFIED reference produced."""
     from oracle import make_golden
-    r = setup[c]
+    r, ceil = setup[c], CEIL[f"hybrid_c{c}"]["golden"]
     rec = torch.load(GOLDEN / f"dpt_fp32_seed0_c{c}.pt")
-    ref = rec["output_sub8"]
-    got = r["y"][:1][..., ::8, ::8]
-    yard = rel(r["y16"][:1][..., ::8, ::8], ref)
-    assert rel(got, ref) <= DRIFT_FACTOR * yard + 1e-3
+    assert rel(r["y"][:1][..., ::8, ::8], rec["output_sub8"]) <= ceil["output_sub8"]
+    checked = 0
     for name, g in rec["taps"].items():
         if name not in r["taps"]:
             continue
         t = r["taps"][name][:1].reshape(-1)
         idx = make_golden.sample_indices(t.numel(), name)
-        yard = rel(r["t16"][name][:1].reshape(-1)[idx], g["samples"])
-        assert rel(t[idx], g["samples"]) <= DRIFT_FACTOR * yard + 2e-3, name
+        assert rel(t[idx], g["samples"]) <= ceil[name], name
+        checked += 1
+    assert checked >= 12
+
+
+def test_not_worse_than_stock_autocast(setup):
+    """The GPU yardstick: the reference network under torch.autocast(bfloat16) on this GPU with the
+    same weights and input.  The production path must not drift further from fp32 than stock autocast does
+    (measured on B200: equal to within 5 % at every tap; both are bounded by bf16 operand rounding)."""
+    from oracle import dpt_oracle
+    r = setup[1]
+    sdg = {k: v.cuda() for k, v in r["sd"].items()}
+    tac = {}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        yac = dpt_oracle.forward_fp32(sdg, r["x"].cuda(), tac).float().cpu()
+    for k in TAPS:
+        mine, stock = rel(r["taps"][k], r["t32"][k]), rel(tac[k].float().cpu(), r["t32"][k])
+        assert mine <= 1.10 * stock, (k, mine, stock)
+    assert rel(r["y"], r["y32"]) <= 1.10 * rel(yac, r["y32"])
 
 
 def test_cuda_graph_replay_equals_eager_and_outputs_are_fresh(setup):
