@@ -138,8 +138,9 @@ int odb_layernorm(const void* x, const float* gamma, const float* beta, void* y,
 /* Fused multi-head attention (timm Attention.forward): qkv bf16 [b][tokens][3][heads][64] as written
  * by the qkv linear; out bf16 [b][tokens][heads*64]; softmax(q k^T * scale) v.  tcgen05 kernel:
  * S and O accumulate in TMEM, exact two-pass fp32 softmax (global row maximum), P rounded to bf16
- * for the PV product, fp32 row sum of the unrounded P.  tokens <= 640. */
-int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads, float scale,
+ * for the PV product, fp32 row sum of the unrounded P.  tokens <= 640.  lse (optional, training): fp32
+ * [b][heads][tokens] = log2 of the row's sum of exp2(s * scale * log2 e), what odb_attention_bwd re-normalises with. */
+int odb_attention(const void* qkv, void* out, float* lse, int32_t b, int32_t tokens, int32_t heads, float scale,
                   void* stream);
 /* fp32 correctness mode of odb_attention: qkv fp32 [b][tokens][3][heads][64], out fp32 [b][tokens][heads*64];
  * dot products and the PV sum in fp64, exp / division exact (no fast-math). */
@@ -211,6 +212,96 @@ int odb_readout_cls_bias(const void* w, const float* bias, const void* tokens, f
 /* dst bf16[n] = round(src fp32[n]) (n a multiple of 8): the hooked ViT activations (M/vit.py:158-165 `get_activation`)
  * leave the fp32 residual stream as bf16 operands of the readout GEMM. */
 int odb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* =====================================================================================================
+ * Backward of the network (train_depth.py:183-190 training_step -> loss.backward(); PL runs autograd over
+ * the reference modules).  dgrad of every conv / linear layer is odb_conv_gemm itself with the re-packed
+ * (in/out swapped, 180-degree rotated) weight from odb_pack_weight; the entry points below are the rest.
+ * `dtype` is the storage type of activations and activation gradients; statistics, affine parameters,
+ * parameter gradients and the ViT residual-stream gradient are fp32.  All reductions have a fixed order.
+ * ===================================================================================================== */
+
+/* Weight gradient of a convolution / linear layer described like odb_conv_gemm (views + taps):
+ *   out[n][t * C + c] (+)= sum_{b,y,x} dy[b,y,x,n] * view[tap_view[t]][b, y + tap_dy[t], x + tap_dx[t], c]
+ * i.e. the gradient in the PACKED weight layout of odb_conv_gemm (fp32).  bf16: tcgen05 kernel with both
+ * operands MN-major straight from the channels-last tensors (the 128-byte-swizzled TMA box of 64 pixels x 64
+ * channels that feeds the forward as a K-major A tile IS the MN-major operand of the transposed product),
+ * split over the pixel range, fp32 partials in `workspace`, ordered reduction.  fp32: FP32-pipe twin. */
+typedef struct odb_wgrad_desc {
+  int32_t num_views;
+  odb_view views[ODB_MAX_VIEWS];
+  int32_t num_taps;
+  int8_t tap_view[ODB_MAX_TAPS];
+  int8_t tap_dx[ODB_MAX_TAPS];
+  int8_t tap_dy[ODB_MAX_TAPS];
+  odb_view dy;            /* c = n; w, h, b = the layer's output extent */
+  int32_t n;
+  float* out;             /* fp32 [n][num_taps * C] */
+  void* workspace;        /* split partials */
+  int64_t workspace_bytes;
+  int32_t accumulate;     /* add to `out` instead of overwriting */
+  int32_t dtype;          /* odb_dtype of views and dy */
+} odb_wgrad_desc;
+int64_t odb_conv_wgrad_workspace_bytes(const odb_wgrad_desc* desc);
+int odb_conv_wgrad(const odb_wgrad_desc* desc, void* stream);
+
+/* Backward of odb_attention (timm Attention.forward): dqkv [b][tokens][3][heads][64] from qkv, the forward output o
+ * [b][tokens][heads*64], its gradient d_o, and (bf16 path) the per-row log2-sum-exp `lse` fp32 [b][heads][tokens]
+ * that odb_attention wrote.  bf16: P and dS are re-materialised per (image, head) by tcgen05 GEMMs with fused
+ * softmax / dS epilogues, dQ / dK / dV are three more batched GEMMs; fp32: FP32-pipe twin (lse unused). */
+int64_t odb_attention_bwd_workspace_bytes(int32_t b, int32_t tokens, int32_t heads, int32_t dtype);
+int odb_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, void* workspace,
+                      int64_t workspace_bytes, int32_t b, int32_t tokens, int32_t heads, float scale, int32_t dtype,
+                      void* stream);
+
+/* out = a + b * [mask > 0]   (a, mask optional): ReLU backward and gradient accumulation; n elements (multiple of 8). */
+int odb_mask_add(const void* a, const void* b, const void* mask, void* out, int64_t n, int32_t dtype, void* stream);
+/* exact-erf GELU (nn.GELU() default) forward on a stored pre-activation, and its backward du = dy * gelu'(u). */
+int odb_gelu_fwd(const void* u, void* y, int64_t n, int32_t dtype, void* stream);
+int odb_gelu_bwd(const void* dy, const void* u, void* du, int64_t n, int32_t dtype, void* stream);
+/* Bias gradients: out[bt][n] (+)= sum over rows of x[bt][row][n] (row / batch strides in elements). */
+int64_t odb_colsum_workspace_bytes(int32_t batches, int32_t n);
+int odb_colsum(const void* x, float* out, void* workspace, int32_t batches, int64_t rows_per_batch, int32_t n,
+               int64_t row_stride, int64_t batch_stride, int32_t accumulate, int32_t dtype, void* stream);
+/* out[bt][i] (+)= sum_p partial[bt][p][i] in fp64, p ascending. */
+int odb_reduce_partials(const float* partial, float* out, int32_t batches, int32_t parts, int64_t n, int32_t accumulate,
+                        void* stream);
+/* LayerNorm backward on the fp32 residual stream: ds_out = ds_in + dLN(dy; x, gamma) (ds_in may be NULL), optional
+ * copy of ds_out in `dtype` (the next GEMM operand), dgamma / dbeta (+)=. */
+int64_t odb_layernorm_bwd_workspace_bytes(int32_t cols);
+int odb_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* ds_in, float* ds_out, void* ds_copy,
+                      float* dgamma, float* dbeta, void* workspace, int64_t rows, int32_t cols, float eps,
+                      int32_t accumulate, int32_t dtype, void* stream);
+/* GroupNorm backward (timm GroupNormAct): g = dy * [mask > 0] (mask NULL: g = dy; the mask is the stored output of the
+ * ReLU that follows the norm); dx, dgamma (+)=, dbeta (+)= from x and the forward statistics (mean, rstd). */
+int64_t odb_groupnorm_bwd_workspace_bytes(int32_t b, int32_t hw, int32_t c, int32_t groups);
+int odb_groupnorm_bwd(const void* dy, const void* mask, const void* x, const float* stats, const float* gamma, void* dx,
+                      float* dgamma, float* dbeta, void* workspace, int32_t b, int32_t hw, int32_t c, int32_t groups,
+                      int32_t accumulate, int32_t dtype, void* stream);
+/* Adjoint of odb_upsample2x_add's bilinear part: dz [b][h][w][c] from dout [b][2h][2w][c]. */
+int odb_upsample2x_bwd(const void* dout, void* dz, int32_t b, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream);
+/* Backward of odb_stem_gn_relu_maxpool down to the GroupNorm output: g_s0 [b][h][w][c] = gradient w.r.t. gn(s0), already
+ * masked by the ReLU; the pooling gradient goes to the first maximum of each window (torch semantics). */
+int odb_stem_pool_bwd(const void* dt, const void* s0, const float* stats, const float* gamma, const float* beta, void* g_s0,
+                      int32_t b, int32_t h, int32_t w, int32_t c, int32_t groups, int32_t dtype, void* stream);
+/* DPT head tail, unfused (training): out[b][k][y][x] = relu?(bias[k] + sum_j w[k][j] a[b][y][x][j]), a has
+ * channel_stride channels per pixel of which the first 32 are used; and its backward (da zero in the padding channels). */
+int odb_head_tail_fwd(const void* a, int32_t channel_stride, const float* w, const float* bias, float* out, int32_t b,
+                      int32_t h, int32_t wd, int32_t head_c, int32_t relu, int32_t dtype, void* stream);
+int64_t odb_head_tail_bwd_workspace_bytes(int32_t head_c);
+int odb_head_tail_bwd(const float* dout, const float* out, const void* a, int32_t channel_stride, const float* w, void* da,
+                      float* dw, float* dbias, void* workspace, int32_t b, int32_t h, int32_t wd, int32_t head_c,
+                      int32_t relu, int32_t accumulate, int32_t dtype, void* stream);
+/* ds_out (fp32) = ds_in (fp32, optional) + g (`dtype`); optional copy of ds_out in `dtype`. */
+int odb_add_cast(const float* ds_in, const void* g, float* ds_out, void* copy, int64_t n, int32_t dtype, void* stream);
+/* Per-step weight packing: w fp32 [n][c][taps] (optionally weight-standardised, timm StdConv2dSame eps) ->
+ * fwd `dtype` [n_pad][taps * c_pad] (odb_conv_gemm weight) and bwd `dtype` [c_pad][taps * n_pad] (dgrad weight). */
+int odb_pack_weight(const float* w, void* fwd, void* bwd, int32_t n, int32_t c, int32_t taps, int32_t n_pad, int32_t c_pad,
+                    int32_t standardize, float eps, int32_t dtype, void* stream);
+/* Packed-layout weight gradient gp fp32 [n][taps * c_pad] -> parameter layout dw fp32 [n][c][taps], through the weight
+ * standardisation when `standardize` (w = the fp32 parameter). */
+int odb_unpack_wgrad(const float* gp, const float* w, float* dw, int32_t n, int32_t c, int32_t taps, int32_t c_pad,
+                     int32_t standardize, float eps, void* stream);
 
 /* ---- depth-training losses (train_depth.py:261-279), forward and (odb_*_bwd) backward with respect to the
  * prediction; all tensors fp32 [b][h][w] ------- */

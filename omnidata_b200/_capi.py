@@ -62,6 +62,24 @@ class ConvGemmDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("num_views", C.c_int32),
+        ("views", View * ODB_MAX_VIEWS),
+        ("num_taps", C.c_int32),
+        ("tap_view", C.c_int8 * ODB_MAX_TAPS),
+        ("tap_dx", C.c_int8 * ODB_MAX_TAPS),
+        ("tap_dy", C.c_int8 * ODB_MAX_TAPS),
+        ("dy", View),
+        ("n", C.c_int32),
+        ("out", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
+        ("accumulate", C.c_int32),
+        ("dtype", C.c_int32),
+    ]
+
+
 _SIGNATURES = {
     "odb_conv_gemm": (C.c_int, [C.POINTER(ConvGemmDesc), C.c_void_p]),
     "odb_conv_gemm_plan": (C.c_int, [C.POINTER(ConvGemmDesc), C.POINTER(C.c_int32)]),
@@ -69,7 +87,7 @@ _SIGNATURES = {
                                          C.c_float, C.c_void_p]),
     "odb_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                 C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
-    "odb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+    "odb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p]),
     "odb_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_void_p]),
@@ -87,6 +105,30 @@ _SIGNATURES = {
     "odb_write_cls_row": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p]),
     "odb_readout_cls_bias": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p]),
     "odb_cast_f32_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "odb_conv_wgrad_workspace_bytes": (C.c_int64, [C.POINTER(WgradDesc)]),
+    "odb_conv_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "odb_attention_bwd_workspace_bytes": (C.c_int64, [C.c_int32] * 4),
+    "odb_attention_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                                       C.c_void_p]),
+    "odb_mask_add": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p]),
+    "odb_gelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "odb_gelu_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p]),
+    "odb_colsum_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "odb_colsum": (C.c_int, [C.c_void_p] * 3 + [C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                                C.c_void_p]),
+    "odb_reduce_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "odb_layernorm_bwd_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "odb_layernorm_bwd": (C.c_int, [C.c_void_p] * 9 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
+    "odb_groupnorm_bwd_workspace_bytes": (C.c_int64, [C.c_int32] * 4),
+    "odb_groupnorm_bwd": (C.c_int, [C.c_void_p] * 9 + [C.c_int32] * 6 + [C.c_void_p]),
+    "odb_upsample2x_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
+    "odb_stem_pool_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int32] * 6 + [C.c_void_p]),
+    "odb_head_tail_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 6 + [C.c_void_p]),
+    "odb_head_tail_bwd_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "odb_head_tail_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 5 + [C.c_int32] * 7 + [C.c_void_p]),
+    "odb_add_cast": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p]),
+    "odb_pack_weight": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 6 + [C.c_float, C.c_int32, C.c_void_p]),
+    "odb_unpack_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
     "odb_make_valid_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "odb_midas_loss_workspace_bytes": (C.c_int64, [C.c_int32]),
     "odb_midas_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,

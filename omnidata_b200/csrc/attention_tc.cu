@@ -38,6 +38,7 @@ static_assert(kTcSmemBytes <= 232448, "attention smem plan exceeds 227 KiB");
 struct AttnTcParams {
   CUtensorMap qkv_map;   // dims {64 d, 3*heads, tokens, batch}; box {64, 1, 128, 1}
   bf16* out;
+  float* lse;            // optional [batch][heads][tokens]: log2 sum_j exp2(s_j c) per query row (training)
   int tokens, heads, batch;
   float scale_log2e;
   unsigned long long* trace;   // diagnostics: per CTA kTraceSlots stamps; per q tile i < 8 at 8 + 12 i:
@@ -271,7 +272,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         }
         xsum[half * 128 + row] = l;
         named_bar_sync(1, kTcSoftmaxThreads);
-        const float inv = 1.0f / (xsum[row] + xsum[128 + row]);
+        const float lsum = xsum[row] + xsum[128 + row];
+        const float inv = 1.0f / lsum;
+        if (p.lse != nullptr && half == 0 && qt * kTcBlk + row < p.tokens)
+          p.lse[((long long)b * p.heads + h) * p.tokens + qt * kTcBlk + row] = mc + log2f(lsum);
         ODB_ATRACE(qt_iter, 7);
         // ---- epilogue: O / l -> bf16 -> global (each thread: 32 of the 64 head dims of its row)
         mbar_wait(o_full, qt_iter & 1u);
@@ -313,8 +317,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
 
 using namespace odb;
 
-extern "C" int odb_attention(const void* qkv, void* out, int32_t b, int32_t tokens, int32_t heads,
-                                float scale, void* stream_) {
+extern "C" int odb_attention(const void* qkv, void* out, float* lse, int32_t b, int32_t tokens, int32_t heads,
+                             float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!qkv || !out || b < 1 || heads < 1 || tokens < 1)
     return fail(ODB_ERR_INVALID, "attention: bad argument");
@@ -332,6 +336,7 @@ extern "C" int odb_attention(const void* qkv, void* out, int32_t b, int32_t toke
     if (rc) return rc;
   }
   p.out = static_cast<bf16*>(out);
+  p.lse = lse;
   p.tokens = tokens; p.heads = heads; p.batch = b;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.trace = debug_trace();

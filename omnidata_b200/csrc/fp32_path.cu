@@ -318,3 +318,283 @@ extern "C" int odb_head_tail_f32(const float* x, const float* w, const float* bi
   count_launch();
   return check_launch("head_tail_f32");
 }
+
+// ============================================================================================ backward, fp32 mode
+namespace odb {
+
+// ---- weight gradient of a (strided / multi-view) convolution:  out[n][t * C + c] = sum_{b,y,x} dY[b,y,x,n] * X_t[b,y+dy,x+dx,c]
+// 64 x 64 tile of (n, c) per CTA and tap; the pixel range is split over gridDim.z, each split writing its own fp32
+// partial (ordered reduction afterwards).  K blocks of 32 pixels in fp32, block sums combined in fp64.
+struct WgradF32Params {
+  const float* view[ODB_MAX_VIEWS];
+  int vw[ODB_MAX_VIEWS], vh[ODB_MAX_VIEWS];
+  long long vsx[ODB_MAX_VIEWS], vsy[ODB_MAX_VIEWS], vsb[ODB_MAX_VIEWS];
+  int C, num_taps;
+  int8_t tap_view[ODB_MAX_TAPS], tap_dx[ODB_MAX_TAPS], tap_dy[ODB_MAX_TAPS];
+  const float* dy; long long dsx, dsy, dsb;
+  int N, ow, oh, ob;
+  float* partial;            // [splits][N][taps * C]
+  long long pixels_per_split;
+};
+
+__global__ void __launch_bounds__(256) wgrad_f32_kernel(const __grid_constant__ WgradF32Params p) {
+  __shared__ float As[kF32BK][kF32BM + kF32Pad];   // [pixel][n]
+  __shared__ float Bs[kF32BK][kF32BN + kF32Pad];   // [pixel][c]
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int n0 = blockIdx.x * 64;
+  const int c_tiles = (p.C + 63) / 64;
+  const int tap = blockIdx.y / c_tiles, c0 = (blockIdx.y % c_tiles) * 64;
+  const int v = p.tap_view[tap];
+  const long long M = (long long)p.ob * p.oh * p.ow;
+  const long long m_begin = (long long)blockIdx.z * p.pixels_per_split;
+  const long long m_end = min(M, m_begin + p.pixels_per_split);
+  double accd[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accd[i][j] = 0.0;
+  // staging: thread -> (pixel 0..31, 8 consecutive channels)
+  const int lp = t >> 3, lc = (t & 7) * 8;
+  for (long long mb = m_begin; mb < m_end; mb += kF32BK) {
+    const long long m = mb + lp;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (m < m_end) {
+      const int x = (int)(m % p.ow), y = (int)((m / p.ow) % p.oh), bi = (int)(m / ((long long)p.ow * p.oh));
+      if (n0 + lc < p.N) {
+        const float* src = p.dy + bi * p.dsb + y * p.dsy + x * p.dsx + n0 + lc;
+        const float4 u0 = *reinterpret_cast<const float4*>(src);
+        a[0] = u0.x; a[1] = u0.y; a[2] = u0.z; a[3] = u0.w;
+        if (n0 + lc + 4 < p.N) {
+          const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
+          a[4] = u1.x; a[5] = u1.y; a[6] = u1.z; a[7] = u1.w;
+        }
+      }
+      const int yy = y + p.tap_dy[tap], xx = x + p.tap_dx[tap];
+      if (yy >= 0 && yy < p.vh[v] && xx >= 0 && xx < p.vw[v] && c0 + lc < p.C) {
+        const float* src = p.view[v] + bi * p.vsb[v] + yy * p.vsy[v] + xx * p.vsx[v] + c0 + lc;
+        const float4 u0 = *reinterpret_cast<const float4*>(src);
+        b[0] = u0.x; b[1] = u0.y; b[2] = u0.z; b[3] = u0.w;
+        if (c0 + lc + 4 < p.C) {
+          const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
+          b[4] = u1.x; b[5] = u1.y; b[6] = u1.z; b[7] = u1.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { As[lp][lc + j] = a[j]; Bs[lp][lc + j] = b[j]; }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kF32BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) accd[i][j] += (double)acc[i][j];
+    __syncthreads();
+  }
+  const long long row_len = (long long)p.num_taps * p.C;
+  float* dst = p.partial + (long long)blockIdx.z * p.N * row_len;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= p.N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + tx * 4 + j;
+      if (c < p.C) dst[n * row_len + (long long)tap * p.C + c] = (float)accd[i][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_splits_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                         int splits, long long n, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double t = 0.0;
+    for (int s = 0; s < splits; ++s) t += (double)partial[(long long)s * n + i];
+    if (accumulate) t += (double)out[i];
+    out[i] = (float)t;
+  }
+}
+
+int conv_wgrad_f32(const odb_wgrad_desc* d, cudaStream_t stream) {
+  WgradF32Params p;
+  memset(&p, 0, sizeof(p));
+  p.C = d->views[0].c;
+  if (p.C % 8 != 0 || d->n % 8 != 0) return fail(ODB_ERR_INVALID, "conv_wgrad (fp32 mode): C and n must be multiples of 8");
+  for (int v = 0; v < d->num_views; ++v) {
+    if (!view_ok(d->views[v]) || d->views[v].c != p.C) return fail(ODB_ERR_INVALID, "conv_wgrad (fp32 mode): bad view");
+    p.view[v] = static_cast<const float*>(d->views[v].ptr);
+    p.vw[v] = d->views[v].w; p.vh[v] = d->views[v].h;
+    fill_strides(d->views[v], &p.vsx[v], &p.vsy[v], &p.vsb[v]);
+  }
+  p.num_taps = d->num_taps;
+  for (int t = 0; t < d->num_taps; ++t) { p.tap_view[t] = d->tap_view[t]; p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t]; }
+  if (!view_ok(d->dy) || d->dy.c != d->n) return fail(ODB_ERR_INVALID, "conv_wgrad (fp32 mode): bad dy view");
+  p.dy = static_cast<const float*>(d->dy.ptr);
+  fill_strides(d->dy, &p.dsx, &p.dsy, &p.dsb);
+  p.N = d->n; p.ow = d->dy.w; p.oh = d->dy.h; p.ob = d->dy.b;
+  const long long M = (long long)p.ob * p.oh * p.ow;
+  const long long row_len = (long long)p.num_taps * p.C;
+  const long long tiles = (long long)((p.N + 63) / 64) * ((p.C + 63) / 64) * p.num_taps;
+  long long splits = (4LL * num_sms() + tiles - 1) / tiles;
+  const long long max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 256) splits = 256;
+  if (splits < 1) splits = 1;
+  if ((long long)d->workspace_bytes < splits * p.N * row_len * 4) {
+    splits = d->workspace_bytes / (p.N * row_len * 4);
+    if (splits < 1) return fail(ODB_ERR_INVALID, "conv_wgrad (fp32 mode): workspace too small (need >= n * taps * C * 4 bytes)");
+  }
+  p.pixels_per_split = ((M + splits - 1) / splits + kF32BK - 1) / kF32BK * kF32BK;
+  p.partial = static_cast<float*>(d->workspace);
+  dim3 grid((p.N + 63) / 64, ((p.C + 63) / 64) * p.num_taps, (unsigned)splits);
+  wgrad_f32_kernel<<<grid, 256, 0, stream>>>(p);
+  count_launch();
+  const long long total = p.N * row_len;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  sum_splits_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p.partial, d->out, (int)splits, total, d->accumulate);
+  count_launch();
+  return check_launch("conv_wgrad (fp32 mode)");
+}
+
+// ---- attention backward, fp32: kernel 1 per (16 queries, head, image): recompute P, dP, dS; write P and dS to the
+// workspace and dQ; kernel 2 per (16 keys, head, image): dK = dS^T Q, dV = P^T dO.
+__global__ void __launch_bounds__(256) attention_bwd_q_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ o,
+                                                                  const float* __restrict__ d_o, float* __restrict__ dqkv,
+                                                                  float* __restrict__ pws, float* __restrict__ dsws,
+                                                                  int tokens, int heads, float scale) {
+  extern __shared__ float att_smem[];
+  float (*q_s)[64] = reinterpret_cast<float (*)[64]>(att_smem);
+  float (*do_s)[64] = reinterpret_cast<float (*)[64]>(att_smem + kAttQ * 64);
+  float (*s_s)[kAttMaxTok] = reinterpret_cast<float (*)[kAttMaxTok]>(att_smem + 2 * kAttQ * 64);                 // S -> P
+  float (*g_s)[kAttMaxTok] = reinterpret_cast<float (*)[kAttMaxTok]>(att_smem + 2 * kAttQ * 64 + kAttQ * kAttMaxTok);  // dP -> dS
+  float* dd_s = att_smem + 2 * kAttQ * 64 + 2 * kAttQ * kAttMaxTok;
+  const int t = threadIdx.x;
+  const int q0 = blockIdx.x * kAttQ, h = blockIdx.y, b = blockIdx.z;
+  const long long rs = 3LL * heads * 64;
+  const float* base = qkv + (long long)b * tokens * rs + h * 64;
+  const long long orow = (long long)heads * 64;
+  for (int i = t; i < kAttQ * 64; i += 256) {
+    const int r = i >> 6, d = i & 63;
+    const bool ok = q0 + r < tokens;
+    q_s[r][d] = ok ? base[(long long)(q0 + r) * rs + d] : 0.f;
+    do_s[r][d] = ok ? d_o[((long long)b * tokens + q0 + r) * orow + h * 64 + d] : 0.f;
+  }
+  __syncthreads();
+  if (t < kAttQ) {
+    double acc = 0.0;
+    if (q0 + t < tokens)
+      for (int d = 0; d < 64; ++d) acc += (double)do_s[t][d] * (double)o[((long long)b * tokens + q0 + t) * orow + h * 64 + d];
+    dd_s[t] = (float)acc;
+  }
+  for (int idx = t; idx < kAttQ * tokens; idx += 256) {
+    const int r = idx & (kAttQ - 1), j = idx / kAttQ;
+    const float* kr = base + (long long)j * rs + heads * 64;
+    const float* vr = base + (long long)j * rs + 2 * heads * 64;
+    double a = 0.0, g = 0.0;
+#pragma unroll 16
+    for (int d = 0; d < 64; ++d) { a += (double)q_s[r][d] * (double)kr[d]; g += (double)do_s[r][d] * (double)vr[d]; }
+    s_s[r][j] = (float)a * scale;
+    g_s[r][j] = (float)g;
+  }
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  for (int r = warp; r < kAttQ; r += 8) {
+    float mx = -INFINITY;
+    for (int j = lane; j < tokens; j += 32) mx = fmaxf(mx, s_s[r][j]);
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    double sum = 0.0;
+    for (int j = lane; j < tokens; j += 32) { const float e = expf(s_s[r][j] - mx); s_s[r][j] = e; sum += (double)e; }
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = (float)(1.0 / sum);
+    const float dd = dd_s[r];
+    const bool ok = q0 + r < tokens;
+    float* prow = pws + (((long long)b * heads + h) * tokens + q0 + r) * tokens;
+    float* drow = dsws + (((long long)b * heads + h) * tokens + q0 + r) * tokens;
+    for (int j = lane; j < tokens; j += 32) {
+      const float pj = s_s[r][j] * inv;
+      const float ds = pj * (g_s[r][j] - dd) * scale;
+      g_s[r][j] = ds;
+      if (ok) { prow[j] = pj; drow[j] = ds; }
+    }
+  }
+  __syncthreads();
+  const int r = t >> 4, d4 = (t & 15) * 4;
+  if (q0 + r < tokens) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const float* kb = base + heads * 64 + d4;
+    for (int j = 0; j < tokens; ++j) {
+      const double ds = (double)g_s[r][j];
+      const float4 kv = *reinterpret_cast<const float4*>(kb + (long long)j * rs);
+      a0 += ds * (double)kv.x; a1 += ds * (double)kv.y; a2 += ds * (double)kv.z; a3 += ds * (double)kv.w;
+    }
+    float* dst = dqkv + ((long long)b * tokens + q0 + r) * rs + h * 64 + d4;
+    *reinterpret_cast<float4*>(dst) = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
+  }
+}
+
+__global__ void __launch_bounds__(256) attention_bwd_kv_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o,
+                                                                   const float* __restrict__ pws, const float* __restrict__ dsws,
+                                                                   float* __restrict__ dqkv, int tokens, int heads) {
+  // thread -> (key row r of 16, 4 head dims)
+  const int t = threadIdx.x;
+  const int j0 = blockIdx.x * kAttQ, h = blockIdx.y, b = blockIdx.z;
+  const int r = t >> 4, d4 = (t & 15) * 4;
+  const int j = j0 + r;
+  if (j >= tokens) return;
+  const long long rs = 3LL * heads * 64, orow = (long long)heads * 64;
+  const float* qb = qkv + (long long)b * tokens * rs + h * 64 + d4;
+  const float* dob = d_o + (long long)b * tokens * orow + h * 64 + d4;
+  const float* pcol = pws + ((long long)b * heads + h) * tokens * tokens + j;
+  const float* dcol = dsws + ((long long)b * heads + h) * tokens * tokens + j;
+  double k0 = 0, k1 = 0, k2 = 0, k3 = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+  for (int q = 0; q < tokens; ++q) {
+    const double ds = (double)dcol[(long long)q * tokens], pj = (double)pcol[(long long)q * tokens];
+    const float4 qv = *reinterpret_cast<const float4*>(qb + (long long)q * rs);
+    const float4 dv = *reinterpret_cast<const float4*>(dob + (long long)q * orow);
+    k0 += ds * (double)qv.x; k1 += ds * (double)qv.y; k2 += ds * (double)qv.z; k3 += ds * (double)qv.w;
+    v0 += pj * (double)dv.x; v1 += pj * (double)dv.y; v2 += pj * (double)dv.z; v3 += pj * (double)dv.w;
+  }
+  float* dk = dqkv + ((long long)b * tokens + j) * rs + heads * 64 + h * 64 + d4;
+  float* dv_ = dqkv + ((long long)b * tokens + j) * rs + 2 * heads * 64 + h * 64 + d4;
+  *reinterpret_cast<float4*>(dk) = make_float4((float)k0, (float)k1, (float)k2, (float)k3);
+  *reinterpret_cast<float4*>(dv_) = make_float4((float)v0, (float)v1, (float)v2, (float)v3);
+}
+
+int attention_bwd_f32(const float* qkv, const float* o, const float* d_o, float* dqkv, void* workspace,
+                      long long workspace_bytes, int b, int tokens, int heads, float scale, cudaStream_t stream) {
+  const long long need = 2LL * b * heads * tokens * tokens * 4;
+  if (workspace == nullptr || workspace_bytes < need) return fail(ODB_ERR_INVALID, "attention_bwd (fp32 mode): workspace too small");
+  if (tokens > kAttMaxTok) return fail(ODB_ERR_UNSUPPORTED, "attention_bwd (fp32 mode): at most 640 tokens");
+  float* pws = static_cast<float*>(workspace);
+  float* dsws = pws + (long long)b * heads * tokens * tokens;
+  dim3 grid((tokens + kAttQ - 1) / kAttQ, heads, b);
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  constexpr int kSmem = (2 * kAttQ * 64 + 2 * kAttQ * kAttMaxTok + kAttQ) * 4;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_q_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return fail_cuda(e, "attention_bwd (fp32 mode): cudaFuncSetAttribute");
+    configured[dev] = true;
+  }
+  attention_bwd_q_f32_kernel<<<grid, 256, kSmem, stream>>>(qkv, o, d_o, dqkv, pws, dsws, tokens, heads, scale);
+  count_launch();
+  attention_bwd_kv_f32_kernel<<<grid, 256, 0, stream>>>(qkv, d_o, pws, dsws, dqkv, tokens, heads);
+  count_launch();
+  return check_launch("attention_bwd (fp32 mode)");
+}
+
+}  // namespace odb

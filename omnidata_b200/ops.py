@@ -246,7 +246,7 @@ def layernorm(x, gamma, beta, out, eps: float = 1e-6):
           out.data_ptr(), rows, x.shape[-1], eps, _dt(x, "x"), _dt(out, "out"))
 
 
-def attention(qkv, out, heads: int = 12, scale: float = 0.125):
+def attention(qkv, out, heads: int = 12, scale: float = 0.125, lse=None):
     b, n, c3 = qkv.shape
     if not (qkv.is_contiguous() and out.is_contiguous()) or c3 != 3 * heads * 64:
         raise _capi.OdbError("attention: qkv must be contiguous [B, tokens, 3*heads*64]")
@@ -257,8 +257,10 @@ def attention(qkv, out, heads: int = 12, scale: float = 0.125):
               b, n, heads, scale)
         return
     _need(qkv, torch.bfloat16, "qkv"); _need(out, torch.bfloat16, "out")
-    _call("odb_attention", info, lib().odb_attention, _same_device(qkv, out), qkv.data_ptr(), out.data_ptr(), b, n,
-          heads, scale)
+    if lse is not None:
+        _need(lse, torch.float32, "lse")
+    _call("odb_attention", info, lib().odb_attention, _same_device(qkv, out, lse), qkv.data_ptr(), out.data_ptr(),
+          _ptr(lse), b, n, heads, scale)
 
 
 _GN_SCRATCH = {}

@@ -52,11 +52,13 @@ def _bf16(t):
 
 # ----------------------------------------------------------------------------- fp32, reference order
 def forward_fp32(sd: Dict[str, torch.Tensor], x: torch.Tensor, taps: Optional[dict] = None,
-                 non_negative: bool = True) -> torch.Tensor:
-    """DPTDepthModel.forward (modules/midas/dpt_depth.py:106-107) == DPT.forward(x).squeeze(1)."""
+                 non_negative: bool = True, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """DPTDepthModel.forward (modules/midas/dpt_depth.py:106-107) == DPT.forward(x).squeeze(1).
+    dtype=torch.float64 evaluates the same arithmetic in double precision: the 'exact' reference against which the
+    fp32 noise of both the reference and this repo is measured (gradient tests)."""
     taps = {} if taps is None else taps
-    g = lambda k: sd[k].float()
-    x = x.float()
+    g = lambda k: sd[k].to(dtype)
+    x = x.to(dtype)
 
     # ---- timm ResNetV2 stem + stages (hooks "1","2": modules/midas/vit.py:363-368)
     def sconv(t, key, stride=1):

@@ -1,0 +1,66 @@
+"""Diagnostics (not a pytest): per-tensor gradient error of the TrainEngine against float64 autograd of the oracle."""
+import inspect
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle import dpt_oracle, make_golden, weights  # noqa
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+dev = torch.device("cuda:0")
+precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+
+code = inspect.getsource(dpt_oracle.forward_fp32).replace(".float()", ".double()").replace("def forward_fp32", "def forward_fp64")
+ns = dict(dpt_oracle.__dict__)
+exec(code, ns)
+
+sd = weights.make_state_dict(0, 1)
+x = make_golden.golden_input(1, seed=0)
+g = torch.Generator(device="cpu").manual_seed(123)
+R = torch.randn(1, 384, 384, generator=g).to(dev)
+
+leaves = {k: v.to(dev).double().requires_grad_(True) for k, v in sd.items()}
+y64 = ns["forward_fp64"](leaves, x.to(dev).double())
+grads = torch.autograd.grad((y64 * R.double()).sum(), list(leaves.values()), allow_unused=True)
+g_ref = {k: (gg if gg is not None else torch.zeros_like(leaves[k])) for k, gg in zip(leaves, grads)}
+
+# the reference's own fp32 autograd (torch library kernels) against the same float64 truth
+l32 = {k: v.to(dev).float().requires_grad_(True) for k, v in sd.items()}
+y32 = dpt_oracle.forward_fp32(l32, x.to(dev))
+gr32 = torch.autograd.grad((y32 * R).sum(), list(l32.values()), allow_unused=True)
+g_ref32 = {k: (gg if gg is not None else torch.zeros_like(l32[k])) for k, gg in zip(l32, gr32)}
+
+from omnidata_b200.model import DPTDepthModel  # noqa
+model = DPTDepthModel()
+model.load_state_dict(sd, strict=True)
+model = model.to(dev).train()
+model.precision = precision
+y = model(x.to(dev))
+(y * R).sum().backward()
+torch.cuda.synchronize()
+rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+print("forward rel", rel(y.detach(), y64.detach()))
+rows = []
+for k, p in model.named_parameters():
+    gr = g_ref[k]
+    if float(gr.norm()) == 0:
+        rows.append((0.0 if float(p.grad.norm()) == 0 else 9e9, k, 0.0, 0.0))
+        continue
+    rows.append((rel(p.grad, gr), k, float(gr.norm()), rel(g_ref32[k], gr)))
+rows.sort(reverse=True)
+import math
+tot = lambda idx: math.sqrt(sum((r[idx] * r[2]) ** 2 for r in rows) / sum(r[2] ** 2 for r in rows))
+print(f"global rel-L2 vs float64: engine {tot(0):.3e}   torch fp32 autograd {tot(3):.3e}")
+for e, k, n, e32 in rows[:40]:
+    print(f"{e:.3e}  (torch fp32: {e32:.3e})  |g|={n:.3e}  {k}")
+rows = [(e, k, n) for e, k, n, _ in rows]
+print("...")
+for e, k, n in rows[-5:]:
+    print(f"{e:.3e}  |g|={n:.3e}  {k}")
+(ROOT / "gpurun_out").mkdir(exist_ok=True)
+(ROOT / "gpurun_out" / f"diag_train_{precision}.json").write_text(json.dumps([[e, k, n] for e, k, n in rows]))
