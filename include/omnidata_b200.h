@@ -294,6 +294,9 @@ int odb_head_tail_bwd(const float* dout, const float* out, const void* a, int32_
                       int32_t relu, int32_t accumulate, int32_t dtype, void* stream);
 /* ds_out (fp32) = ds_in (fp32, optional) + g (`dtype`); optional copy of ds_out in `dtype`. */
 int odb_add_cast(const float* ds_in, const void* g, float* ds_out, void* copy, int64_t n, int32_t dtype, void* stream);
+/* train_depth.py:263 `torch.clamp(depth_preds, 0, 1)` and its backward: out = (g1 + g2) * [0 <= p <= 1] (g2 optional). */
+int odb_clamp01(const float* p, float* out, int64_t n, void* stream);
+int odb_clamp01_bwd(const float* p, const float* g1, const float* g2, float* out, int64_t n, void* stream);
 /* Per-step weight packing: w fp32 [n][c][taps] (optionally weight-standardised, timm StdConv2dSame eps) ->
  * fwd `dtype` [n_pad][taps * c_pad] (odb_conv_gemm weight) and bwd `dtype` [c_pad][taps * n_pad] (dgrad weight). */
 int odb_pack_weight(const float* w, void* fwd, void* bwd, int32_t n, int32_t c, int32_t taps, int32_t n_pad, int32_t c_pad,

@@ -127,6 +127,8 @@ _SIGNATURES = {
     "odb_head_tail_bwd_workspace_bytes": (C.c_int64, [C.c_int32]),
     "odb_head_tail_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 5 + [C.c_int32] * 7 + [C.c_void_p]),
     "odb_add_cast": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p]),
+    "odb_clamp01": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "odb_clamp01_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]),
     "odb_pack_weight": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 6 + [C.c_float, C.c_int32, C.c_void_p]),
     "odb_unpack_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
     "odb_make_valid_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

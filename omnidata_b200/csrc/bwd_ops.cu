@@ -632,6 +632,21 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
   }
 }
 
+// ---- train_depth.py:263 `depth_preds = torch.clamp(depth_preds, 0, 1)` and its backward (sum of the loss gradients,
+// passed where 0 <= p <= 1 as torch does)
+__global__ void __launch_bounds__(256) clamp01_kernel(const float* __restrict__ p, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = fminf(fmaxf(p[i], 0.f), 1.f);
+}
+__global__ void __launch_bounds__(256) clamp01_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g1,
+                                                          const float* __restrict__ g2, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = p[i];
+    const float g = g1[i] + (g2 != nullptr ? g2[i] : 0.f);
+    out[i] = (v >= 0.f && v <= 1.f) ? g : 0.f;
+  }
+}
+
 // ---- small ordered reductions of per-block / per-image partials into parameter gradients
 __global__ void ln_param_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        int blocks, int cols, int accumulate) {
@@ -928,4 +943,22 @@ extern "C" int odb_unpack_wgrad(const float* gp, const float* w, float* dw, int3
   unpack_wgrad_kernel<<<n, 256, 0, stream>>>(gp, w, dw, n, c, taps, c_pad, standardize, eps);
   count_launch();
   return check_launch("unpack_wgrad");
+}
+
+extern "C" int odb_clamp01(const float* p, float* out, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!p || !out || n < 0) return fail(ODB_ERR_INVALID, "clamp01: bad argument");
+  if (n == 0) return ODB_OK;
+  clamp01_kernel<<<grid_for(n), 256, 0, stream>>>(p, out, n);
+  count_launch();
+  return check_launch("clamp01");
+}
+
+extern "C" int odb_clamp01_bwd(const float* p, const float* g1, const float* g2, float* out, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!p || !g1 || !out || n < 0) return fail(ODB_ERR_INVALID, "clamp01_bwd: bad argument");
+  if (n == 0) return ODB_OK;
+  clamp01_bwd_kernel<<<grid_for(n), 256, 0, stream>>>(p, g1, g2, out, n);
+  count_launch();
+  return check_launch("clamp01_bwd");
 }

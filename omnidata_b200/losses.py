@@ -210,3 +210,81 @@ def normal_step_losses(normal_preds, normal_gt, mask_float):
     mask_valid = make_valid_mask(mask_float)
     total, l1, cos = normal_losses(normal_preds, normal_gt, mask_valid, clamp_preds=True)
     return {"l1_loss": l1, "cos_loss": cos, "normal_loss": total}
+
+
+class DepthStepLoss:
+    """The loss arithmetic of Depth._shared_step (train_depth.py:261-279) AND its gradient with respect to the raw
+    network output, as one fixed launch sequence with no host synchronisation and no autograd graph (the train step's
+    hot path; `depth_step_losses` above is the autograd-facing equivalent):
+
+        pc = clamp(pred, 0, 1); mask = make_valid_mask(mask_float); (ssi, reg) = MidasLoss(pc, gt, mask)
+        vn = VNL_Loss(pc, gt)                     # (pred, gt) order as the reference calls it
+        loss = ssi                                 if global_step < 15000 (train)
+               ssi + 0.1 reg + 10 vn               otherwise
+        d loss / d pred
+
+    `points`: the three VNL index arrays (host NumPy RNG, reference call sequence); drawn with np.random if None."""
+
+    def __init__(self, input_size=(384, 384), alpha: float = 0.1, scales: int = 4):
+        self.midas = MidasLoss(alpha=alpha, scales=scales)
+        self.vnl = VNL_Loss(1.0, 1.0, tuple(input_size))
+        self._bufs = {}
+
+    def _buf(self, name, shape, dtype, device):
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device:
+            t = self._bufs[name] = torch.empty(tuple(shape), dtype=dtype, device=device)
+        return t
+
+    @torch.no_grad()
+    def __call__(self, pred: torch.Tensor, depth_gt: torch.Tensor, mask_float: torch.Tensor, full_mix: bool = True,
+                 points=None):
+        """pred, depth_gt, mask_float: [B,1,H,W] fp32 CUDA.  Returns (losses fp32 [4] = (loss, ssi, reg, vn), dpred)."""
+        p, g = _f32(pred, "pred"), _f32(depth_gt, "depth_gt")
+        dev = p.device
+        b, h, w = p.shape[0], p.shape[-2], p.shape[-1]
+        n = b * h * w
+        st = torch.cuda.current_stream(dev).cuda_stream
+        pc = self._buf("pc", (b, 1, h, w), torch.float32, dev)
+        check(lib().odb_clamp01(p.data_ptr(), pc.data_ptr(), n, st), "odb_clamp01")
+        m = make_valid_mask(mask_float).to(torch.uint8)
+        alpha, scales = self.midas.alpha, self.midas.scales
+        ws_bytes = int(lib().odb_midas_loss_workspace_bytes(b))
+        ws = self._buf("midas_ws", (ws_bytes + 256,), torch.uint8, dev)
+        off = (-ws.data_ptr()) % 256
+        out3 = self._buf("midas_out", (3,), torch.float32, dev)
+        check(lib().odb_midas_loss_fwd(pc.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, alpha, scales, out3.data_ptr(),
+                                       ws.data_ptr() + off, ws_bytes, st), "odb_midas_loss_fwd")
+        bws = self._buf("midas_bws", (int(lib().odb_midas_loss_bwd_workspace_bytes(b)) // 8,), torch.float64, dev)
+        gbuf = self._buf("midas_gbuf", (n,), torch.float32, dev)
+        gm = self._buf("midas_grad", (n,), torch.float32, dev)
+        check(lib().odb_midas_loss_bwd(pc.data_ptr(), g.data_ptr(), m.data_ptr(), b, h, w, scales, 1.0,
+                                       alpha if full_mix else 0.0, ws.data_ptr() + off, bws.data_ptr(), gbuf.data_ptr(),
+                                       gm.data_ptr(), st), "odb_midas_loss_bwd")
+        losses = self._buf("losses", (4,), torch.float32, dev)
+        gv = None
+        if full_mix:
+            p1, p2, p3 = points if points is not None else self.vnl.select_index()
+            t1, t2, t3 = (torch.from_numpy(np.ascontiguousarray(q)).to(dev, non_blocking=True) for q in (p1, p2, p3))
+            npts = t1.numel()
+            scratch = self._buf("vnl_scratch", (b * npts,), torch.float32, dev)
+            vout = self._buf("vnl_out", (1,), torch.float32, dev)
+            check(lib().odb_vnl_loss_fwd(pc.data_ptr(), g.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(), npts, b, h,
+                                         w, self.vnl.fx, self.vnl.fy, self.vnl.delta_z, 1, vout.data_ptr(),
+                                         scratch.data_ptr(), st), "odb_vnl_loss_fwd")
+            acc = self._buf("vnl_acc", (n,), torch.int64, dev)
+            sel = self._buf("vnl_sel", (4,), torch.float64, dev)
+            gv = self._buf("vnl_grad", (n,), torch.float32, dev)
+            check(lib().odb_vnl_loss_bwd(pc.data_ptr(), g.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(), npts, b, h,
+                                         w, self.vnl.fx, self.vnl.fy, 1, scratch.data_ptr(), 10.0, acc.data_ptr(),
+                                         sel.data_ptr(), gv.data_ptr(), st), "odb_vnl_loss_bwd")
+            losses[1:3].copy_(out3[1:3])
+            losses[3:4].copy_(vout)
+            torch.add(out3[1] + alpha * out3[2], vout[0], alpha=10.0, out=losses[0])
+        else:
+            losses.zero_()
+            losses[0:2].copy_(out3[1:2].expand(2))
+        dpred = self._buf("dpred", (b, 1, h, w), torch.float32, dev)
+        check(lib().odb_clamp01_bwd(p.data_ptr(), gm.data_ptr(), None if gv is None else gv.data_ptr(), dpred.data_ptr(), n,
+                                    st), "odb_clamp01_bwd")
+        return losses, dpred

@@ -403,8 +403,11 @@ class TrainEngine:
             ops.conv_gemm([dy], taps, w, dx[:, py::2, px::2, :])
 
     @torch.no_grad()
-    def backward(self, dout: torch.Tensor):
-        """dout: gradient w.r.t. the forward's output [B,C,H,W] fp32.  Fills self.flat_grad (all 368 tensors)."""
+    def backward(self, dout: torch.Tensor, on_ready=None):
+        """dout: gradient w.r.t. the forward's output [B,C,H,W] fp32.  Fills self.flat_grad (all 368 tensors).
+        on_ready(tag) is called when a contiguous range of the flat gradient is final (plan_grad_buckets): the
+        data-parallel train step launches that range's all-reduce while the rest of the backward runs."""
+        ready = on_ready if on_ready is not None else (lambda tag: None)
         S, P, G, Wt, buf = self.saved, self.P, self.G, self.W, self.buf
         if S is None:
             raise OdbError("TrainEngine.backward: call forward first")
@@ -509,6 +512,7 @@ class TrainEngine:
 
         dtk4 = readout_bwd(4, du4)
         dtk3 = readout_bwd(3, d_layers[2])
+        ready("decoder")
         # ---- ViT blocks (fp32 stream gradient ds, activation-type copy ds16 for the GEMMs)
         pm = "pretrained.model."
         rows = B * ntok
@@ -520,6 +524,8 @@ class TrainEngine:
         for i in range(11, -1, -1):
             p = f"{pm}blocks.{i}."
             v = vit[i]
+            if i == 5:
+                ready("vit_hi")
             if i == 8:                                               # hook after block 8: tokens_8 also feed readout 3
                 bwd.add_cast(ds, dtk3, ds, ds16)
             g16 = ds if self.fp32 else ds16
@@ -559,6 +565,7 @@ class TrainEngine:
         tmpb = buf("tmp.projbias", (B, D), f32)
         bwd.colsum(ds[:, 1:, :], tmpb, batches=B)
         bwd.colsum(tmpb, G[pm + "patch_embed.proj.bias"].view(1, -1))
+        ready("vit_lo")
 
         # ---- ResNetV2 bottlenecks, last to first
         d_out = df3
@@ -623,6 +630,7 @@ class TrainEngine:
         g147 = buf("tmp.stem_g", (64, 147), f32)
         g147.copy_(gp[:, :147])
         bwd.unpack_wgrad(g147, P[bb + "stem.conv.weight"], G[bb + "stem.conv.weight"], 64, 3, 49, 3, True)
+        ready("resnet")
         return self.flat_grad
 
 
@@ -651,3 +659,83 @@ def differentiable_forward(model: DPTDepthModel, x: torch.Tensor) -> torch.Tenso
     params = [p for _, p in model.named_parameters()]
     out = _DptFunction.apply(eng, x, *params)
     return out.squeeze(dim=1)
+
+
+# ====================================================================================== the train step
+def plan_grad_buckets(names: List[str], sizes: List[int]) -> List[Tuple[int, int, str]]:
+    """Contiguous [start, end) ranges of the flat gradient buffer (state_dict order, padded sizes) in the order the
+    backward COMPLETES them, so that each range can be all-reduced while the rest of the backward still runs:
+      decoder + reassemble (scratch.*, act_postprocess*) -> ViT blocks 6..11 -> ViT blocks 0..5 + patch projection ->
+      cls / pos_embed + the ResNetV2 stem and stages.
+    Returns (start, end, ready_after) with ready_after in {"decoder", "vit_hi", "vit_lo", "resnet"}."""
+    offs, off = {}, 0
+    for n, s in zip(names, sizes):
+        offs[n] = (off, off + s)
+        off += s
+    total = off
+
+    def first(pred):
+        return min(offs[n][0] for n in names if pred(n))
+    b_blocks = first(lambda n: n.startswith("pretrained.model.blocks."))
+    b_proj = first(lambda n: n.startswith("pretrained.model.patch_embed.proj."))
+    b_blk6 = first(lambda n: n.startswith("pretrained.model.blocks.6."))
+    b_tail = first(lambda n: n.startswith("pretrained.model.norm.") or n.startswith("pretrained.act_postprocess") or
+                   n.startswith("scratch."))
+    assert b_proj < b_blocks < b_blk6 < b_tail
+    return [(b_tail, total, "decoder"), (b_blk6, b_tail, "vit_hi"), (b_proj, b_blk6, "vit_lo"), (0, b_proj, "resnet")]
+
+
+class DepthTrainStep:
+    """One process per GPU.  step(rgb, depth_gt, mask_float): forward -> clamp + MiDaS SSI + gradient-matching + virtual
+    normal loss -> backward -> gradient all-reduce (data parallel, as the reference's PL DDP, train_depth.py:424-426:
+    mean over ranks, bucketed, overlapped with the rest of the backward on a communication stream) -> clip_grad_norm_(10)
+    -> Adam(lr) on the flat fp32 master weights (train_depth.py:381-383, Trainer(gradient_clip_val=10))."""
+
+    def __init__(self, model: DPTDepthModel, lr: float = 1e-5, clip: Optional[float] = 10.0, precision: str = "bf16",
+                 input_size=(384, 384)):
+        import torch.distributed as dist
+        from .losses import DepthStepLoss
+        from .optim import FlatAdam
+        self.engine = TrainEngine(model, precision)
+        self.loss = DepthStepLoss(input_size)
+        self.opt = FlatAdam(self.engine.flat, lr=lr)
+        self.clip = clip
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        eng = self.engine
+        sizes = [(eng.P[n].numel() + 3) // 4 * 4 for n in eng.param_names]
+        self.buckets = plan_grad_buckets(eng.param_names, sizes)
+        self.comm_stream = torch.cuda.Stream(eng.device) if self.dist else None
+        self.global_step = 0
+        self.allreduce_bytes = sum(e - s for s, e, _ in self.buckets) * 4 if self.dist else 0
+        self._hooks_done: Dict[str, torch.cuda.Event] = {}
+
+    def _allreduce_bucket(self, tag: str):
+        """called by the backward when the range `tag` of the flat gradient is final"""
+        if self.dist is None:
+            return
+        s, e = next((s, e) for s, e, t in self.buckets if t == tag)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.engine.device))
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            self.dist.all_reduce(self.engine.flat_grad[s:e], op=self.dist.ReduceOp.AVG)
+
+    @torch.no_grad()
+    def step(self, rgb: torch.Tensor, depth_gt: torch.Tensor, mask_float: torch.Tensor, points=None,
+             full_mix: Optional[bool] = None) -> torch.Tensor:
+        """-> fp32 [5] on the device: (loss, ssi, reg, vn, gradient norm before clipping); no host synchronisation."""
+        eng = self.engine
+        if full_mix is None:
+            full_mix = self.global_step >= 15000                     # train_depth.py:274-279
+        out = eng.forward(rgb)                                        # [B,1,H,W]
+        losses, dpred = self.loss(out, depth_gt, mask_float, full_mix=full_mix, points=points)
+        eng.backward(dpred, on_ready=self._allreduce_bucket)
+        if self.dist is not None:
+            torch.cuda.current_stream(eng.device).wait_stream(self.comm_stream)
+        norm = self.opt.step(eng.flat_grad, max_norm=self.clip)
+        self.global_step += 1
+        res = torch.empty(5, device=eng.device, dtype=torch.float32)
+        res[:4].copy_(losses)
+        res[4:5].copy_(norm.reshape(1) if norm is not None else torch.zeros(1, device=eng.device))
+        return res

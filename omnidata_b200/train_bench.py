@@ -1,0 +1,183 @@
+"""bench.py --config 4: the train_depth.py step (BASELINE.json configs[4]) — DPT-Hybrid forward + MiDaS SSI +
+gradient-matching + virtual-normal loss + backward + data-parallel gradient all-reduce + clip + Adam, batch 16 per GPU
+(128 at 8 GPUs), synthetic 384x384 inputs (gt = rand, mask = rand > 0.1, VNL indices from NumPy).
+One JSON line on stdout (rank 0), same contract as the inference configs."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+IMG = 384
+TRAIN_GFLOP_PER_IMAGE = 765.7      # forward + dgrad + wgrad = 3 x 255.23 GFLOP
+
+
+def main(args):
+    import numpy as np
+    import torch
+    import bench
+    from . import _capi, ops, parallel, synthetic
+    from .model import DPTDepthModel
+    from .train import DepthTrainStep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback")
+    rank, world, local = parallel.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch or 16
+    peaks = bench.load_peaks()
+
+    model = DPTDepthModel(backbone="vitb_rn50_384")
+    model.load_state_dict(synthetic.make_state_dict(0, 1), strict=True)       # same seed on every rank = identical replicas
+    model = model.to(dev).train()
+    step = DepthTrainStep(model, lr=1e-5, clip=10.0, precision="bf16", input_size=(IMG, IMG))
+
+    gen = torch.Generator(device="cpu").manual_seed(2000 + rank)
+    n_rot = 3
+    host = []
+    for _ in range(n_rot):
+        rgb = (torch.rand(B, 3, IMG, IMG, generator=gen) * 2 - 1).pin_memory()
+        gt = torch.rand(B, 1, IMG, IMG, generator=gen).pin_memory()
+        mask = (torch.rand(B, 1, IMG, IMG, generator=gen) > 0.1).float().pin_memory()
+        host.append((rgb, gt, mask))
+    devin = [tuple(t.to(dev) for t in h) for h in host]
+    np.random.seed(1234 + rank)
+
+    n0 = _capi.launch_count()
+    step.step(*devin[0], full_mix=True)
+    torch.cuda.synchronize()
+    launches_per_step = _capi.launch_count() - n0
+    for i in range(max(args.warmup, 3) - 1):
+        step.step(*devin[i % n_rot], full_mix=True)
+    torch.cuda.synchronize()
+
+    sampler = bench.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    parallel.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        res = step.step(*devin[i % n_rot], full_mix=True)
+    e1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    ms = parallel.reduce_max(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    last = [float(v) for v in res.cpu()]
+
+    # ---- end to end: pinned-host inputs copied every step, the loss read back every step
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    parallel.barrier()
+    torch.cuda.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        slot = slots[i & 1]
+        for d, h in zip(slot, host[i % n_rot]):
+            d.copy_(h, non_blocking=True)
+        r = step.step(*slot, full_mix=True)
+        _ = r.cpu()                                                  # the step's result (loss, parts, grad norm) on the host
+    e3.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    ms_e2e = parallel.reduce_max(e2.elapsed_time(e3), dev)
+
+    # ---- gradient all-reduce alone (NVLink): the flat fp32 gradient, bucketed as in the step
+    allreduce = None
+    if world > 1:
+        import torch.distributed as dist
+        g = step.engine.flat_grad
+        for _ in range(2):
+            for s, e, _t in step.buckets:
+                dist.all_reduce(g[s:e], op=dist.ReduceOp.AVG)
+        torch.cuda.synchronize()
+        parallel.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        reps = 5
+        for _ in range(reps):
+            for s, e, _t in step.buckets:
+                dist.all_reduce(g[s:e], op=dist.ReduceOp.AVG)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = parallel.reduce_max(a0.elapsed_time(a1), dev) / reps
+        nbytes = g.numel() * 4
+        allreduce = {"bytes": nbytes, "ms": round(ar_ms, 3), "algbw_gbs": round(nbytes / (ar_ms * 1e-3) / 1e9, 1),
+                     "busbw_gbs": round(nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world, 1),
+                     "dtype": "fp32 (as the reference's DDP)", "buckets": len(step.buckets),
+                     "overlap": "launched on a communication stream as each bucket's gradients complete (decoder first)"}
+
+    # ---- instrumented step: per-launch CUDA events
+    detail, roof, roof_w = {}, None, None
+    if rank == 0:
+        with ops.LaunchTimer() as lt:
+            for i in range(2):
+                step.step(*devin[i % n_rot], full_mix=True)
+        recs = lt.results()
+        recs = recs[len(recs) // 2:]
+        agg = {}
+        for name, info, t_ms in recs:
+            key = name
+            if name == "odb_conv_gemm":
+                key = "conv_gemm (fp32 pipe, tiny)" if info.get("f32") else "conv_gemm (fwd + dgrad)"
+            if name == "odb_conv_wgrad":
+                key = "conv_wgrad (fp32 pipe, tiny)" if info.get("f32") else "conv_wgrad"
+            a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0})
+            a["ms"] += t_ms
+            a["launches"] += 1
+            if name in ("odb_conv_gemm", "odb_conv_wgrad"):
+                a["flops"] += 2.0 * info["m"] * info["n"] * info["k"]
+            a["flops"] += info.get("flops", 0.0)
+        total_ms = sum(a["ms"] for a in agg.values())
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            d = {"ms_per_step": round(a["ms"], 3), "launches": a["launches"], "share": round(a["ms"] / total_ms, 4)}
+            if a["flops"]:
+                d["tflops"] = round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 1)
+            detail[k] = d
+        peak = peaks["tflops_sustained"]
+        for key, name in (("conv_gemm (fwd + dgrad)", "roof"), ("conv_wgrad", "roof_w")):
+            a = agg.get(key)
+            if a:
+                ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
+                r = {"kernel": ("conv_gemm_kernel (tcgen05 implicit GEMM): every forward conv / linear layer and every dgrad"
+                                if name == "roof" else
+                                "bgemm_kernel (tcgen05, MN-major operands): every weight gradient"),
+                     "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                     "launches": a["launches"], "avg_launch_ms": round(a["ms"] / a["launches"], 4),
+                     "share_of_step": round(a["ms"] / total_ms, 4), "traffic": None,
+                     "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
+                     "how": "CUDA events around every launch on the launching stream, one instrumented step"}
+                if name == "roof":
+                    roof = r
+                else:
+                    roof_w = r
+
+    images = B * world * args.steps
+    value = images / (ms * 1e-3)
+    if rank == 0:
+        line = {
+            "metric": "384x384 images/sec (DPT-Hybrid-384 depth train step)", "value": round(value, 2), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": bench.WORKLOADS[4], "index": 4, "global_batch": B * world, "per_gpu_batch": B,
+                       "parallelism": f"dp{world}: replicated fp32 master weights, gradient all-reduce (mean) over NCCL",
+                       "precision": "bf16 operands / activations, fp32 accumulation, fp32 ViT residual stream, fp32 master "
+                                    "weights + Adam state", "optimizer": "clip_grad_norm_(10) + Adam(lr=1e-5)",
+                       "loss": "ssi + 0.1 reg + 10 vn (the mix after step 15000)",
+                       "l2": f"{n_rot} rotating input batches; activations kept for the backward: several GB per step"},
+            "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
+                    "h2d_bytes_per_step": B * IMG * IMG * 4 * 5, "d2h_bytes_per_step": 20},
+            "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+            "clocks": clocks,
+            "model_tflops": round(TRAIN_GFLOP_PER_IMAGE * 1e9 * value / 1e12, 2),
+            "model_frac_of_sustained_peak": round(TRAIN_GFLOP_PER_IMAGE * 1e9 * value / world / 1e12 / peaks["tflops_sustained"], 4),
+            "last_step": {"loss": last[0], "ssi": last[1], "reg": last[2], "vn": last[3], "grad_norm": last[4]},
+            "allreduce": allreduce,
+            "roofline": roof, "roofline_wgrad": roof_w, "roofline_detail": detail,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()

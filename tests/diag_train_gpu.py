@@ -35,6 +35,13 @@ y32 = dpt_oracle.forward_fp32(l32, x.to(dev))
 gr32 = torch.autograd.grad((y32 * R).sum(), list(l32.values()), allow_unused=True)
 g_ref32 = {k: (gg if gg is not None else torch.zeros_like(l32[k])) for k, gg in zip(l32, gr32)}
 
+# stock torch.autocast(bfloat16) training of the same network: the bf16 yardstick
+lac = {k: v.to(dev).float().requires_grad_(True) for k, v in sd.items()}
+with torch.autocast("cuda", dtype=torch.bfloat16):
+    yac = dpt_oracle.forward_fp32(lac, x.to(dev))
+grac = torch.autograd.grad((yac.float() * R).sum(), list(lac.values()), allow_unused=True)
+g_refac = {k: (gg if gg is not None else torch.zeros_like(lac[k])) for k, gg in zip(lac, grac)}
+
 from omnidata_b200.model import DPTDepthModel  # noqa
 model = DPTDepthModel()
 model.load_state_dict(sd, strict=True)
@@ -49,16 +56,23 @@ rows = []
 for k, p in model.named_parameters():
     gr = g_ref[k]
     if float(gr.norm()) == 0:
-        rows.append((0.0 if float(p.grad.norm()) == 0 else 9e9, k, 0.0, 0.0))
+        rows.append((0.0 if float(p.grad.norm()) == 0 else 9e9, k, 0.0, 0.0, 0.0))
         continue
-    rows.append((rel(p.grad, gr), k, float(gr.norm()), rel(g_ref32[k], gr)))
+    rows.append((rel(p.grad, gr), k, float(gr.norm()), rel(g_ref32[k], gr), rel(g_refac[k], gr)))
 rows.sort(reverse=True)
 import math
 tot = lambda idx: math.sqrt(sum((r[idx] * r[2]) ** 2 for r in rows) / sum(r[2] ** 2 for r in rows))
-print(f"global rel-L2 vs float64: engine {tot(0):.3e}   torch fp32 autograd {tot(3):.3e}")
-for e, k, n, e32 in rows[:40]:
-    print(f"{e:.3e}  (torch fp32: {e32:.3e})  |g|={n:.3e}  {k}")
-rows = [(e, k, n) for e, k, n, _ in rows]
+print(f"global rel-L2 vs float64: engine {tot(0):.3e}   torch fp32 autograd {tot(3):.3e}   torch autocast bf16 {tot(4):.3e}")
+for e, k, n, e32, eac in rows[:25]:
+    print(f"{e:.3e}  (torch fp32: {e32:.3e}, autocast: {eac:.3e})  |g|={n:.3e}  {k}")
+import re
+for pat in ("blocks.0.attn.qkv.weight", "blocks.11.mlp.fc2.weight", "blocks.5.norm1.weight", "refinenet1.resConfUnit2.conv1.weight",
+            "output_conv.0.weight", "layer1_rn.weight", "act_postprocess3.3.weight", "patch_embed.proj.weight", "stem.conv.weight",
+            "stages.2.blocks.8.conv3.weight", "stages.2.blocks.8.norm3.bias", "stages.2.blocks.8.conv1.weight"):
+    for e, k, n, e32, eac in rows:
+        if k.endswith(pat):
+            print(f"   {k}: engine {e:.3e} autocast {eac:.3e}")
+rows = [(e, k, n) for e, k, n, _, _ in rows]
 print("...")
 for e, k, n in rows[-5:]:
     print(f"{e:.3e}  |g|={n:.3e}  {k}")

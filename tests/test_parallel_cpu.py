@@ -63,3 +63,63 @@ def test_shard_range_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_grad_bucket_plan_covers_the_flat_gradient_in_completion_order():
+    """train step (configs[4]): the flat gradient is all-reduced in four contiguous ranges as the backward completes them."""
+    from omnidata_b200.model import state_dict_spec
+    from omnidata_b200.train import plan_grad_buckets
+    import math
+    spec = state_dict_spec(1)
+    names = [k for k, _ in spec]
+    sizes = [(math.prod(s) + 3) // 4 * 4 for _, s in spec]
+    buckets = plan_grad_buckets(names, sizes)
+    assert [t for _, _, t in buckets] == ["decoder", "vit_hi", "vit_lo", "resnet"]
+    spans = sorted((s, e) for s, e, _ in buckets)
+    assert spans[0][0] == 0 and spans[-1][1] == sum(sizes)
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    offs, off = {}, 0
+    for n, s in zip(names, sizes):
+        offs[n] = off
+        off += s
+    rng = {t: (s, e) for s, e, t in buckets}
+    inside = lambda n, t: rng[t][0] <= offs[n] < rng[t][1]
+    assert inside("scratch.output_conv.0.weight", "decoder") and inside("pretrained.act_postprocess3.3.weight", "decoder")
+    assert inside("pretrained.model.blocks.11.mlp.fc2.weight", "vit_hi") and inside("pretrained.model.blocks.6.norm1.weight", "vit_hi")
+    assert inside("pretrained.model.blocks.5.mlp.fc2.bias", "vit_lo") and inside("pretrained.model.patch_embed.proj.weight", "vit_lo")
+    assert inside("pretrained.model.pos_embed", "resnet") and inside("pretrained.model.patch_embed.backbone.stem.conv.weight", "resnet")
+
+
+def _bucket_worker(rank, world, port, out):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from omnidata_b200 import parallel
+    from omnidata_b200.train import plan_grad_buckets
+    parallel.init_from_env("gloo")
+    names = ["pretrained.model.cls_token", "pretrained.model.patch_embed.backbone.stem.conv.weight",
+             "pretrained.model.patch_embed.proj.weight", "pretrained.model.blocks.0.norm1.weight",
+             "pretrained.model.blocks.6.norm1.weight", "pretrained.model.norm.weight", "scratch.output_conv.0.weight"]
+    sizes = [8, 12, 16, 8, 8, 4, 20]
+    flat = torch.arange(sum(sizes), dtype=torch.float32) * (rank + 1)
+    for s, e, _ in plan_grad_buckets(names, sizes):          # data-parallel mean, bucket by bucket (gloo has no AVG)
+        dist.all_reduce(flat[s:e], op=dist.ReduceOp.SUM)
+        flat[s:e] /= world
+    out.put((rank, flat.tolist()))            # plain lists: tensors in a Queue need the sender alive at receive time
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_bucketed_gradient_mean():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (torch.arange(76, dtype=torch.float32) * 1.5).tolist()
+    assert res[0] == want and res[1] == want
