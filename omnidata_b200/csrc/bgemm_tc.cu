@@ -20,12 +20,13 @@
 
 namespace odb {
 
-constexpr int kBgStages = 4;
+constexpr int kBgStages = 4;                // M = 128 tiles: 4 stages of 48 KiB; M = 256 tiles: 3 stages of 64 KiB
 constexpr int kBgAStage = 128 * 128;        // 16 KiB: 128 x 64 bf16 either way
 constexpr int kBgBStage = 256 * 128;        // 32 KiB: up to 256 x 64 bf16
 constexpr int kBgSubBytes = 64 * 128;       // MN-major sub-box: 64 K-rows x 64 MN elements
 constexpr int kBgThreads = 192;
-constexpr int kBgSmem = kBgStages * (kBgAStage + kBgBStage) + 256 + 1024;
+constexpr int kBgRing = kBgStages * (kBgAStage + kBgBStage);      // 192 KiB operand ring
+constexpr int kBgSmem = kBgRing + 256 + 1024;
 
 enum : int { BG_EPI_F32 = 0, BG_EPI_BF16 = 1, BG_EPI_P = 2, BG_EPI_DS = 3 };
 
@@ -43,6 +44,8 @@ struct BgParams {
   int nk1, nk2, nk3;
   int MT, NT, Z1, Z2;
   int split_mode, ksteps_per_split;
+  int mt2;               // 1: 128-row M tiles, double-buffered accumulator; 2: 256-row M tiles (two 128-row UMMAs sharing the
+                         //    B tile: half the B traffic per flop), one accumulator set — for long K loops (weight gradients)
   int bn;
   int tap_mode;
   int8_t tap_view[ODB_MAX_TAPS], tap_dx[ODB_MAX_TAPS], tap_dy[ODB_MAX_TAPS];
@@ -80,8 +83,11 @@ ODB_DEVINL void bg_issue_loads(const BgOperand& o, const CUtensorMap* map, uint3
 __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_constant__ BgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = sbase, b_base = sbase + kBgStages * kBgAStage;
-  const uint32_t bar0 = b_base + kBgStages * kBgBStage;
+  const int stages = p.mt2 == 2 ? 3 : kBgStages;
+  const uint32_t a_stage = static_cast<uint32_t>(p.mt2) * kBgAStage;
+  const uint32_t stage_stride = a_stage + kBgBStage;          // stage s: A at s * stride, B right behind it
+  const uint32_t a_base = sbase, b_base = sbase + a_stage;
+  const uint32_t bar0 = sbase + kBgRing;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kBgStages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kBgStages + a); };
@@ -133,9 +139,9 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
           const int k1 = ks % p.nk1, k2 = (ks / p.nk1) % p.nk2, k3 = ks / (p.nk1 * p.nk2);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
-          bg_issue_loads(p.a, &p.a.map[0], a_base + stage * kBgAStage, full_bar(stage), mt * 128, k1, k2, k3, zb1, zz2, 0, 0);
-          bg_issue_loads(p.b, bmap, b_base + stage * kBgBStage, full_bar(stage), nt * p.bn, k1, k2, k3, zb1, zz2, dx, dy);
-          if (++stage == kBgStages) { stage = 0; phase ^= 1u; }
+          bg_issue_loads(p.a, &p.a.map[0], a_base + stage * stage_stride, full_bar(stage), mt * 128 * p.mt2, k1, k2, k3, zb1, zz2, 0, 0);
+          bg_issue_loads(p.b, bmap, b_base + stage * stage_stride, full_bar(stage), nt * p.bn, k1, k2, k3, zb1, zz2, dx, dy);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -149,23 +155,24 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
         int mt, nt, z1, z2, kb, ke;
         decode(unit, mt, nt, z1, z2);
         krange(z2, kb, ke);
-        const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
+        const uint32_t acc = p.mt2 == 2 ? 0u : (iter & 1u), acc_phase = p.mt2 == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256u;
         for (int ks = kb; ks < ke; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint64_t adesc = bg_desc(a_base + stage * kBgAStage, p.a.mn_major ? kBgSubBytes : 16u);
-          const uint64_t bdesc = bg_desc(b_base + stage * kBgBStage, p.b.mn_major ? kBgSubBytes : 16u);
+          const uint64_t adesc = bg_desc(a_base + stage * stage_stride, p.a.mn_major ? kBgSubBytes : 16u);
+          const uint64_t bdesc = bg_desc(b_base + stage * stage_stride, p.b.mn_major ? kBgSubBytes : 16u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (ks > kb || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t accum = (ks > kb || k > 0) ? 1u : 0u;
+            umma_bf16_ss(d_tmem, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, accum);
+            // second 128 rows of a 256-row tile: the A sub-tile one 16 KiB block further, accumulator columns [256, 512)
+            if (p.mt2 == 2) umma_bf16_ss(d_tmem + 256u, adesc + (kBgAStage >> 4) + a_kstep * k, bdesc + b_kstep * k, idesc, accum);
+          }
           umma_commit(empty_bar(stage));
-          if (++stage == kBgStages) { stage = 0; phase ^= 1u; }
-        }
-        if (ke <= kb) {
-          // empty K range (cannot happen with the host's split plan): define the accumulator as zero
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
       }
@@ -177,15 +184,16 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++iter) {
       int mt, nt, z1, z2;
       decode(unit, mt, nt, z1, z2);
-      const uint32_t acc = iter & 1u, acc_phase = (iter >> 1) & 1u;
+      const uint32_t acc = p.mt2 == 2 ? 0u : (iter & 1u), acc_phase = p.mt2 == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = mt * 128 + row_in_tile;
+      for (int half = 0; half < p.mt2; ++half) {
+      const int row = (mt * p.mt2 + half) * 128 + row_in_tile;
       const bool row_ok = row < p.m_valid;
       const long long obase = z2 * p.o_z2 + z1 * p.o_z1 + static_cast<long long>(row) * p.o_row;
       float rv = 0.f;
       if ((p.epi == BG_EPI_P || p.epi == BG_EPI_DS) && row_ok) rv = p.rowvec[z2 * p.rv_z2 + z1 * p.rv_z1 + row];
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256u;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (p.mt2 == 2 ? half * 256u : acc * 256u);
       for (int c0 = 0; c0 < p.bn; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(t_row + c0, r);
@@ -227,6 +235,7 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
             *reinterpret_cast<uint4*>(dst + 8 * j) = u;
           }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -312,7 +321,7 @@ static void view_strides(const odb_view& v, long long* sx, long long* sy, long l
   if (v.b == 1 && *sb == 0) *sb = (long long)v.h * *sy;
 }
 
-struct WgradPlan { int tw, th, nk1, nk2, nk3, bn, MT, NT, splits, kps; long long row_len; };
+struct WgradPlan { int tw, th, nk1, nk2, nk3, bn, mt2, MT, NT, splits, kps; long long row_len; };
 
 static int wgrad_plan(const odb_wgrad_desc* d, long long workspace_bytes, WgradPlan* pl) {
   const int C = d->views[0].c, n = d->n;
@@ -327,13 +336,15 @@ static int wgrad_plan(const odb_wgrad_desc* d, long long workspace_bytes, WgradP
   pl->nk3 = ob;
   const int cpad = (C + 63) / 64 * 64;
   pl->bn = cpad < 256 ? cpad : 256;
-  pl->MT = (n + 127) / 128;
+  pl->mt2 = n > 128 ? 2 : 1;
+  pl->MT = (n + 128 * pl->mt2 - 1) / (128 * pl->mt2);
   pl->NT = (C + pl->bn - 1) / pl->bn;
   pl->row_len = (long long)d->num_taps * C;
   const long long ksteps = (long long)pl->nk1 * pl->nk2 * pl->nk3;
   const long long tiles = (long long)pl->MT * pl->NT * d->num_taps;
-  long long splits = (2LL * num_sms() + tiles - 1) / tiles;
-  if (splits > ksteps / 2) splits = ksteps / 2;
+  // one wave of CTAs: every extra split costs a full fp32 partial of the gradient (write + re-read in the reduction)
+  long long splits = tiles >= num_sms() ? 1 : num_sms() / tiles;
+  if (splits > ksteps / 8) splits = ksteps / 8;
   if (splits > 256) splits = 256;
   if (splits < 1) splits = 1;
   if (workspace_bytes >= 0) {
@@ -375,7 +386,7 @@ int conv_wgrad_tc(const odb_wgrad_desc* d, cudaStream_t stream) {
     rc = bg_encode(&p.a.map[0], d->dy.ptr, dims, str, box);
     if (rc) return rc;
     for (int v = 1; v < ODB_MAX_VIEWS; ++v) p.a.map[v] = p.a.map[0];
-    p.a.mn_major = 1; p.a.nsub = 2; p.a.sub_dim = 0; p.a.sub_bytes = kBgSubBytes;
+    p.a.mn_major = 1; p.a.nsub = 2 * pl.mt2; p.a.sub_dim = 0; p.a.sub_bytes = kBgSubBytes;
     p.a.mul_mn[0] = 1; p.a.mul_k1[1] = pl.tw; p.a.mul_k2[2] = pl.th; p.a.mul_k3[3] = 1;
   }
   // B = input views, MN-major: N = input channel, same pixel traversal shifted by the tap
@@ -396,6 +407,7 @@ int conv_wgrad_tc(const odb_wgrad_desc* d, cudaStream_t stream) {
   p.nk1 = pl.nk1; p.nk2 = pl.nk2; p.nk3 = pl.nk3;
   p.MT = pl.MT; p.NT = pl.NT; p.Z1 = d->num_taps; p.Z2 = pl.splits;
   p.split_mode = 1; p.ksteps_per_split = pl.kps;
+  p.mt2 = pl.mt2;
   p.bn = pl.bn;
   p.tap_mode = 1;
   for (int t = 0; t < d->num_taps; ++t) { p.tap_view[t] = d->tap_view[t]; p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t]; }
@@ -472,6 +484,7 @@ int attention_bwd_tc(const void* qkv, const void* o, const void* d_o, const floa
     p.b.off[1] = pass == 0 ? H : 2 * H;                         // K slot / V slot
     p.nk1 = p.nk2 = p.nk3 = 1;
     p.MT = MTq; p.NT = kAttPad / 128; p.Z1 = H; p.Z2 = b;
+    p.mt2 = 1;
     p.bn = 128;
     p.epi = pass == 0 ? BG_EPI_P : BG_EPI_DS;
     p.out = pass == 0 ? static_cast<void*>(P) : static_cast<void*>(dS);
@@ -494,6 +507,7 @@ int attention_bwd_tc(const void* qkv, const void* o, const void* d_o, const floa
     p.b.off[1] = H; p.b.mul_k1[2] = 64; p.b.mul_z1[1] = 1; p.b.mul_z2[3] = 1;
     p.nk1 = kAttPad / 64; p.nk2 = p.nk3 = 1;
     p.MT = MTq; p.NT = 1; p.Z1 = H; p.Z2 = b;
+    p.mt2 = 1;
     p.bn = 64;
     p.epi = BG_EPI_BF16;
     p.out = dq;
@@ -513,6 +527,7 @@ int attention_bwd_tc(const void* qkv, const void* o, const void* d_o, const floa
     p.b.mul_k1[2] = 64; p.b.mul_z1[1] = 1; p.b.mul_z2[3] = 1;           // Q slot 0 / dO
     p.nk1 = (T + 63) / 64; p.nk2 = p.nk3 = 1;
     p.MT = MTq; p.NT = 1; p.Z1 = H; p.Z2 = b;
+    p.mt2 = 1;
     p.bn = 64;
     p.epi = BG_EPI_BF16;
     p.out = dq + (pass == 0 ? 1 : 2) * H * 64;

@@ -96,39 +96,37 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ dy,
 // ------------------------------------------------------------------------------------------ column sums (bias grads)
 // out[bt][n] = sum over rows_per_batch rows of x[bt][row][n]; stage 1: slab partials (fixed 64 slabs per batch),
 // stage 2: ordered fp64 combination.  x rows may be strided (row_stride elements).
-constexpr int kColsumSlabs = 32;
+constexpr int kColsumSlabs = 128;   // upper bound of row slabs per batch (workspace sizing); the launch uses min(this, rows / 64)
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, float* __restrict__ partial,
                                                              long long rows_per_batch, int n, long long row_stride,
-                                                             long long batch_stride) {
-  // block: 32 column octets (256 columns) x 8 row lanes; grid (n / 256 rounded up, slabs, batches)
-  const int oct = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
-  const int c0 = (blockIdx.x * 32 + oct) * 8;
+                                                             long long batch_stride, int slabs) {
+  // block: 8 column octets (64 columns = one 128-byte bf16 segment per row) x 32 row lanes;
+  // grid (ceil(n / 64), slabs, batches)
+  const int oct = threadIdx.x & 7, lane_r = threadIdx.x >> 3;
+  const int c0 = (blockIdx.x * 8 + oct) * 8;
   const int slab = blockIdx.y, bt = blockIdx.z;
-  const long long per = (rows_per_batch + kColsumSlabs - 1) / kColsumSlabs;
+  const long long per = (rows_per_batch + slabs - 1) / slabs;
   const long long r0 = slab * per, r1 = min(rows_per_batch, r0 + per);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < n) {
     const T* base = x + bt * batch_stride + c0;
-    for (long long r = r0 + lane_r; r < r1; r += 8) {
+    for (long long r = r0 + lane_r; r < r1; r += 32) {
       float v[8];
       ld8(base + r * row_stride, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
   }
-  __shared__ float s[8][256];
+  __shared__ float s[32][64];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[lane_r][oct * 8 + j] = acc[j];
   __syncthreads();
-  if (lane_r == 0 && c0 < n) {
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < n) {
+    float t = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t += s[q][oct * 8 + j];
-      partial[((long long)bt * kColsumSlabs + slab) * n + c0 + j] = t;
-    }
+    for (int q = 0; q < 32; ++q) t += s[q][threadIdx.x];
+    partial[((long long)bt * slabs + slab) * n + blockIdx.x * 64 + threadIdx.x] = t;
   }
 }
 // out[bt][c] (+)= sum over `parts` partial rows (fp64, fixed order); scale applied to the sum
@@ -583,8 +581,22 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     float v = 0.f;
     if (n < N && c < C) v = (w[((long long)n * C + c) * taps + t] - mean) * inv;
     if (fwd != nullptr) stf(fwd + (long long)n * taps * c_pad + i, v);
-    if (bwd != nullptr) stf(bwd + ((long long)c * taps + (taps - 1 - t)) * n_pad + n, v);
+    if (bwd != nullptr) stf(bwd + ((long long)c * taps + (taps - 1 - t)) * n_pad + n, v);   // only without a fwd buffer
   }
+}
+// bwd[c][(taps-1-t) * n_pad + n] = fwd[n][t * c_pad + c]: 32 x 32 tiles through shared memory, coalesced both ways
+template <typename T>
+__global__ void __launch_bounds__(256) pack_transpose_kernel(const T* __restrict__ fwd, T* __restrict__ bwd, int taps,
+                                                             int n_pad, int c_pad) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32, t = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    tile[r][tx] = (n0 + r < n_pad && c0 + tx < c_pad) ? ldf(fwd + ((long long)(n0 + r) * taps + t) * c_pad + c0 + tx) : 0.f;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (c0 + r < c_pad && n0 + tx < n_pad)
+      stf(bwd + ((long long)(c0 + r) * taps + (taps - 1 - t)) * n_pad + n0 + tx, tile[tx][r]);
 }
 // gradient of the packed weight gp fp32 [n_pad][taps * c_pad] -> gradient in parameter layout [N][C][taps], through
 // the weight standardisation if the layer has one:  dw = (g - mean(g)) / (sigma + eps) - mean(g * what) * what / sigma
@@ -744,13 +756,16 @@ extern "C" int odb_colsum(const void* x, float* out, void* workspace, int32_t ba
   if (!x || !out || !workspace || batches < 1 || rows_per_batch < 1 || n < 8 || n % 8 || row_stride % 8 || batch_stride % 8 ||
       !aligned16(x))
     return fail(ODB_ERR_INVALID, "colsum: bad argument");
-  dim3 grid((n + 255) / 256, kColsumSlabs, batches);
+  long long slabs = (rows_per_batch + 63) / 64;
+  if (slabs > kColsumSlabs) slabs = kColsumSlabs;
+  if (slabs < 1) slabs = 1;
+  dim3 grid((n + 63) / 64, (unsigned)slabs, batches);
   float* partial = static_cast<float*>(workspace);
   ODB_DT(dtype, T, "colsum",
          colsum_partial_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), partial, rows_per_batch, n, row_stride,
-                                                            batch_stride));
+                                                            batch_stride, (int)slabs));
   count_launch();
-  reduce_partials_kernel<<<dim3((n + 255) / 256, batches), 256, 0, stream>>>(partial, out, kColsumSlabs, n, accumulate);
+  reduce_partials_kernel<<<dim3((n + 255) / 256, batches), 256, 0, stream>>>(partial, out, (int)slabs, n, accumulate);
   count_launch();
   return check_launch("colsum");
 }
@@ -928,10 +943,19 @@ extern "C" int odb_pack_weight(const float* w, void* fwd, void* bwd, int32_t n, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!w || (!fwd && !bwd) || n < 1 || c < 1 || taps < 1 || n_pad < n || c_pad < c)
     return fail(ODB_ERR_INVALID, "pack_weight: bad argument");
+  // with both operands wanted: rows of fwd (coalesced), then bwd as a tiled transpose of fwd; bwd alone: direct
+  const bool two_pass = fwd != nullptr && bwd != nullptr;
   ODB_DT(dtype, T, "pack_weight",
-         pack_weight_kernel<T><<<n_pad, 256, 0, stream>>>(w, static_cast<T*>(fwd), static_cast<T*>(bwd), n, c, taps, n_pad, c_pad,
-                                                          standardize, eps));
+         pack_weight_kernel<T><<<n_pad, 256, 0, stream>>>(w, static_cast<T*>(fwd), two_pass ? nullptr : static_cast<T*>(bwd), n,
+                                                          c, taps, n_pad, c_pad, standardize, eps));
   count_launch();
+  if (two_pass) {
+    dim3 grid((n_pad + 31) / 32, (c_pad + 31) / 32, taps);
+    ODB_DT(dtype, T, "pack_weight",
+           pack_transpose_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(fwd), static_cast<T*>(bwd), taps, n_pad,
+                                                              c_pad));
+    count_launch();
+  }
   return check_launch("pack_weight");
 }
 

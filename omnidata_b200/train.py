@@ -132,6 +132,8 @@ class TrainEngine:
             self.W[key] = (fwd, bwd_)
         self.meta = {key: (pname, n, c, taps, n_pad, std) for key, pname, n, c, taps, n_pad, std in T}
         self.gp = torch.empty(768 * 9 * 768, device=self.device, dtype=torch.float32)     # packed-layout wgrad scratch
+        self.zb = torch.zeros(4096, device=self.device, dtype=torch.float32)               # zero "bias" of the dgrad convs:
+        #   selects the straight-line (bias / bias + residual) epilogues of the tensor-core kernel
 
     @torch.no_grad()
     def pack(self):
@@ -185,6 +187,10 @@ class TrainEngine:
             tmp = self.buf("tmp.bias", (1, dy.shape[-1]), torch.float32)
             bwd.colsum(dy.reshape(-1, dy.shape[-1]), tmp)
             g.copy_(tmp[0, :g.numel()])
+
+    def _zb(self, w: torch.Tensor):
+        """zero bias vector for a dgrad convolution with weight `w` [n_out][K] (tensor-core path only)."""
+        return None if self.fp32 else self.zb[: w.shape[0]]
 
     def _cast(self, name: str, x32: torch.Tensor) -> torch.Tensor:
         """fp32 residual-stream tensor as a GEMM operand of the activation type."""
@@ -400,7 +406,7 @@ class TrainEngine:
         stored through a strided view of dx."""
         for (py, px) in ((0, 0), (0, 1), (1, 0), (1, 1)):
             w, taps = self.plane_w[(key, (py, px))]
-            ops.conv_gemm([dy], taps, w, dx[:, py::2, px::2, :])
+            ops.conv_gemm([dy], taps, w, dx[:, py::2, px::2, :], bias=self._zb(w))
 
     @torch.no_grad()
     def backward(self, dout: torch.Tensor, on_ready=None):
@@ -420,13 +426,13 @@ class TrainEngine:
         bwd.head_tail_bwd(dout, hd["out"], hd["a"], hd["w4"], da, G["scratch.output_conv.4.weight"].view(self.C, 32),
                           G["scratch.output_conv.4.bias"], self.non_negative)
         dh1u = buf("g.head_h1u", hd["h1u"].shape)
-        ops.conv3x3(da, Wt["head2"][1], dh1u)
+        ops.conv3x3(da, Wt["head2"][1], dh1u, bias=self._zb(Wt["head2"][1]))
         self._wgrad("head2", [hd["h1u"]], bwd.TAPS_3X3, da)
         self._bias_grad("scratch.output_conv.2.bias", da, n=32)
         dh1 = buf("g.head_h1", hd["h1"].shape)
         bwd.upsample2x_bwd(dh1u, dh1)
         dpath = buf("g.path_1", hd["path_1"].shape)
-        ops.conv3x3(dh1, Wt["head0"][1], dpath)
+        ops.conv3x3(dh1, Wt["head0"][1], dpath, bias=self._zb(Wt["head0"][1]))
         self._wgrad("head0", [hd["path_1"]], bwd.TAPS_3X3, dh1)
         self._bias_grad("scratch.output_conv.0.bias", dh1)
 
@@ -436,12 +442,12 @@ class TrainEngine:
             r = S[f"ff{n}.rcu{u_}"]
             p = f"scratch.refinenet{n}.resConfUnit{u_}."
             dt = buf(f"g.ff{n}_rcu{u_}_t", r["tmid"].shape)
-            ops.conv3x3(d_out, Wt[f"ff{n}.rcu{u_}.c2"][1], dt)
+            ops.conv3x3(d_out, Wt[f"ff{n}.rcu{u_}.c2"][1], dt, bias=self._zb(Wt[f"ff{n}.rcu{u_}.c2"][1]))
             self._wgrad(f"ff{n}.rcu{u_}.c2", [r["tmid"]], bwd.TAPS_3X3, d_out)
             self._bias_grad(p + "conv2.bias", d_out)
             bwd.mask_add(dt, dt, mask=r["tmid"])                        # through relu(conv1 + b1)
             dxr = buf(f"g.ff{n}_rcu{u_}_x", r["x_raw"].shape)
-            ops.conv3x3(dt, Wt[f"ff{n}.rcu{u_}.c1"][1], dxr)
+            ops.conv3x3(dt, Wt[f"ff{n}.rcu{u_}.c1"][1], dxr, bias=self._zb(Wt[f"ff{n}.rcu{u_}.c1"][1]))
             self._wgrad(f"ff{n}.rcu{u_}.c1", [r["x_relu"]], bwd.TAPS_3X3, dt)
             self._bias_grad(p + "conv1.bias", dt)
             bwd.mask_add(dx, dxr, a=d_out, mask=r["x_relu"])            # skip + through relu(x)
@@ -452,7 +458,7 @@ class TrainEngine:
         for n in (1, 2, 3, 4):
             f = S[f"ff{n}"]
             dy = buf(f"g.ff{n}_y", f["y"].shape)
-            ops.conv1x1(dz, Wt[f"ff{n}.out"][1], dy)
+            ops.conv1x1(dz, Wt[f"ff{n}.out"][1], dy, bias=self._zb(Wt[f"ff{n}.out"][1]))
             self._wgrad(f"ff{n}.out", [f["y"]], bwd.TAPS_1, dz)
             self._bias_grad(f"scratch.refinenet{n}.out_conv.bias", dz)
             ds_ = buf(f"g.ff{n}_s", f["y"].shape)
@@ -470,7 +476,7 @@ class TrainEngine:
         for n in (1, 2, 3, 4):
             l = S["layers"][n - 1]
             dl = buf(f"g.layer_{n}", l.shape)
-            ops.conv3x3(d_rn[n - 1], Wt[f"rn{n}"][1], dl)
+            ops.conv3x3(d_rn[n - 1], Wt[f"rn{n}"][1], dl, bias=self._zb(Wt[f"rn{n}"][1]))
             self._wgrad(f"rn{n}", [l], bwd.TAPS_3X3, d_rn[n - 1])
             d_layers.append(dl)
         # ---- reassemble: act_postprocess4.4 (stride 2), then the two readouts
@@ -487,7 +493,7 @@ class TrainEngine:
             r = S[f"ro{n}"]
             pp = f"pretrained.act_postprocess{n}."
             dr = buf(f"g.ro{n}_r", r["r"].shape)
-            ops.conv1x1(do, Wt[f"pp{n}"][1], dr.view(B, gh, gw, D))
+            ops.conv1x1(do, Wt[f"pp{n}"][1], dr.view(B, gh, gw, D), bias=self._zb(Wt[f"pp{n}"][1]))
             self._wgrad(f"pp{n}", [r["r"].view(B, gh, gw, D)], bwd.TAPS_1, do)
             self._bias_grad(pp + "3.bias", do)
             bwd.gelu_bwd(dr, r["pre"], dr)
@@ -531,24 +537,24 @@ class TrainEngine:
             g16 = ds if self.fp32 else ds16
             # mlp: x_{i+1} = xm + fc2(gelu(fc1(LN2(xm))))
             dmlp = buf("g.vit_mlp", v["mlp"].shape)
-            ops.linear(g16.view(rows, -1), Wt[f"blk{i}.fc2"][1], dmlp.view(rows, -1))
+            ops.linear(g16.view(rows, -1), Wt[f"blk{i}.fc2"][1], dmlp.view(rows, -1), bias=self._zb(Wt[f"blk{i}.fc2"][1]))
             self._wgrad(f"blk{i}.fc2", [v["mlp"].view(rows, -1)], bwd.TAPS_1, g16.view(rows, -1))
             bwd.colsum(ds.view(rows, -1), G[p + "mlp.fc2.bias"].view(1, -1))
             bwd.gelu_bwd(dmlp, v["u"], dmlp)
             dh = buf("g.vit_h", v["h2"].shape)
-            ops.linear(dmlp.view(rows, -1), Wt[f"blk{i}.fc1"][1], dh.view(rows, -1))
+            ops.linear(dmlp.view(rows, -1), Wt[f"blk{i}.fc1"][1], dh.view(rows, -1), bias=self._zb(Wt[f"blk{i}.fc1"][1]))
             self._wgrad(f"blk{i}.fc1", [v["h2"].view(rows, -1)], bwd.TAPS_1, dmlp.view(rows, -1))
             self._bias_grad(p + "mlp.fc1.bias", dmlp.view(rows, -1))
             bwd.layernorm_bwd(dh, xm[i], P[p + "norm2.weight"], ds, ds_b, ds16, G[p + "norm2.weight"], G[p + "norm2.bias"])
             g16 = ds_b if self.fp32 else ds16
             # attention: xm = x_i + proj(attn(qkv(LN1(x_i))))
             datt = buf("g.vit_att", v["att"].shape)
-            ops.linear(g16.view(rows, -1), Wt[f"blk{i}.proj"][1], datt.view(rows, -1))
+            ops.linear(g16.view(rows, -1), Wt[f"blk{i}.proj"][1], datt.view(rows, -1), bias=self._zb(Wt[f"blk{i}.proj"][1]))
             self._wgrad(f"blk{i}.proj", [v["att"].view(rows, -1)], bwd.TAPS_1, g16.view(rows, -1))
             bwd.colsum(ds_b.view(rows, -1), G[p + "attn.proj.bias"].view(1, -1))
             dqkv = buf("g.vit_qkv", v["qkv"].shape)
             bwd.attention_bwd(v["qkv"], v["att"], datt, v["lse"], dqkv, heads=12, scale=0.125)
-            ops.linear(dqkv.view(rows, -1), Wt[f"blk{i}.qkv"][1], dh.view(rows, -1))
+            ops.linear(dqkv.view(rows, -1), Wt[f"blk{i}.qkv"][1], dh.view(rows, -1), bias=self._zb(Wt[f"blk{i}.qkv"][1]))
             self._wgrad(f"blk{i}.qkv", [v["h1"].view(rows, -1)], bwd.TAPS_1, dqkv.view(rows, -1))
             self._bias_grad(p + "attn.qkv.bias", dqkv.view(rows, -1))
             bwd.layernorm_bwd(dh, xs[i], P[p + "norm1.weight"], ds_b, ds, ds16, G[p + "norm1.weight"], G[p + "norm1.bias"])
@@ -560,7 +566,7 @@ class TrainEngine:
         f3 = S["f3"]
         dtok = g16[:, 1:, :].unsqueeze(1)
         df3 = buf("g.f3", f3.shape)
-        ops.linear(dtok, Wt["proj"][1], df3.view(B, 1, gh * gw, 1024))
+        ops.linear(dtok, Wt["proj"][1], df3.view(B, 1, gh * gw, 1024), bias=self._zb(Wt["proj"][1]))
         self._wgrad("proj", [f3.view(B, 1, gh * gw, 1024)], bwd.TAPS_1, dtok)
         tmpb = buf("tmp.projbias", (B, D), f32)
         bwd.colsum(ds[:, 1:, :], tmpb, batches=B)
@@ -583,7 +589,7 @@ class TrainEngine:
             dy3 = buf(f"g.{tag}_y3", out.shape)
             bwd.groupnorm_bwd(g, rec["y3"], rec["st3"], P[p + "norm3.weight"], dy3, G[p + "norm3.weight"], G[p + "norm3.bias"])
             da2 = buf(f"g.{tag}_a2", rec["a2"].shape)
-            ops.conv1x1(dy3, Wt[tag + ".w3"][1], da2)
+            ops.conv1x1(dy3, Wt[tag + ".w3"][1], da2, bias=self._zb(Wt[tag + ".w3"][1]))
             self._wgrad(tag + ".w3", [rec["a2"]], bwd.TAPS_1, dy3)
             dy2 = buf(f"g.{tag}_y2", rec["y2"].shape)
             bwd.groupnorm_bwd(da2, rec["y2"], rec["st2"], P[p + "norm2.weight"], dy2, G[p + "norm2.weight"], G[p + "norm2.bias"],
@@ -591,7 +597,7 @@ class TrainEngine:
             da1 = buf(f"g.{tag}_a1", rec["a1"].shape)
             a1 = rec["a1"]
             if stride == 1:
-                ops.conv3x3(dy2, Wt[tag + ".w2"][1], da1)
+                ops.conv3x3(dy2, Wt[tag + ".w2"][1], da1, bias=self._zb(Wt[tag + ".w2"][1]))
                 self._wgrad(tag + ".w2", [a1], bwd.TAPS_3X3, dy2)
             else:
                 self._dgrad_s2(tag + ".w2", dy2, da1)
@@ -607,14 +613,14 @@ class TrainEngine:
                                   G[p + "downsample.norm.weight"], G[p + "downsample.norm.bias"])
                 if stride > 1:
                     dt_in.zero_()
-                    ops.conv1x1(dd, Wt[tag + ".wd"][1], dt_in[:, ::stride, ::stride, :])
+                    ops.conv1x1(dd, Wt[tag + ".wd"][1], dt_in[:, ::stride, ::stride, :], bias=self._zb(Wt[tag + ".wd"][1]))
                     self._wgrad(tag + ".wd", [t_in[:, ::stride, ::stride, :]], bwd.TAPS_1, dd)
                 else:
-                    ops.conv1x1(dd, Wt[tag + ".wd"][1], dt_in)
+                    ops.conv1x1(dd, Wt[tag + ".wd"][1], dt_in, bias=self._zb(Wt[tag + ".wd"][1]))
                     self._wgrad(tag + ".wd", [t_in], bwd.TAPS_1, dd)
-                ops.conv1x1(dy1, Wt[tag + ".w1"][1], dt_in, residual=dt_in)
+                ops.conv1x1(dy1, Wt[tag + ".w1"][1], dt_in, residual=dt_in, bias=self._zb(Wt[tag + ".w1"][1]))
             else:
-                ops.conv1x1(dy1, Wt[tag + ".w1"][1], dt_in, residual=g)
+                ops.conv1x1(dy1, Wt[tag + ".w1"][1], dt_in, residual=g, bias=self._zb(Wt[tag + ".w1"][1]))
             self._wgrad(tag + ".w1", [t_in], bwd.TAPS_1, dy1)
             d_out = dt_in
         # ---- stem

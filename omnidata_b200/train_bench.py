@@ -36,11 +36,20 @@ def main(args):
     gen = torch.Generator(device="cpu").manual_seed(2000 + rank)
     n_rot = 3
     host = []
+    model.eval()
     for _ in range(n_rot):
         rgb = (torch.rand(B, 3, IMG, IMG, generator=gen) * 2 - 1).pin_memory()
-        gt = torch.rand(B, 1, IMG, IMG, generator=gen).pin_memory()
+        # target: the seeded network's own initial prediction, perturbed (multiplicative + additive noise).  A uniformly
+        # random target makes the first Adam steps move all 123 M seeded weights coherently (Adam's first updates are
+        # +-lr per weight whatever the gradient's size), which kills the final ReLU within ~8 steps: a dead network
+        # with zero gradients is a poor benchmark subject.  The arithmetic per step is identical either way.
+        with torch.no_grad():
+            p0 = model(rgb.to(dev)).float().cpu().unsqueeze(1)
+        noise = torch.rand(B, 1, IMG, IMG, generator=gen)
+        gt = (p0 * (0.8 + 0.4 * noise) + 0.05 * torch.rand(B, 1, IMG, IMG, generator=gen)).clamp(0, 1).pin_memory()
         mask = (torch.rand(B, 1, IMG, IMG, generator=gen) > 0.1).float().pin_memory()
         host.append((rgb, gt, mask))
+    model.train()
     devin = [tuple(t.to(dev) for t in h) for h in host]
     np.random.seed(1234 + rank)
 
@@ -167,6 +176,8 @@ def main(args):
                        "precision": "bf16 operands / activations, fp32 accumulation, fp32 ViT residual stream, fp32 master "
                                     "weights + Adam state", "optimizer": "clip_grad_norm_(10) + Adam(lr=1e-5)",
                        "loss": "ssi + 0.1 reg + 10 vn (the mix after step 15000)",
+                       "targets": "depth_gt = the seeded network's initial prediction, perturbed; mask = rand > 0.1; VNL "
+                                  "indices from NumPy's RNG each step (reference call sequence)",
                        "l2": f"{n_rot} rotating input batches; activations kept for the backward: several GB per step"},
             "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_bytes_per_step": B * IMG * IMG * 4 * 5, "d2h_bytes_per_step": 20},
