@@ -24,9 +24,14 @@ constexpr int kBgStages = 4;                // M = 128 tiles: 4 stages of 48 KiB
 constexpr int kBgAStage = 128 * 128;        // 16 KiB: 128 x 64 bf16 either way
 constexpr int kBgBStage = 256 * 128;        // 32 KiB: up to 256 x 64 bf16
 constexpr int kBgSubBytes = 64 * 128;       // MN-major sub-box: 64 K-rows x 64 MN elements
-constexpr int kBgThreads = 192;
+constexpr int kBgMaxThreads = 320;          // warp 0 TMA, warp 1 MMA, 4 or 8 epilogue warps
 constexpr int kBgRing = kBgStages * (kBgAStage + kBgBStage);      // 192 KiB operand ring
-constexpr int kBgSmem = kBgRing + 256 + 1024;
+constexpr int kBgStagePitch = 144;                               // 128-byte row + 16: conflict-free row / piece access
+constexpr int kBgWarpStage = 32 * kBgStagePitch;                  // one 32-row x 128-byte staging tile per epilogue warp
+static int bg_smem_bytes(int stages, int mt2, int epi_warps) {
+  return stages * (mt2 * kBgAStage + kBgBStage) + 256 + epi_warps * kBgWarpStage + 1024;
+}
+constexpr int kBgSmemMax = 227 * 1024;
 
 enum : int { BG_EPI_F32 = 0, BG_EPI_BF16 = 1, BG_EPI_P = 2, BG_EPI_DS = 3 };
 
@@ -44,6 +49,9 @@ struct BgParams {
   int nk1, nk2, nk3;
   int MT, NT, Z1, Z2;
   int split_mode, ksteps_per_split;
+  int stages;            // operand ring depth (3 or 4)
+  int epi_warps;         // 4: one epilogue warp per TMEM lane quadrant; 8: two per quadrant, each owning half of the columns
+                         //    (short-K GEMMs with heavy epilogues: the attention P / dS products)
   int mt2;               // 1: 128-row M tiles, double-buffered accumulator; 2: 256-row M tiles (two 128-row UMMAs sharing the
                          //    B tile: half the B traffic per flop), one accumulator set — for long K loops (weight gradients)
   int bn;
@@ -80,25 +88,26 @@ ODB_DEVINL void bg_issue_loads(const BgOperand& o, const CUtensorMap* map, uint3
   }
 }
 
-__global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_constant__ BgParams p) {
+__global__ void __launch_bounds__(kBgMaxThreads, 1) bgemm_kernel(const __grid_constant__ BgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stages = p.mt2 == 2 ? 3 : kBgStages;
+  const int stages = p.stages;
   const uint32_t a_stage = static_cast<uint32_t>(p.mt2) * kBgAStage;
   const uint32_t stage_stride = a_stage + kBgBStage;          // stage s: A at s * stride, B right behind it
   const uint32_t a_base = sbase, b_base = sbase + a_stage;
-  const uint32_t bar0 = sbase + kBgRing;
+  const uint32_t bar0 = sbase + static_cast<uint32_t>(stages) * stage_stride;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kBgStages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kBgStages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kBgStages + 2 + a); };
   const uint32_t tmem_slot = bar0 + 8u * (2 * kBgStages + 4);
+  const uint32_t stage_base = bar0 + 256u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), p.epi_warps); }
     mbar_fence_init();
     tma_prefetch_desc(&p.a.map[0]);
     tma_prefetch_desc(&p.b.map[0]);
@@ -187,54 +196,88 @@ __global__ void __launch_bounds__(kBgThreads, 1) bgemm_kernel(const __grid_const
       const uint32_t acc = p.mt2 == 2 ? 0u : (iter & 1u), acc_phase = p.mt2 == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      // Every global access of the epilogue is staged through a per-warp shared-memory tile of 32 rows x 128 bytes:
+      // a thread owns one accumulator ROW (TMEM lane), but a warp-wide store of "my row, 16 bytes" touches 32
+      // different 128-byte lines.  Staged, lanes 8k..8k+7 move one row's 128 contiguous bytes: 4 full lines per
+      // instruction.  (Measured on the attention backward: the direct version ran the P / dS GEMMs store-bound.)
+      const uint32_t wst = stage_base + static_cast<uint32_t>(warp - 2) * kBgWarpStage;
+      const int ncols = p.epi_warps == 8 ? p.bn / 2 : p.bn;          // columns this warp owns
+      const int cbeg = p.epi_warps == 8 ? ((warp - 2) >> 2) * ncols : 0;
+      const int piece = lane & 7, rsub = lane >> 3;
+      const bool f32out = p.epi == BG_EPI_F32;
+      const int cw = f32out ? 32 : 64;                               // columns per 128-byte row segment
+      const int esz = f32out ? 4 : 2;
       for (int half = 0; half < p.mt2; ++half) {
-      const int row = (mt * p.mt2 + half) * 128 + row_in_tile;
+      const int row0 = (mt * p.mt2 + half) * 128 + quad * 32;        // first row of this warp
+      const int row = row0 + lane;
       const bool row_ok = row < p.m_valid;
-      const long long obase = z2 * p.o_z2 + z1 * p.o_z1 + static_cast<long long>(row) * p.o_row;
+      const long long zbase = z2 * p.o_z2 + z1 * p.o_z1;
       float rv = 0.f;
       if ((p.epi == BG_EPI_P || p.epi == BG_EPI_DS) && row_ok) rv = p.rowvec[z2 * p.rv_z2 + z1 * p.rv_z1 + row];
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (p.mt2 == 2 ? half * 256u : acc * 256u);
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c0, r);
-        tmem_ld_wait();
+      for (int c0 = cbeg; c0 < cbeg + ncols; c0 += cw) {
         const int col0 = nt * p.bn + c0;
-        if (!row_ok || col0 >= p.n_store) continue;
-        float v[32];
+        uint32_t r[64];
+        tmem_ld_32x32(t_row + c0, r);
+        if (!f32out) tmem_ld_32x32(t_row + c0 + 32, r + 32);
+        tmem_ld_wait();
+        if (col0 >= p.n_store) continue;                              // warp-uniform
+        uint32_t q[32];                                               // this row's 128 output bytes
+        if (f32out) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.epi == BG_EPI_F32) {
-          float* dst = static_cast<float*>(p.out) + obase + col0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (col0 + 4 * j < p.n_store)
-              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 32; ++j) q[j] = r[j];
         } else {
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
           if (p.epi == BG_EPI_P) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.n_valid) ? ex2_approx(fmaf(v[j], p.c1, -rv)) : 0.f;
+            for (int j = 0; j < 64; ++j) v[j] = (col0 + j < p.n_valid) ? ex2_approx(fmaf(v[j], p.c1, -rv)) : 0.f;
           } else if (p.epi == BG_EPI_DS) {
-            const bf16* pp = p.pmat + obase + col0;
+            // P tile: coalesced global -> staging tile, then every thread reads its own row
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (col0 + 8 * j >= p.n_store) { for (int q = 0; q < 8; ++q) v[8 * j + q] = 0.f; continue; }
-              const uint4 u = *reinterpret_cast<const uint4*>(pp + 8 * j);
-              const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+            for (int i = 0; i < 8; ++i) {
+              const int rr = rsub + 4 * i, grow = row0 + rr;
+              uint4 u = make_uint4(0u, 0u, 0u, 0u);
+              if (grow < p.m_valid && col0 + piece * 8 < p.n_store)
+                u = *reinterpret_cast<const uint4*>(p.pmat + zbase + static_cast<long long>(grow) * p.o_row + col0 + piece * 8);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + rr * kBgStagePitch + piece * 16), "r"(u.x),
+                           "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t a0, a1, a2, a3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                           : "r"(wst + lane * kBgStagePitch + j * 16) : "memory");
+              const float2 p0 = unpack_bf16x2(a0), p1 = unpack_bf16x2(a1), p2 = unpack_bf16x2(a2), p3 = unpack_bf16x2(a3);
               const float pv[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[8 * j + q] = pv[q] * (v[8 * j + q] - rv) * p.c1;
+              for (int e = 0; e < 8; ++e) v[8 * j + e] = pv[e] * (v[8 * j + e] - rv) * p.c1;
             }
+            __syncwarp();
           }
-          bf16* dst = static_cast<bf16*>(p.out) + obase + col0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (col0 + 8 * j >= p.n_store) continue;
+          for (int j = 0; j < 32; ++j) q[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + lane * kBgStagePitch + j * 16), "r"(q[4 * j]),
+                       "r"(q[4 * j + 1]), "r"(q[4 * j + 2]), "r"(q[4 * j + 3]) : "memory");
+        __syncwarp();
+        const int ecol = col0 + piece * (16 / esz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = rsub + 4 * i, grow = row0 + rr;
+          if (grow < p.m_valid && ecol < p.n_store) {
             uint4 u;
-            u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(dst + 8 * j) = u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                         : "r"(wst + rr * kBgStagePitch + piece * 16) : "memory");
+            char* dst = static_cast<char*>(p.out) + (zbase + static_cast<long long>(grow) * p.o_row + ecol) * esz;
+            *reinterpret_cast<uint4*>(dst) = u;
           }
         }
+        __syncwarp();
       }
       }
       tc_fence_before();
@@ -292,18 +335,24 @@ static int bg_encode(CUtensorMap* map, const void* ptr, const long long dims_[4]
                       CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-static int bg_launch(const BgParams& p, cudaStream_t stream) {
+static int bg_launch(BgParams& p, cudaStream_t stream) {
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBgSmem);
+    cudaError_t e = cudaFuncSetAttribute(bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBgSmemMax);
     if (e != cudaSuccess) return fail_cuda(e, "bgemm: cudaFuncSetAttribute");
     configured[dev] = true;
   }
+  if (p.epi_warps != 8) p.epi_warps = 4;
+  if (p.mt2 == 2) { p.stages = 3; p.epi_warps = 4; }
+  else if (p.stages != 3) p.stages = kBgStages;
+  if (p.epi_warps == 8) p.stages = 3;
+  const int smem = bg_smem_bytes(p.stages, p.mt2, p.epi_warps);
+  if (smem > kBgSmemMax) return fail(ODB_ERR_INVALID, "bgemm: shared-memory plan too large");
   const long long units = (long long)p.MT * p.NT * p.Z1 * p.Z2;
   if (units < 1 || units > 0x7fffffffLL) return fail(ODB_ERR_INVALID, "bgemm: bad unit count");
   const int grid = units < num_sms() ? (int)units : num_sms();
-  bgemm_kernel<<<grid, kBgThreads, kBgSmem, stream>>>(p);
+  bgemm_kernel<<<grid, 64 + 32 * p.epi_warps, smem, stream>>>(p);
   count_launch();
   return check_launch("bgemm");
 }
@@ -485,6 +534,7 @@ int attention_bwd_tc(const void* qkv, const void* o, const void* d_o, const floa
     p.nk1 = p.nk2 = p.nk3 = 1;
     p.MT = MTq; p.NT = kAttPad / 128; p.Z1 = H; p.Z2 = b;
     p.mt2 = 1;
+    p.epi_warps = 8;
     p.bn = 128;
     p.epi = pass == 0 ? BG_EPI_P : BG_EPI_DS;
     p.out = pass == 0 ? static_cast<void*>(P) : static_cast<void*>(dS);

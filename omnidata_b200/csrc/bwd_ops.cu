@@ -411,40 +411,54 @@ __global__ void __launch_bounds__(256) stem_pool_bwd_kernel(const T* __restrict_
   }
   __syncthreads();
   const int oh = h / 2, ow = w / 2;
-  const long long total = (long long)h * w * c;
+  const int octets = c >> 3;
+  const long long total = (long long)h * w * octets;
   const T* sb = s0 + (long long)b * h * w * c;
   const T* db = dt + (long long)b * oh * ow * c;
   T* gb = g_s0 + (long long)b * h * w * c;
+  // thread = (input pixel, 8 channels): 16-byte loads; the 3x3 neighbourhoods of its <= 4 windows come from L1/L2
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % c);
-    const int ix = (int)((i / c) % w), iy = (int)(i / ((long long)c * w));
-    const float a = coef[ch], sh = coef[c + ch];
-    const float v = fmaxf(fmaf(ldf(sb + i), a, sh), 0.f);
-    float acc = 0.f;
-    if (v > 0.f) {
-      // windows (oy, ox) with 2*oy <= iy <= 2*oy + 2
+    const int oct = (int)(i % octets);
+    const int ix = (int)((i / octets) % w), iy = (int)(i / ((long long)octets * w));
+    float a[8], sh[8], v[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = coef[oct * 8 + j]; sh[j] = coef[c + oct * 8 + j]; acc[j] = 0.f; }
+    ld8(sb + ((long long)iy * w + ix) * c + oct * 8, v);
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = fmaxf(fmaf(v[j], a[j], sh[j]), 0.f); any |= v[j] > 0.f; }
+    if (any) {
       for (int oy = max((iy - 1) / 2, 0); oy <= min(iy / 2, oh - 1); ++oy) {
         if (2 * oy > iy || 2 * oy + 2 < iy) continue;
         for (int ox = max((ix - 1) / 2, 0); ox <= min(ix / 2, ow - 1); ++ox) {
           if (2 * ox > ix || 2 * ox + 2 < ix) continue;
-          bool is_arg = true;
-          for (int dy = 0; dy < 3 && is_arg; ++dy) {
+          bool is_arg[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) is_arg[j] = v[j] > 0.f;
+          for (int dy = 0; dy < 3; ++dy) {
             const int yy = 2 * oy + dy;
             if (yy >= h) continue;
             for (int dx = 0; dx < 3; ++dx) {
               const int xx = 2 * ox + dx;
-              if (xx >= w) continue;
-              if (yy == iy && xx == ix) continue;
-              const float u = fmaxf(fmaf(ldf(sb + ((long long)yy * w + xx) * c + ch), a, sh), 0.f);
+              if (xx >= w || (yy == iy && xx == ix)) continue;
+              float u[8];
+              ld8(sb + ((long long)yy * w + xx) * c + oct * 8, u);
               const bool before = (yy < iy) || (yy == iy && xx < ix);
-              if (u > v || (before && u == v)) { is_arg = false; break; }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float uu = fmaxf(fmaf(u[j], a[j], sh[j]), 0.f);
+                if (uu > v[j] || (before && uu == v[j])) is_arg[j] = false;
+              }
             }
           }
-          if (is_arg) acc += ldf(db + ((long long)oy * ow + ox) * c + ch);
+          float g[8];
+          ld8(db + ((long long)oy * ow + ox) * c + oct * 8, g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += is_arg[j] ? g[j] : 0.f;
         }
       }
     }
-    stf(gb + i, acc);
+    st8(gb + ((long long)iy * w + ix) * c + oct * 8, acc);
   }
 }
 
@@ -603,12 +617,15 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(const T* __restrict
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ gp, const float* __restrict__ w,
                                                            float* __restrict__ dw, int N, int C, int taps, int c_pad,
                                                            int standardize, float eps) {
+  extern __shared__ float row[];         // the packed gradient row of this output channel: [taps][c_pad], loaded coalesced
   const int n = blockIdx.x;
   const int K = C * taps;
+  for (int i = threadIdx.x; i < taps * c_pad; i += blockDim.x) row[i] = gp[(long long)n * taps * c_pad + i];
+  __syncthreads();
   if (!standardize) {
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
       const int c = i / taps, t = i - c * taps;
-      dw[(long long)n * K + i] = gp[((long long)n * taps + t) * c_pad + c];
+      dw[(long long)n * K + i] = row[t * c_pad + c];
     }
     return;
   }
@@ -616,7 +633,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
   double s = 0.0, q = 0.0, sg = 0.0, sgw = 0.0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     const int c = i / taps, t = i - c * taps;
-    const double v = w[(long long)n * K + i], g = gp[((long long)n * taps + t) * c_pad + c];
+    const double v = w[(long long)n * K + i], g = row[t * c_pad + c];
     s += v; q += v * v; sg += g; sgw += g * v;
   }
   red[0][threadIdx.x] = s; red[1][threadIdx.x] = q; red[2][threadIdx.x] = sg; red[3][threadIdx.x] = sgw;
@@ -637,7 +654,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
   const double mgw = (st[3] - mean * st[2]) / (sden * K);
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     const int c = i / taps, t = i - c * taps;
-    const double v = w[(long long)n * K + i], g = gp[((long long)n * taps + t) * c_pad + c];
+    const double v = w[(long long)n * K + i], g = row[t * c_pad + c];
     const double what = (v - mean) / sden;
     const double r = (g - mg) / sden - (sigma > 0.0 ? mgw * what / sigma : 0.0);
     dw[(long long)n * K + i] = (float)r;
@@ -881,7 +898,8 @@ extern "C" int odb_stem_pool_bwd(const void* dt, const void* s0, const float* st
   if (!dt || !s0 || !stats || !gamma || !beta || !g_s0 || b < 1 || h < 2 || w < 2 || (h & 1) || (w & 1) || c < 1 ||
       c % groups || b > 65535)
     return fail(ODB_ERR_INVALID, "stem_pool_bwd: bad argument");
-  long long gx = ((long long)h * w * c + 255) / 256;
+  if (c % 8) return fail(ODB_ERR_INVALID, "stem_pool_bwd: c must be a multiple of 8");
+  long long gx = ((long long)h * w * (c / 8) + 255) / 256;
   const long long cap = ((long long)num_sms() * 16 + b - 1) / b;
   if (gx > cap) gx = cap;
   ODB_DT(dtype, T, "stem_pool_bwd",
@@ -964,7 +982,8 @@ extern "C" int odb_unpack_wgrad(const float* gp, const float* w, float* dw, int3
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!gp || !dw || (standardize && !w) || n < 1 || c < 1 || taps < 1 || c_pad < c)
     return fail(ODB_ERR_INVALID, "unpack_wgrad: bad argument");
-  unpack_wgrad_kernel<<<n, 256, 0, stream>>>(gp, w, dw, n, c, taps, c_pad, standardize, eps);
+  if ((long long)taps * c_pad * 4 > 40 * 1024) return fail(ODB_ERR_UNSUPPORTED, "unpack_wgrad: taps * c_pad too large");
+  unpack_wgrad_kernel<<<n, 256, (size_t)taps * c_pad * sizeof(float), stream>>>(gp, w, dw, n, c, taps, c_pad, standardize, eps);
   count_launch();
   return check_launch("unpack_wgrad");
 }

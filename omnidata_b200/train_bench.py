@@ -121,10 +121,13 @@ def main(args):
 
     # ---- instrumented step: per-launch CUDA events
     detail, roof, roof_w = {}, None, None
+    # every rank runs the two instrumented steps (they contain the gradient all-reduce: a collective); rank 0 records
+    import contextlib
+    with (ops.LaunchTimer() if rank == 0 else contextlib.nullcontext()) as lt:
+        for i in range(2):
+            step.step(*devin[i % n_rot], full_mix=True)
+    torch.cuda.synchronize()
     if rank == 0:
-        with ops.LaunchTimer() as lt:
-            for i in range(2):
-                step.step(*devin[i % n_rot], full_mix=True)
         recs = lt.results()
         recs = recs[len(recs) // 2:]
         agg = {}
