@@ -29,7 +29,14 @@ def main(args):
     peaks = bench.load_peaks()
 
     model = DPTDepthModel(backbone="vitb_rn50_384")
-    model.load_state_dict(synthetic.make_state_dict(0, 1), strict=True)       # same seed on every rank = identical replicas
+    sd = synthetic.make_state_dict(0, 1)                                       # same seed on every rank = identical replicas
+    # The seeded checkpoint leaves ~70 % of the output pixels behind the final ReLU (prediction exactly 0).  MidasLoss
+    # inverts the prediction (1 / (p + 1e-6), losses/midas_loss.py:147): at p = 0 its gradient is ~1e12 per pixel, one
+    # Adam step then kills the network — torch autograd + torch.optim.Adam over the reference arithmetic collapses the
+    # same way after ONE step (tests/diag_dynamics_gpu.py).  Shift the output bias so that the seeded network predicts
+    # inside (0, 1): a trained depth model's regime.  The arithmetic per step does not depend on the values.
+    sd["scratch.output_conv.4.bias"] = sd["scratch.output_conv.4.bias"] + 0.35
+    model.load_state_dict(sd, strict=True)
     model = model.to(dev).train()
     step = DepthTrainStep(model, lr=1e-5, clip=10.0, precision="bf16", input_size=(IMG, IMG))
 
@@ -54,9 +61,10 @@ def main(args):
     np.random.seed(1234 + rank)
 
     n0 = _capi.launch_count()
-    step.step(*devin[0], full_mix=True)
+    first = step.step(*devin[0], full_mix=True)
     torch.cuda.synchronize()
     launches_per_step = _capi.launch_count() - n0
+    first = [float(v) for v in first.cpu()]
     for i in range(max(args.warmup, 3) - 1):
         step.step(*devin[i % n_rot], full_mix=True)
     torch.cuda.synchronize()
@@ -188,6 +196,7 @@ def main(args):
             "clocks": clocks,
             "model_tflops": round(TRAIN_GFLOP_PER_IMAGE * 1e9 * value / 1e12, 2),
             "model_frac_of_sustained_peak": round(TRAIN_GFLOP_PER_IMAGE * 1e9 * value / world / 1e12 / peaks["tflops_sustained"], 4),
+            "first_step": {"loss": first[0], "ssi": first[1], "reg": first[2], "vn": first[3], "grad_norm": first[4]},
             "last_step": {"loss": last[0], "ssi": last[1], "reg": last[2], "vn": last[3], "grad_norm": last[4]},
             "allreduce": allreduce,
             "roofline": roof, "roofline_wgrad": roof_w, "roofline_detail": detail,

@@ -23,6 +23,25 @@ sd = weights.make_state_dict(0, 1)
 x = make_golden.golden_input(1, seed=0)
 g = torch.Generator(device="cpu").manual_seed(123)
 R = torch.randn(1, 384, 384, generator=g).to(dev)
+if len(sys.argv) > 2 and sys.argv[2] == "loss":
+    # R := d(ssi + 0.1 reg + 10 vn)/d(pred) at the fp32 forward's output for a perturbed-prediction target (the bench's
+    # synthetic data): the linear functional sum(y * R) then has the train step's gradient
+    import numpy as np
+    from omnidata_b200 import losses
+    from omnidata_b200.model import DPTDepthModel as _M
+    x = torch.cat([make_golden.golden_input(1, seed=0), make_golden.golden_input(1, seed=7)])
+    m0 = _M(); m0.load_state_dict(sd); m0 = m0.to(dev).eval(); m0.precision = "fp32"
+    with torch.no_grad():
+        p0 = m0(x.to(dev)).float().unsqueeze(1)
+    noise = torch.rand(2, 1, 384, 384, generator=g).to(dev)
+    gt = (p0 * (0.8 + 0.4 * noise) + 0.05 * torch.rand(2, 1, 384, 384, generator=g).to(dev)).clamp(0, 1)
+    mask = (torch.rand(2, 1, 384, 384, generator=g) > 0.1).float().to(dev)
+    np.random.seed(7)
+    fn = losses.DepthStepLoss((384, 384))
+    _, dpred = fn(p0, gt, mask, full_mix=True)
+    R = dpred[:, 0].clone()
+    print("real-loss gradient: |R| =", float(R.norm()), " max", float(R.abs().max()))
+    del m0
 
 leaves = {k: v.to(dev).double().requires_grad_(True) for k, v in sd.items()}
 y64 = ns["forward_fp64"](leaves, x.to(dev).double())
