@@ -296,6 +296,7 @@ def main():
         bcast_bytes += parallel.broadcast_packed_weights(m, dev, src=0)
         torch.cuda.synchronize()
         bcast_ms += 1e3 * (time.perf_counter() - t0)
+        weights_identical = parallel.packed_weights_identical(m, dev) and (weights_identical if models else True)
         m.use_cuda_graph = not args.no_graph
         models.append(m)
 
@@ -455,7 +456,8 @@ def main():
             "clocks": clocks,
             "model_tflops": round(GFLOP_PER_IMAGE * nets * 1e9 * value / 1e12, 2),
             "model_frac_of_sustained_peak": round(GFLOP_PER_IMAGE * nets * 1e9 * value / world / 1e12 / peaks["tflops_sustained"], 4),
-            "weight_broadcast": {"bytes": bcast_bytes, "ms": round(bcast_ms, 2), "what": "packed bf16 kernel operands"},
+            "weight_broadcast": {"bytes": bcast_bytes, "ms": round(bcast_ms, 2), "what": "packed bf16 kernel operands",
+                                 "identical_on_all_ranks": weights_identical},
             "roofline": roof,
             "roofline_vit_blocks": roof_vit,
             "roofline_hbm": roof_hbm,

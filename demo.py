@@ -25,9 +25,18 @@ _VIRIDIS = np.array([[68, 1, 84], [72, 40, 120], [62, 74, 137], [49, 104, 142], 
 
 
 def viridis(a: np.ndarray) -> np.ndarray:
-    """plt.imsave(cmap='viridis') behaviour: normalise to the data range, map through the colormap."""
+    """Depth colouring of demo.py:147 `plt.imsave(path, depth, cmap='viridis')`: normalise to the data range, map through
+    viridis.  With matplotlib installed its own 256-entry LUT and quantisation are used (the reference's exact RGB
+    values; the reference writes RGBA, this writes RGB).  matplotlib is absent from this image and its table is not
+    reproducible offline: the fallback interpolates ten anchor colours of the map and is off by a few levels between
+    anchors — a visual approximation, not a bit-exact one."""
     lo, hi = float(a.min()), float(a.max())
     t = (a - lo) / (hi - lo) if hi > lo else np.zeros_like(a)
+    try:
+        from matplotlib import cm
+        return (cm.get_cmap("viridis")(t, bytes=True)[..., :3]).astype(np.uint8)
+    except Exception:
+        pass
     pos = t * (len(_VIRIDIS) - 1)
     i0 = np.clip(np.floor(pos).astype(int), 0, len(_VIRIDIS) - 2)
     w = (pos - i0)[..., None]

@@ -201,5 +201,32 @@ def check(rc: int, what: str = ""):
         raise OdbError(f"{what or 'omnidata_b200'} failed (status {rc}): {msg}")
 
 
+def on_tensor_device(fn):
+    """Decorator for host entry points that enqueue C-ABI work with `torch.cuda.current_stream()`: makes the device of
+    the first CUDA tensor argument (or of an object argument with a CUDA `.device`) current for the duration of the
+    call, so that kernels, kernel attributes and streams all belong to the device the data lives on."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        import torch
+        dev = None
+        for a in list(args) + list(kw.values()):
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    dev = a.device
+                    break
+                continue
+            d = getattr(a, "device", None)
+            if isinstance(d, torch.device) and d.type == "cuda":
+                dev = d
+                break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
+
+
 def launch_count() -> int:
     return int(lib().odb_launch_count())

@@ -125,6 +125,7 @@ class DevicePreprocessor:
             self._plans[key] = _Plan(w, h, self.size, self.device)
         return self._plans[key]
 
+    @_capi.on_tensor_device
     def __call__(self, img, out: Optional[torch.Tensor] = None, out_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
         if not isinstance(img, torch.Tensor):
             img = torch.from_numpy(np.array(img))              # (copy: PIL buffers are read-only)
@@ -154,6 +155,7 @@ class DevicePreprocessor:
         return out
 
 
+@_capi.on_tensor_device
 def bicubic_resize(x: torch.Tensor, size: Tuple[int, int], *, clamp_in: bool = False, clamp_out: bool = False,
                    invert: bool = False) -> torch.Tensor:
     """F.interpolate(x, size, mode='bicubic') for fp32 [..., h, w] with demo.py's clamps / 1 - x fused."""
@@ -169,6 +171,7 @@ def bicubic_resize(x: torch.Tensor, size: Tuple[int, int], *, clamp_in: bool = F
     return out
 
 
+@_capi.on_tensor_device
 def to_uint8_hwc(x: torch.Tensor, clamp01: bool = True) -> torch.Tensor:
     """transforms.ToPILImage() arithmetic for a float [C, H, W] tensor: uint8 [H, W, C] = trunc(x * 255)."""
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3:

@@ -25,6 +25,7 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.detach().float().contiguous()
 
 
+@_capi.on_tensor_device
 def make_valid_mask(mask_float: torch.Tensor, max_pool_size: int = 4) -> torch.Tensor:
     """train_depth.py:215-242 (the 4-D [B,1,H,W] case): bool mask of pixels whose 4x4 cell is fully valid."""
     if mask_float.dim() == 3:
@@ -59,6 +60,7 @@ class _MidasFn(torch.autograd.Function):
     in the train step: target and mask are data)."""
 
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, prediction, target, mask, alpha, scales):
         p, g = _f32(prediction, "prediction"), _f32(target, "target")
         b = p.shape[0]
@@ -75,6 +77,7 @@ class _MidasFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, grad_out):
         p, g, m, ws = ctx.saved_tensors
         b, h, w, alpha, scales, off, shape, dtype = ctx.meta
@@ -124,6 +127,7 @@ class VNL_Loss(torch.nn.Module):
 
 class _VnlFn(torch.autograd.Function):
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, first, second, pts, fx, fy, delta_z, select):
         a, d = _f32(first, "gt_depth"), _f32(second, "pred_depth")
         b = a.shape[0]
@@ -140,6 +144,7 @@ class _VnlFn(torch.autograd.Function):
         return out[0]
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, grad_out):
         a, d, t1, t2, t3, scratch = ctx.saved_tensors
         b, h, w, n, fx, fy, select, shape, dtype = ctx.meta
@@ -166,6 +171,7 @@ def depth_step_losses(depth_preds, depth_gt, mask_float, midas: MidasLoss, vnl: 
 
 class _NormalLossFn(torch.autograd.Function):
     @staticmethod
+    @_capi.on_tensor_device
     def forward(ctx, preds, gt, mask_u8, clamp_preds):
         p, g = _f32(preds, "normal_preds"), _f32(gt, "normal_gt")
         b, _, h, w = p.shape
@@ -178,6 +184,7 @@ class _NormalLossFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_capi.on_tensor_device
     def backward(ctx, grad_out):
         p, g, m, ws = ctx.saved_tensors
         b, h, w, clamp_preds, dtype = ctx.meta
@@ -236,6 +243,7 @@ class DepthStepLoss:
             t = self._bufs[name] = torch.empty(tuple(shape), dtype=dtype, device=device)
         return t
 
+    @_capi.on_tensor_device
     @torch.no_grad()
     def __call__(self, pred: torch.Tensor, depth_gt: torch.Tensor, mask_float: torch.Tensor, full_mix: bool = True,
                  points=None):

@@ -305,7 +305,7 @@ class DPTDepthModel(nn.Module):
     @torch.no_grad()
     def _prepack(self, device) -> dict:
         sd = {k: v.detach().to(device) for k, v in self.state_dict().items()}
-        f32 = lambda k: sd[k].float().contiguous()
+        f32 = lambda k: sd[k].float().clone().contiguous()      # own storage: packed state never aliases a parameter
         wdt = torch.float32 if self._precision == "fp32" else torch.bfloat16
         bf = lambda t: t.to(wdt).contiguous()                      # operand storage type of the GEMM weights
         _pack = ops.pack_conv_weight

@@ -48,6 +48,7 @@ class FlatAdam:
         self._ws = torch.zeros(int(lib().odb_grad_norm_workspace_bytes()), device=flat_params.device, dtype=torch.uint8)
         self._clip = torch.zeros(2, device=flat_params.device, dtype=torch.float32)
 
+    @_capi.on_tensor_device
     def step(self, flat_grads: torch.Tensor, max_norm: Optional[float] = 10.0) -> Optional[torch.Tensor]:
         g = flat_grads
         if not g.is_cuda or g.dtype != torch.float32 or g.shape != self.params.shape or not g.is_contiguous():

@@ -117,7 +117,20 @@ def broadcast_packed_weights(model, device, src: int = 0) -> int:
             total += flat.numel() * flat.element_size()
     model._packed["pos_cache"] = {}
     model._graphs.clear()
+    model._packed_sig = model._weights_signature()      # the received operands are current: the next forward must not re-pack
     return total
+
+
+def packed_weights_identical(model, device) -> bool:
+    """True when every rank holds bit-identical packed operands (checked after broadcast_packed_weights): per-tensor
+    float64 checksums, MAX- and MIN-reduced."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return True
+    sums = torch.stack([t.double().abs().sum() + t.double().sum() * 0.5 for _, t in _packed_tensors(model._packed)]).to(device)
+    hi, lo = sums.clone(), sums.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return bool(torch.equal(hi, lo))
 
 
 def reduce_max(value: float, device) -> float:

@@ -24,6 +24,7 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.detach().float().contiguous()
 
 
+@_capi.on_tensor_device
 def compute_quantiles(depth: torch.Tensor, n_quantiles: int, eps: float = 0.0001) -> torch.Tensor:
     """compute_quantiles (:82-87) + the permute of :188 -> quantile_vals [B, n_quantiles + 1]."""
     d = _f32c(depth, "depth")
@@ -35,6 +36,7 @@ def compute_quantiles(depth: torch.Tensor, n_quantiles: int, eps: float = 0.0001
     return qv
 
 
+@_capi.on_tensor_device
 def refocus_image(rgb, depth, focus_distance, aperture_size, quantile_vals, return_segments: bool = False):
     """refocus_image (:144-157)."""
     x, d, qv = _f32c(rgb, "rgb"), _f32c(depth, "depth"), _f32c(quantile_vals, "quantile_vals")

@@ -171,3 +171,25 @@ def test_streaming_predictor_matches_direct_forward(setup):
             assert torch.equal(model(x.cuda()).cpu(), o)
     model.use_cuda_graph = False
     model.keep_taps = True
+
+
+def test_in_place_weight_updates_are_seen_by_the_next_forward(setup):
+    """Packed bf16 operands and captured graphs are derived state: an optimizer-style in-place update, a copy_ or
+    re-pointed storage must be picked up by the next forward without any explicit invalidation."""
+    from omnidata_b200.model import DPTDepthModel
+    r = setup[1]
+    model = DPTDepthModel(backbone="vitb_rn50_384")
+    model.load_state_dict(r["sd"], strict=True)
+    model = model.to("cuda:0").eval()
+    model.use_cuda_graph = True
+    x = r["x"][:1].cuda()
+    with torch.no_grad():
+        y0 = model(x).clone()
+        p = model.state_dict(keep_vars=True)["scratch.output_conv.4.bias"]
+        p.add_(0.25)                                           # in place: bumps the version counter
+        y1 = model(x).clone()
+        w = model.state_dict(keep_vars=True)["scratch.output_conv.2.weight"]
+        w.data = (w.data * 1.1).clone()                        # re-pointed storage
+        y2 = model(x).clone()
+    assert not torch.equal(y0, y1) and not torch.equal(y1, y2)
+    assert float((y1 - y0).max()) <= 0.25 + 1e-5 and float((y1 - y0).max()) > 0.2

@@ -123,3 +123,46 @@ def test_world2_gloo_bucketed_gradient_mean():
         assert p.exitcode == 0
     want = (torch.arange(76, dtype=torch.float32) * 1.5).tolist()
     assert res[0] == want and res[1] == want
+
+
+def _packed_worker(rank, world, port, out):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from omnidata_b200 import parallel
+    from omnidata_b200.model import DPTDepthModel
+    parallel.init_from_env("gloo")
+    model = DPTDepthModel()
+    if rank == 1:                                           # a different checkpoint on the receiving rank
+        with torch.no_grad():
+            for p in model.parameters():
+                p.mul_(1.5).add_(0.01)
+    sent = parallel.broadcast_packed_weights(model, torch.device("cpu"), src=0)
+    sig = 0.0
+    n_bf16 = 0
+    for _, t in parallel._packed_tensors(model._packed):
+        sig += float(t.double().abs().sum())
+        n_bf16 += t.numel() if t.dtype == torch.bfloat16 else 0
+    fresh = model._packed_sig == model._weights_signature()      # the staleness check will not re-pack the received weights
+    out.put((rank, sig, sent, n_bf16, fresh))
+    torch.distributed.destroy_process_group()
+
+
+def test_world2_gloo_packed_bf16_weight_broadcast():
+    """the PACKED kernel operands (bf16 GEMM weights + fp32 vectors, ~248 MB) travel, not the fp32 state_dict."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_packed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    (_, sig0, sent0, nb0, fresh0), (_, sig1, sent1, nb1, fresh1) = res
+    assert sig0 == sig1 and sig0 > 0                       # rank 1 now holds rank 0's packed weights
+    assert fresh0 and fresh1
+    assert 240e6 < sent0 < 256e6 and sent0 == sent1        # about half of the 493 MB fp32 state_dict
+    assert nb0 > 100e6
