@@ -30,14 +30,25 @@ def main(args):
 
     model = DPTDepthModel(backbone="vitb_rn50_384")
     sd = synthetic.make_state_dict(0, 1)                                       # same seed on every rank = identical replicas
-    # The seeded checkpoint leaves ~70 % of the output pixels behind the final ReLU (prediction exactly 0).  MidasLoss
-    # inverts the prediction (1 / (p + 1e-6), losses/midas_loss.py:147): at p = 0 its gradient is ~1e12 per pixel, one
-    # Adam step then kills the network — torch autograd + torch.optim.Adam over the reference arithmetic collapses the
-    # same way after ONE step (tests/diag_dynamics_gpu.py).  Shift the output bias so that the seeded network predicts
-    # inside (0, 1): a trained depth model's regime.  The arithmetic per step does not depend on the values.
-    sd["scratch.output_conv.4.bias"] = sd["scratch.output_conv.4.bias"] + 0.35
     model.load_state_dict(sd, strict=True)
-    model = model.to(dev).train()
+    model = model.to(dev)
+    # The seeded checkpoint leaves ~70 % of the output pixels behind the final ReLU (prediction exactly 0).  MidasLoss
+    # inverts the prediction (1 / (p + 1e-6), losses/midas_loss.py:147): at p = 0 its gradient is ~1e12 per pixel and one
+    # Adam step kills the network — torch autograd + torch.optim.Adam over the reference arithmetic collapses the same way
+    # after ONE step (tests/diag_dynamics_gpu.py).  Rescale the last 1x1 conv so that the seeded network predicts inside
+    # [0.1, 0.9] on a probe batch: a trained depth model's regime.  The arithmetic per step does not depend on the values.
+    probe = (torch.rand(4, 3, IMG, IMG, generator=torch.Generator().manual_seed(77)) * 2 - 1).to(dev)
+    w4, b4 = model.state_dict(keep_vars=True)["scratch.output_conv.4.weight"], model.state_dict(keep_vars=True)["scratch.output_conv.4.bias"]
+    with torch.no_grad():
+        b4.add_(100.0)                                  # nothing is clipped by the final ReLU: out = pre-activation + 100
+        model.eval()
+        pre = model(probe).float() - 100.0
+        b4.sub_(100.0)
+        lo, hi = float(pre.min()), float(pre.max())
+        sc = 0.8 / max(hi - lo, 1e-6)
+        w4.mul_(sc)
+        b4.copy_((b4 - lo) * sc + 0.1)
+    model.train()
     step = DepthTrainStep(model, lr=1e-5, clip=10.0, precision="bf16", input_size=(IMG, IMG))
 
     gen = torch.Generator(device="cpu").manual_seed(2000 + rank)
