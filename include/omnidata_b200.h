@@ -301,6 +301,15 @@ int odb_clamp01_bwd(const float* p, const float* g1, const float* g2, float* out
  * fwd `dtype` [n_pad][taps * c_pad] (odb_conv_gemm weight) and bwd `dtype` [c_pad][taps * n_pad] (dgrad weight). */
 int odb_pack_weight(const float* w, void* fwd, void* bwd, int32_t n, int32_t c, int32_t taps, int32_t n_pad, int32_t c_pad,
                     int32_t standardize, float eps, int32_t dtype, void* stream);
+/* Multi-tensor forms: one launch for a whole table of layers.  `items` is a DEVICE array of n_items records
+ *   pack:   { const float* w; void* fwd; void* bwd; int32 n, c, taps, n_pad, c_pad, standardize, first_block, first_tile; }
+ *   unpack: { const float* gp; const float* w; float* dw; int32 n, c, taps, c_pad, standardize, first_block, pad, pad; }
+ * first_block / first_tile: prefix sums of n_pad (pack rows), ceil(n_pad/32)*ceil(c_pad/32)*taps (transpose tiles), n (unpack
+ * rows); total_rows / total_tiles their totals; max_row_floats = max taps * c_pad over the table. */
+int odb_pack_weights_multi(const void* items, int32_t n_items, int32_t total_rows, int32_t total_tiles, float eps, int32_t dtype,
+                           void* stream);
+int odb_unpack_wgrads_multi(const void* items, int32_t n_items, int32_t total_rows, int32_t max_row_floats, float eps,
+                            void* stream);
 /* Packed-layout weight gradient gp fp32 [n][taps * c_pad] -> parameter layout dw fp32 [n][c][taps], through the weight
  * standardisation when `standardize` (w = the fp32 parameter). */
 int odb_unpack_wgrad(const float* gp, const float* w, float* dw, int32_t n, int32_t c, int32_t taps, int32_t c_pad,

@@ -62,6 +62,18 @@ class ConvGemmDesc(C.Structure):
     ]
 
 
+class PackItem(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("fwd", C.c_void_p), ("bwd", C.c_void_p), ("n", C.c_int32), ("c", C.c_int32),
+                ("taps", C.c_int32), ("n_pad", C.c_int32), ("c_pad", C.c_int32), ("standardize", C.c_int32),
+                ("first_block", C.c_int32), ("first_tile", C.c_int32)]
+
+
+class UnpackItem(C.Structure):
+    _fields_ = [("gp", C.c_void_p), ("w", C.c_void_p), ("dw", C.c_void_p), ("n", C.c_int32), ("c", C.c_int32),
+                ("taps", C.c_int32), ("c_pad", C.c_int32), ("standardize", C.c_int32), ("first_block", C.c_int32),
+                ("pad0", C.c_int32), ("pad1", C.c_int32)]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [
         ("num_views", C.c_int32),
@@ -130,6 +142,8 @@ _SIGNATURES = {
     "odb_clamp01": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "odb_clamp01_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]),
     "odb_pack_weight": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 6 + [C.c_float, C.c_int32, C.c_void_p]),
+    "odb_pack_weights_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "odb_unpack_wgrads_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "odb_unpack_wgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
     "odb_make_valid_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "odb_midas_loss_workspace_bytes": (C.c_int64, [C.c_int32]),

@@ -144,6 +144,56 @@ def unpack_wgrad(gp, w, dw, n: int, c: int, taps: int, c_pad: int, standardize: 
           taps, c_pad, 1 if standardize else 0, eps)
 
 
+def _item_table(items, device) -> torch.Tensor:
+    """ctypes records -> one device byte tensor (the multi-tensor kernels' tables)."""
+    import numpy as np
+    raw = b"".join(bytes(it) for it in items)
+    return torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()).to(device)
+
+
+class PackTable:
+    """One-launch weight packing of a fixed set of layers (pointers are captured: the buffers must stay alive)."""
+
+    def __init__(self, layers, dtype):
+        """layers: (w fp32 [n][c][taps], fwd, bwd, n, c, taps, n_pad, c_pad, standardize)."""
+        items, rows, tiles = [], 0, 0
+        keep = []
+        for w, fwd, bwd_, n, c, taps, n_pad, c_pad, std in layers:
+            items.append(_capi.PackItem(w.data_ptr(), fwd.data_ptr(), bwd_.data_ptr(), n, c, taps, n_pad, c_pad, 1 if std else 0,
+                                        rows, tiles))
+            rows += n_pad
+            tiles += ((n_pad + 31) // 32) * ((c_pad + 31) // 32) * taps
+            keep += [w, fwd, bwd_]
+        self.keep, self.n, self.rows, self.tiles = keep, len(items), rows, tiles
+        self.table = _item_table(items, layers[0][0].device)
+        self.dtype = _capi.DTYPE_F32 if dtype == torch.float32 else _capi.DTYPE_BF16
+        self.device = layers[0][0].device
+
+    def run(self, eps: float = 1e-8):
+        _call("odb_pack_weights_multi", {}, lib().odb_pack_weights_multi, self.device, self.table.data_ptr(), self.n, self.rows,
+              self.tiles, eps, self.dtype)
+
+
+class UnpackTable:
+    """One-launch conversion of packed-layout weight gradients into parameter layout (+ weight-standardisation backward)."""
+
+    def __init__(self, layers):
+        """layers: (gp fp32 [n_pad][taps*c_pad], w fp32 param, dw fp32 grad, n, c, taps, c_pad, standardize)."""
+        items, rows, mx, keep = [], 0, 1, []
+        for gp, w, dw, n, c, taps, c_pad, std in layers:
+            items.append(_capi.UnpackItem(gp.data_ptr(), w.data_ptr(), dw.data_ptr(), n, c, taps, c_pad, 1 if std else 0, rows, 0, 0))
+            rows += n
+            mx = max(mx, taps * c_pad)
+            keep += [gp, w, dw]
+        self.keep, self.n, self.rows, self.max_row = keep, len(items), rows, mx
+        self.device = layers[0][0].device
+        self.table = _item_table(items, self.device)
+
+    def run(self, eps: float = 1e-8):
+        _call("odb_unpack_wgrads_multi", {}, lib().odb_unpack_wgrads_multi, self.device, self.table.data_ptr(), self.n, self.rows,
+              self.max_row, eps)
+
+
 def conv_wgrad(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]], dy: torch.Tensor, out: torch.Tensor,
                accumulate: bool = False):
     """out fp32 [n][len(taps) * C] (+)= sum_pixels dy[pixel, n] * view_t[pixel + offset_t, c]."""

@@ -661,6 +661,122 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
   }
 }
 
+// ---- multi-tensor versions: ONE launch packs / unpacks every layer of a table (the per-layer launches of ~100 small
+// kernels cost more in launch gaps than in work).  Tables live in device memory; blockIdx.x -> (item, row) by binary search
+// over the items' first block.
+struct PackItem {
+  const float* w; void* fwd; void* bwd;
+  int n, c, taps, n_pad, c_pad, standardize, first_block, first_tile;
+};
+struct UnpackItem {
+  const float* gp; const float* w; float* dw;
+  int n, c, taps, c_pad, standardize, first_block, pad0, pad1;
+};
+template <typename Item>
+ODB_DEVINL int find_item(const Item* items, int n_items, int block, int Item::*first) {
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].*first <= block) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackItem* __restrict__ items, int n_items, float eps) {
+  const PackItem it = items[find_item(items, n_items, (int)blockIdx.x, &PackItem::first_block)];
+  const int n = blockIdx.x - it.first_block;
+  const int K = it.c * it.taps;
+  __shared__ double red[2][256];
+  __shared__ float s_mean, s_inv;
+  float mean = 0.f, inv = 1.f;
+  if (n < it.n && it.standardize) {
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) { const double v = it.w[(long long)n * K + i]; s += v; q += v * v; }
+    red[0][threadIdx.x] = s; red[1][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double ts = 0.0, tq = 0.0;
+      for (int i = 0; i < 256; ++i) { ts += red[0][i]; tq += red[1][i]; }
+      const double m = ts / K;
+      double var = tq / K - m * m;
+      if (var < 0.0) var = 0.0;
+      s_mean = (float)m;
+      s_inv = (float)(1.0 / (sqrt(var) + (double)eps));
+    }
+    __syncthreads();
+    mean = s_mean; inv = s_inv;
+  }
+  T* fwd = static_cast<T*>(it.fwd);
+  for (int i = threadIdx.x; i < it.c_pad * it.taps; i += blockDim.x) {
+    const int t = i / it.c_pad, c = i - t * it.c_pad;
+    float v = 0.f;
+    if (n < it.n && c < it.c) v = (it.w[((long long)n * it.c + c) * it.taps + t] - mean) * inv;
+    stf(fwd + (long long)n * it.taps * it.c_pad + i, v);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) pack_transpose_multi_kernel(const PackItem* __restrict__ items, int n_items) {
+  const PackItem it = items[find_item(items, n_items, (int)blockIdx.x, &PackItem::first_tile)];
+  __shared__ float tile[32][33];
+  int tl = blockIdx.x - it.first_tile;
+  const int tn = (it.n_pad + 31) / 32, tc = (it.c_pad + 31) / 32;
+  const int n0 = (tl % tn) * 32; tl /= tn;
+  const int c0 = (tl % tc) * 32;
+  const int t = tl / tc;
+  const T* fwd = static_cast<const T*>(it.fwd);
+  T* bwd = static_cast<T*>(it.bwd);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    tile[r][tx] = (n0 + r < it.n_pad && c0 + tx < it.c_pad) ? ldf(fwd + ((long long)(n0 + r) * it.taps + t) * it.c_pad + c0 + tx) : 0.f;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (c0 + r < it.c_pad && n0 + tx < it.n_pad)
+      stf(bwd + ((long long)(c0 + r) * it.taps + (it.taps - 1 - t)) * it.n_pad + n0 + tx, tile[tx][r]);
+}
+__global__ void __launch_bounds__(256) unpack_wgrads_multi_kernel(const UnpackItem* __restrict__ items, int n_items, float eps) {
+  extern __shared__ float row[];
+  const UnpackItem it = items[find_item(items, n_items, (int)blockIdx.x, &UnpackItem::first_block)];
+  const int n = blockIdx.x - it.first_block;
+  const int K = it.c * it.taps, taps = it.taps, c_pad = it.c_pad;
+  for (int i = threadIdx.x; i < taps * c_pad; i += blockDim.x) row[i] = it.gp[(long long)n * taps * c_pad + i];
+  __syncthreads();
+  if (!it.standardize) {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const int c = i / taps, t = i - c * taps;
+      it.dw[(long long)n * K + i] = row[t * c_pad + c];
+    }
+    return;
+  }
+  __shared__ double red[4][256];
+  double s = 0.0, q = 0.0, sg = 0.0, sgw = 0.0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int c = i / taps, t = i - c * taps;
+    const double v = it.w[(long long)n * K + i], g = row[t * c_pad + c];
+    s += v; q += v * v; sg += g; sgw += g * v;
+  }
+  red[0][threadIdx.x] = s; red[1][threadIdx.x] = q; red[2][threadIdx.x] = sg; red[3][threadIdx.x] = sgw;
+  __syncthreads();
+  __shared__ double st[4];
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int i = 0; i < 256; ++i) t += red[threadIdx.x][i];
+    st[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const double mean = st[0] / K;
+  double var = st[1] / K - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double sigma = sqrt(var), sden = sigma + (double)eps;
+  const double mg = st[2] / K;
+  const double mgw = (st[3] - mean * st[2]) / (sden * K);
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int c = i / taps, t = i - c * taps;
+    const double v = it.w[(long long)n * K + i], g = row[t * c_pad + c];
+    const double what = (v - mean) / sden;
+    it.dw[(long long)n * K + i] = (float)((g - mg) / sden - (sigma > 0.0 ? mgw * what / sigma : 0.0));
+  }
+}
+
 // ---- train_depth.py:263 `depth_preds = torch.clamp(depth_preds, 0, 1)` and its backward (sum of the loss gradients,
 // passed where 0 <= p <= 1 as torch does)
 __global__ void __launch_bounds__(256) clamp01_kernel(const float* __restrict__ p, float* __restrict__ out, long long n) {
@@ -1004,4 +1120,29 @@ extern "C" int odb_clamp01_bwd(const float* p, const float* g1, const float* g2,
   clamp01_bwd_kernel<<<grid_for(n), 256, 0, stream>>>(p, g1, g2, out, n);
   count_launch();
   return check_launch("clamp01_bwd");
+}
+
+extern "C" int odb_pack_weights_multi(const void* items, int32_t n_items, int32_t total_rows, int32_t total_tiles, float eps,
+                                      int32_t dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!items || n_items < 1 || total_rows < 1 || total_tiles < 0) return fail(ODB_ERR_INVALID, "pack_weights_multi: bad argument");
+  const PackItem* it = static_cast<const PackItem*>(items);
+  ODB_DT(dtype, T, "pack_weights_multi", pack_weights_multi_kernel<T><<<total_rows, 256, 0, stream>>>(it, n_items, eps));
+  count_launch();
+  if (total_tiles > 0) {
+    ODB_DT(dtype, T, "pack_weights_multi", pack_transpose_multi_kernel<T><<<total_tiles, 256, 0, stream>>>(it, n_items));
+    count_launch();
+  }
+  return check_launch("pack_weights_multi");
+}
+
+extern "C" int odb_unpack_wgrads_multi(const void* items, int32_t n_items, int32_t total_rows, int32_t max_row_floats, float eps,
+                                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!items || n_items < 1 || total_rows < 1 || max_row_floats < 1 || (long long)max_row_floats * 4 > 40 * 1024)
+    return fail(ODB_ERR_INVALID, "unpack_wgrads_multi: bad argument (rows of at most 10240 floats)");
+  unpack_wgrads_multi_kernel<<<total_rows, 256, (size_t)max_row_floats * sizeof(float), stream>>>(
+      static_cast<const UnpackItem*>(items), n_items, eps);
+  count_launch();
+  return check_launch("unpack_wgrads_multi");
 }

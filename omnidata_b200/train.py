@@ -132,15 +132,27 @@ class TrainEngine:
             self.W[key] = (fwd, bwd_)
         self.meta = {key: (pname, n, c, taps, n_pad, std) for key, pname, n, c, taps, n_pad, std in T}
         self.gp = torch.empty(768 * 9 * 768, device=self.device, dtype=torch.float32)     # packed-layout wgrad scratch
+        # one-launch packing of all layers; packed-layout gradient buffers of the layers that need the unpack pass
+        # (3x3 taps or weight standardisation), converted by ONE launch per all-reduce bucket
+        self.pack_table = bwd.PackTable([(self.P[pn], self.W[k][0], self.W[k][1], n, c, taps, n_pad, c, std)
+                                         for k, pn, n, c, taps, n_pad, std in T], self.adt)
+        self.gp_layer: Dict[str, torch.Tensor] = {}
+        groups = {"decoder": [], "resnet": []}
+        for k, pn, n, c, taps, n_pad, std in T:
+            if taps == 1 and not std and n_pad == n:
+                continue                                           # written straight into the flat gradient
+            gp = torch.zeros((n_pad, taps * c), device=self.device, dtype=torch.float32)
+            self.gp_layer[k] = gp
+            tag = "resnet" if "backbone" in pn else "decoder"
+            groups[tag].append((gp, self.P[pn], self.G[pn], n, c, taps, c, std))
+        self.unpack_tables = {t: bwd.UnpackTable(v) for t, v in groups.items() if v}
         self.zb = torch.zeros(4096, device=self.device, dtype=torch.float32)               # zero "bias" of the dgrad convs:
         #   selects the straight-line (bias / bias + residual) epilogues of the tensor-core kernel
 
     @torch.no_grad()
     def pack(self):
         """fp32 master weights -> GEMM operands (every step: the optimizer just changed them)."""
-        for key, pname, n, c, taps, n_pad, std in self.layers:
-            fwd, bwd_ = self.W[key]
-            bwd.pack_weight(self.P[pname], fwd, bwd_, n, c, taps, n_pad, c, std)
+        self.pack_table.run()
         P = self.P
         bb = "pretrained.model.patch_embed.backbone."
         # stem 7x7 (3 input channels): [64,3,7,7] -> standardise -> [64, (ky,kx,c)=147] padded to 160 columns
@@ -175,9 +187,11 @@ class TrainEngine:
     def _wgrad(self, key: str, views, taps, dy, n_rows: Optional[int] = None):
         """weight gradient of layer `key` into the flat gradient buffer (through the weight standardisation)."""
         pname, n, c, ntaps, n_pad, std = self.meta[key]
-        gp = self.gp[: n_pad * ntaps * c].view(n_pad, ntaps * c)
-        bwd.conv_wgrad(views, taps, dy, gp)
-        bwd.unpack_wgrad(gp, self.P[pname], self.G[pname], n, c, ntaps, c, std)
+        if ntaps == 1 and not std and n_pad == n:
+            # linear / 1x1 layer without weight standardisation: the packed gradient layout IS the parameter layout
+            bwd.conv_wgrad(views, taps, dy, self.G[pname].view(n, c))
+            return
+        bwd.conv_wgrad(views, taps, dy, self.gp_layer[key])        # converted to parameter layout by the bucket's unpack launch
 
     def _bias_grad(self, pname: str, dy, n: Optional[int] = None):
         g = self.G[pname]
@@ -518,6 +532,7 @@ class TrainEngine:
 
         dtk4 = readout_bwd(4, du4)
         dtk3 = readout_bwd(3, d_layers[2])
+        self.unpack_tables["decoder"].run()
         ready("decoder")
         # ---- ViT blocks (fp32 stream gradient ds, activation-type copy ds16 for the GEMMs)
         pm = "pretrained.model."
@@ -636,6 +651,7 @@ class TrainEngine:
         g147 = buf("tmp.stem_g", (64, 147), f32)
         g147.copy_(gp[:, :147])
         bwd.unpack_wgrad(g147, P[bb + "stem.conv.weight"], G[bb + "stem.conv.weight"], 64, 3, 49, 3, True)
+        self.unpack_tables["resnet"].run()
         ready("resnet")
         return self.flat_grad
 
