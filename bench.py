@@ -480,10 +480,11 @@ def main():
         torch.distributed.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this round
-# (profiles/r02_*): filled by hand from the capture; None until a capture of the current build exists
-NCU_TRAFFIC = {"unit": "bytes per launch, mean over the launches captured (ncu --set full, profiles/r02_conv_gemm_ncu.csv)",
-               "conv_gemm_all": None}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this round (profiles/r02_*):
+# filled by hand from the capture (batch 32, configs[1])
+NCU_TRAFFIC = {"unit": "bytes per launch = (dram__bytes_read.sum + dram__bytes_write.sum) summed over the 130 conv_gemm launches of "
+                       "one batch-32 forward / 130 (profiles/r02_conv_gemm_ncu.csv: 9.96 GB read + 3.29 GB written)",
+               "conv_gemm_all": 101.9e6}
 
 
 if __name__ == "__main__":
