@@ -5,8 +5,8 @@
     norm = opt.step(flat_grads, max_norm=10.0)     # clip_grad_norm_ + Adam update; returns the norm tensor
 
 `flatten_parameters(module)` re-points a module's parameters into such a buffer (views), which is also the
-layout a bucketed gradient all-reduce wants.  The gradients themselves are not produced by this repo yet (the
-backward of the network is the next scope row); the step is exercised against torch.optim.Adam in the tests.
+layout the bucketed gradient all-reduce of `train.DepthTrainStep` wants (train.TrainEngine writes the network's
+gradients straight into the matching flat gradient buffer).  The step is checked against torch.optim.Adam in the tests.
 """
 from __future__ import annotations
 
