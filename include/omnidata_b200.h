@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ODB_ABI_VERSION 3
+#define ODB_ABI_VERSION 4
 
 typedef enum odb_status {
   ODB_OK = 0,
@@ -123,6 +123,17 @@ typedef struct odb_conv_gemm_desc {
    *                 partial sums combined in fp64; bias / act / residual / out2 as above, no gn_partial / head. */
   int32_t in_dtype;
   int32_t out_dtype;
+  /* With gn_partial: when gn_stats != NULL the call also delivers the finished statistics gn_stats[b][gn_groups][2] =
+   * (mean, 1/sqrt(var + gn_eps)), bit-identical to odb_groupnorm_finalize on gn_partial.  On the specialised epilogue the
+   * kernel does it itself: the CTA that completes the last tile of an image (per-image ticket in gn_counters: uint32 [b],
+   * zero before the first use, left zero by the kernel) reduces that image's partial sums — no second launch; on the
+   * generic epilogue odb_conv_gemm launches the reduction after the kernel. */
+  float* gn_stats;
+  uint32_t* gn_counters;
+  float gn_eps;
+  /* Activation of the out2 copy: ODB_ACT_NONE / ODB_ACT_RELU = relu (ResidualConvUnit's `relu(out)` operand),
+   * ODB_ACT_GELU = exact-erf GELU (train mode: out keeps the pre-activation of mlp.fc1 for the backward, out2 feeds fc2). */
+  int32_t out2_act;
 } odb_conv_gemm_desc;
 
 int odb_conv_gemm(const odb_conv_gemm_desc* desc, void* stream);
@@ -260,17 +271,19 @@ int odb_mask_add(const void* a, const void* b, const void* mask, void* out, int6
 int odb_gelu_fwd(const void* u, void* y, int64_t n, int32_t dtype, void* stream);
 int odb_gelu_bwd(const void* dy, const void* u, void* du, int64_t n, int32_t dtype, void* stream);
 /* Bias gradients: out[bt][n] (+)= sum over rows of x[bt][row][n] (row / batch strides in elements). */
-int64_t odb_colsum_workspace_bytes(int32_t batches, int32_t n);
+int64_t odb_colsum_workspace_bytes(int32_t batches, int64_t rows_per_batch, int32_t n);
 int odb_colsum(const void* x, float* out, void* workspace, int32_t batches, int64_t rows_per_batch, int32_t n,
                int64_t row_stride, int64_t batch_stride, int32_t accumulate, int32_t dtype, void* stream);
-/* out[bt][i] (+)= sum_p partial[bt][p][i] in fp64, p ascending. */
+/* out[bt][i] (+)= sum_p partial[bt][p][i] in fp64, in a fixed order (8 interleaved part lanes, then the lanes). */
 int odb_reduce_partials(const float* partial, float* out, int32_t batches, int32_t parts, int64_t n, int32_t accumulate,
                         void* stream);
 /* LayerNorm backward on the fp32 residual stream: ds_out = ds_in + dLN(dy; x, gamma) (ds_in may be NULL), optional
- * copy of ds_out in `dtype` (the next GEMM operand), dgamma / dbeta (+)=. */
+ * copy of ds_out in `dtype` (the next GEMM operand), dgamma / dbeta (+)=, and optionally (dcolsum != NULL) the column
+ * sums of ds_out (+)= : the bias gradient of the linear layer whose output gradient ds_out is (timm Block: attn.proj
+ * after norm2's backward, the previous block's mlp.fc2 after norm1's). */
 int64_t odb_layernorm_bwd_workspace_bytes(int32_t cols);
 int odb_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* ds_in, float* ds_out, void* ds_copy,
-                      float* dgamma, float* dbeta, void* workspace, int64_t rows, int32_t cols, float eps,
+                      float* dgamma, float* dbeta, float* dcolsum, void* workspace, int64_t rows, int32_t cols, float eps,
                       int32_t accumulate, int32_t dtype, void* stream);
 /* GroupNorm backward (timm GroupNormAct): g = dy * [mask > 0] (mask NULL: g = dy; the mask is the stored output of the
  * ReLU that follows the norm); dx, dgamma (+)=, dbeta (+)= from x and the forward statistics (mean, rstd). */

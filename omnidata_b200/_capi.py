@@ -59,6 +59,10 @@ class ConvGemmDesc(C.Structure):
         ("epilogue", C.c_int32),
         ("in_dtype", C.c_int32),
         ("out_dtype", C.c_int32),
+        ("gn_stats", C.c_void_p),
+        ("gn_counters", C.c_void_p),
+        ("gn_eps", C.c_float),
+        ("out2_act", C.c_int32),
     ]
 
 
@@ -125,12 +129,12 @@ _SIGNATURES = {
     "odb_mask_add": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p]),
     "odb_gelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "odb_gelu_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p]),
-    "odb_colsum_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "odb_colsum_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32]),
     "odb_colsum": (C.c_int, [C.c_void_p] * 3 + [C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                                 C.c_void_p]),
     "odb_reduce_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "odb_layernorm_bwd_workspace_bytes": (C.c_int64, [C.c_int32]),
-    "odb_layernorm_bwd": (C.c_int, [C.c_void_p] * 9 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
+    "odb_layernorm_bwd": (C.c_int, [C.c_void_p] * 10 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "odb_groupnorm_bwd_workspace_bytes": (C.c_int64, [C.c_int32] * 4),
     "odb_groupnorm_bwd": (C.c_int, [C.c_void_p] * 9 + [C.c_int32] * 6 + [C.c_void_p]),
     "odb_upsample2x_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p]),
@@ -182,7 +186,7 @@ _SIGNATURES = {
     "odb_debug_conv_trace": (C.c_int, [C.c_void_p]),
 }
 
-ABI_VERSION = 3        # include/omnidata_b200.h: ODB_ABI_VERSION (descriptor layouts this module mirrors)
+ABI_VERSION = 4        # include/omnidata_b200.h: ODB_ABI_VERSION (descriptor layouts this module mirrors)
 
 _lib = None
 

@@ -70,18 +70,24 @@ def colsum(x, out, accumulate: bool = False, batches: int = 1):
         rows, row_stride, batch_stride = x.shape[0] // batches, n, (x.shape[0] // batches) * n
     if x.stride(-1) != 1:
         raise _capi.OdbError("colsum: unit stride in the last dim required")
-    ws = _scratch(lib().odb_colsum_workspace_bytes(batches, n), x.device)
+    ws = _scratch(lib().odb_colsum_workspace_bytes(batches, rows, n), x.device)
     _call("odb_colsum", {"bytes": x.element_size() * batches * rows * n}, lib().odb_colsum, _same_device(x, out), x.data_ptr(),
           out.data_ptr(), ws.data_ptr(), batches, rows, n, row_stride, batch_stride, 1 if accumulate else 0, _dt(x))
 
 
-def layernorm_bwd(dy, x, gamma, ds_in, ds_out, ds_copy, dgamma, dbeta, eps: float = 1e-6, accumulate: bool = False):
+def layernorm_bwd(dy, x, gamma, ds_in, ds_out, ds_copy, dgamma, dbeta, eps: float = 1e-6, accumulate: bool = False,
+                  dcolsum=None):
+    """`dcolsum` (fp32 [cols], optional): column sums of ds_out, i.e. the bias gradient of the linear layer whose output
+    gradient ds_out is — saves a separate pass over the fp32 stream."""
     _need(x, torch.float32, "x"); _need(ds_out, torch.float32, "ds_out")
+    if dcolsum is not None:
+        _need(dcolsum, torch.float32, "dcolsum")
     rows, cols = x.numel() // x.shape[-1], x.shape[-1]
     ws = _scratch(lib().odb_layernorm_bwd_workspace_bytes(cols), x.device)
     _call("odb_layernorm_bwd", {"bytes": x.numel() * (8 + dy.element_size() * 2)}, lib().odb_layernorm_bwd,
-          _same_device(dy, x, gamma, ds_in, ds_out, ds_copy, dgamma, dbeta), dy.data_ptr(), x.data_ptr(), gamma.data_ptr(),
-          _ptr(ds_in), ds_out.data_ptr(), _ptr(ds_copy), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), rows, cols, eps,
+          _same_device(dy, x, gamma, ds_in, ds_out, ds_copy, dgamma, dbeta, dcolsum), dy.data_ptr(), x.data_ptr(),
+          gamma.data_ptr(), _ptr(ds_in), ds_out.data_ptr(), _ptr(ds_copy), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dcolsum),
+          ws.data_ptr(), rows, cols, eps,
           1 if accumulate else 0, _dt(dy))
 
 
@@ -162,7 +168,7 @@ class PackTable:
             items.append(_capi.PackItem(w.data_ptr(), fwd.data_ptr(), bwd_.data_ptr(), n, c, taps, n_pad, c_pad, 1 if std else 0,
                                         rows, tiles))
             rows += n_pad
-            tiles += ((n_pad + 31) // 32) * ((c_pad + 31) // 32) * taps
+            tiles += ((n_pad + 63) // 64) * ((c_pad + 63) // 64) * taps           # kPackTile (bwd_ops.cu)
             keep += [w, fwd, bwd_]
         self.keep, self.n, self.rows, self.tiles = keep, len(items), rows, tiles
         self.table = _item_table(items, layers[0][0].device)

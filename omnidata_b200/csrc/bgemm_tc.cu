@@ -299,6 +299,18 @@ __global__ void __launch_bounds__(256) bg_sum_splits_kernel(const float* __restr
     out[i] = (float)t;
   }
 }
+// many splits (small gradients split over the whole chip): 8 split lanes per element shorten the dependent chain;
+// grid ceil(n / 32)
+__global__ void __launch_bounds__(256) bg_sum_splits_lanes_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                                  int splits, long long n, int accumulate) {
+  const long long i = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+  const float* src = partial + i;
+  double t = ordered_sum8(splits, i < n, [&](int s) { return __ldg(src + (long long)s * n); });
+  if (threadIdx.x < 32 && i < n) {
+    if (accumulate) t += (double)out[i];
+    out[i] = (float)t;
+  }
+}
 
 // D[b][h][row] = sum_d dO[b][row][h*64+d] * O[b][row][h*64+d]
 __global__ void __launch_bounds__(256) attn_rowdot_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o,
@@ -467,10 +479,15 @@ int conv_wgrad_tc(const odb_wgrad_desc* d, cudaStream_t stream) {
   rc = bg_launch(p, stream);
   if (rc || direct) return rc;
   const long long total = (long long)n * pl.row_len;
-  long long blocks = (total + 255) / 256;
-  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
-  bg_sum_splits_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float*>(d->workspace), d->out, pl.splits, total,
-                                                             d->accumulate);
+  if (pl.splits >= 16) {
+    bg_sum_splits_lanes_kernel<<<(unsigned)((total + 31) / 32), 256, 0, stream>>>(static_cast<const float*>(d->workspace), d->out,
+                                                                                  pl.splits, total, d->accumulate);
+  } else {
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    bg_sum_splits_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const float*>(d->workspace), d->out, pl.splits, total,
+                                                               d->accumulate);
+  }
   count_launch();
   return check_launch("conv_wgrad: split reduction");
 }

@@ -33,6 +33,12 @@ ODB_DEVINL float ldf(const bf16* p) { return __bfloat162float(*p); }
 ODB_DEVINL float ldf(const float* p) { return *p; }
 ODB_DEVINL void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
 ODB_DEVINL void stf(float* p, float v) { *p = v; }
+ODB_DEVINL float2 ld2(const bf16* p) { return unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p)); }
+ODB_DEVINL float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+ODB_DEVINL void st2(bf16* p, float2 v) { *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v.x, v.y); }
+ODB_DEVINL void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+ODB_DEVINL void st4(bf16* p, float4 v) { *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)); }
+ODB_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 static unsigned grid_for(long long items, int block = 256, int per_sm = 16) {
   long long blocks = (items + block - 1) / block;
@@ -94,15 +100,26 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ dy,
 }
 
 // ------------------------------------------------------------------------------------------ column sums (bias grads)
-// out[bt][n] = sum over rows_per_batch rows of x[bt][row][n]; stage 1: slab partials (fixed 64 slabs per batch),
-// stage 2: ordered fp64 combination.  x rows may be strided (row_stride elements).
-constexpr int kColsumSlabs = 128;   // upper bound of row slabs per batch (workspace sizing); the launch uses min(this, rows / 64)
+// out[bt][n] = sum over rows_per_batch rows of x[bt][row][n]; stage 1: slab partials, stage 2: ordered fp64 combination.
+// x rows may be strided (row_stride elements).
+constexpr int kColsumMaxSlabs = 512;
+constexpr int kColsumTargetBlocks = 148 * 8;
+// row slabs per batch: enough blocks to fill the chip, at least 64 rows (two per row lane) per slab
+static int colsum_slabs(long long batches, long long rows_per_batch, long long n) {
+  const long long col_blocks = (n + 63) / 64;
+  long long want = (kColsumTargetBlocks + col_blocks * batches - 1) / (col_blocks * batches);
+  const long long by_rows = rows_per_batch / 64;
+  if (want > by_rows) want = by_rows;
+  if (want > kColsumMaxSlabs) want = kColsumMaxSlabs;
+  if (want < 1) want = 1;
+  return (int)want;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, float* __restrict__ partial,
                                                              long long rows_per_batch, int n, long long row_stride,
                                                              long long batch_stride, int slabs) {
   // block: 8 column octets (64 columns = one 128-byte bf16 segment per row) x 32 row lanes;
-  // grid (ceil(n / 64), slabs, batches)
+  // grid (ceil(n / 64), slabs, batches); four independent row loads in flight per thread
   const int oct = threadIdx.x & 7, lane_r = threadIdx.x >> 3;
   const int c0 = (blockIdx.x * 8 + oct) * 8;
   const int slab = blockIdx.y, bt = blockIdx.z;
@@ -111,11 +128,17 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < n) {
     const T* base = x + bt * batch_stride + c0;
-    for (long long r = r0 + lane_r; r < r1; r += 32) {
-      float v[8];
-      ld8(base + r * row_stride, v);
+    for (long long r = r0 + lane_r; r < r1; r += 128) {
+      float v[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      for (int u = 0; u < 4; ++u)
+        if (r + 32 * u < r1) ld8(base + (r + 32 * u) * row_stride, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + 32 * u < r1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+        }
     }
   }
   __shared__ float s[32][64];
@@ -129,13 +152,14 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
     partial[((long long)bt * slabs + slab) * n + blockIdx.x * 64 + threadIdx.x] = t;
   }
 }
-// out[bt][c] (+)= sum over `parts` partial rows (fp64, fixed order); scale applied to the sum
+// out[bt][c] (+)= sum over `parts` partial rows (ordered_sum8); grid (ceil(n / 32), batches)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                               int parts, long long n, int accumulate) {
   const long long bt = blockIdx.y;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
-    double t = 0.0;
-    for (int p = 0; p < parts; ++p) t += (double)partial[(bt * parts + p) * n + c];
+  const long long c = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+  const float* src = partial + bt * parts * n + c;
+  double t = ordered_sum8(parts, c < n, [&](int p) { return __ldg(src + (long long)p * n); });
+  if (threadIdx.x < 32 && c < n) {
     if (accumulate) t += (double)out[bt * n + c];
     out[bt * n + c] = (float)t;
   }
@@ -144,30 +168,65 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // ------------------------------------------------------------------------------------------ LayerNorm backward
 // y = (x - mean) * rstd * g + b over the last dim.  Per row:  dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)).
 // ds_out = ds_in + dx (the residual-stream gradient, fp32) and optionally a T copy of it (the next GEMM operand).
-// dgamma / dbeta: each block accumulates its rows in registers and writes one partial row [2][cols].
+// dgamma / dbeta and (optionally) the column sums of ds_out (the bias gradient of the linear layer whose output gradient
+// ds_out is): each block accumulates its rows in registers and writes one partial row [3][cols].
+// One warp per row, the next row's loads are issued before the current row is reduced (one block per SM, 8 warps).
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 u;
+  ODB_DEVINL void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  ODB_DEVINL void get(float* v) const {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  ODB_DEVINL void load(const float* p) { a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1]; }
+  ODB_DEVINL void get(float* v) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+};
 template <int VPL, typename T>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x,
-                                                            const float* __restrict__ gamma, const float* __restrict__ ds_in,
-                                                            float* __restrict__ ds_out, T* __restrict__ ds_copy,
-                                                            float* __restrict__ partial, long long rows, float eps) {
+__global__ void __launch_bounds__(256, 1) layernorm_bwd_kernel(const T* __restrict__ dy, const float* __restrict__ x,
+                                                               const float* __restrict__ gamma, const float* __restrict__ ds_in,
+                                                               float* __restrict__ ds_out, T* __restrict__ ds_copy,
+                                                               float* __restrict__ partial, long long rows, float eps,
+                                                               int want_colsum) {
   constexpr int COLS = VPL * 256;
+  __shared__ float sh[8][COLS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float g[VPL][8], dg[VPL][8], db[VPL][8];
+  float g[VPL][8], dg[VPL][8], db[VPL][8], dc[VPL][8];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int c0 = (i * 32 + lane) * 8;
-    ld8(gamma + c0, g[i]);
+    ld8(gamma + (i * 32 + lane) * 8, g[i]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; dc[i][j] = 0.f; }
   }
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+  const long long stride = (long long)gridDim.x * 8;
+  long long row = (long long)blockIdx.x * 8 + warp;
+  Raw8<float> xr[VPL], xn[VPL];
+  Raw8<T> dr[VPL], dn[VPL];
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xr[i].load(x + row * COLS + (i * 32 + lane) * 8);
+      dr[i].load(dy + row * COLS + (i * 32 + lane) * 8);
+    }
+  }
+  while (row < rows) {
+    const long long next = row + stride;
+    if (next < rows) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        xn[i].load(x + next * COLS + (i * 32 + lane) * 8);
+        dn[i].load(dy + next * COLS + (i * 32 + lane) * 8);
+      }
+    }
     float xv[VPL][8], dv[VPL][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int c0 = (i * 32 + lane) * 8;
-      ld8(x + row * COLS + c0, xv[i]);
-      ld8(dy + row * COLS + c0, dv[i]);
+      xr[i].get(xv[i]);
+      dr[i].get(dv[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += xv[i][j];
     }
@@ -203,26 +262,48 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
         for (int j = 0; j < 8; ++j) o[j] = 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += rstd * (dv[i][j] * g[i][j] - s1 - xv[i][j] * s2);
+      for (int j = 0; j < 8; ++j) {
+        o[j] += rstd * (dv[i][j] * g[i][j] - s1 - xv[i][j] * s2);
+        dc[i][j] += o[j];
+      }
       st8(ds_out + row * COLS + c0, o);
       if (ds_copy != nullptr) st8(ds_copy + row * COLS + c0, o);
     }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { xr[i] = xn[i]; dr[i] = dn[i]; }
+    row = next;
   }
-  // block partial of dgamma / dbeta: 8 warps combined in a fixed order through shared memory
-  __shared__ float sh[8][COLS];
-  for (int pass = 0; pass < 2; ++pass) {
+  // block partials of dgamma / dbeta / column sums: 8 warps combined in a fixed order through shared memory
+  const int passes = want_colsum ? 3 : 2;
+  for (int pass = 0; pass < passes; ++pass) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sh[warp][(i * 32 + lane) * 8 + j] = pass == 0 ? dg[i][j] : db[i][j];
+      for (int j = 0; j < 8; ++j) sh[warp][(i * 32 + lane) * 8 + j] = pass == 0 ? dg[i][j] : (pass == 1 ? db[i][j] : dc[i][j]);
     __syncthreads();
     for (int c = threadIdx.x; c < COLS; c += 256) {
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += sh[w][c];
-      partial[((long long)blockIdx.x * 2 + pass) * COLS + c] = t;
+      partial[((long long)blockIdx.x * 3 + pass) * COLS + c] = t;
     }
     __syncthreads();
+  }
+}
+// dgamma / dbeta / colsum (+)= ordered sum of the block partials [blocks][3][cols]; grid ceil(passes * cols / 32)
+__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ dcol, int blocks,
+                                                              int cols, int accumulate) {
+  const int passes = dcol != nullptr ? 3 : 2;
+  const int e = blockIdx.x * 32 + (threadIdx.x & 31);          // pass * cols + column
+  const bool active = e < passes * cols;
+  const float* src = partial + e;
+  double t = ordered_sum8(blocks, active, [&](int b) { return __ldg(src + (long long)b * 3 * cols); });
+  if (threadIdx.x < 32 && active) {
+    const int pass = e / cols, c = e - pass * cols;
+    float* dst = (pass == 0 ? dgamma : (pass == 1 ? dbeta : dcol)) + c;
+    if (accumulate) t += (double)*dst;
+    *dst = (float)t;
   }
 }
 
@@ -268,23 +349,35 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_sums_kernel(const T* __rest
     dst[1] = (float)tq;
   }
 }
-// stage 2 (one block per image): reduce the slabs, then the per-(image, channel / group) coefficients of
+// stage 2 (one block per image, 1024 threads): reduce the slabs (L = 1024 / c slab lanes per channel, each lane sums
+// slabs l, l+L, ... in fp64, lanes combined in lane order), then the per-(image, channel / group) coefficients of
 //   dx = A[c] * g + Bg[group] * x + Cg[group]   and this image's share of dgamma / dbeta.
-__global__ void __launch_bounds__(256) groupnorm_bwd_coef_kernel(const float* __restrict__ partial, const float* __restrict__ stats,
-                                                                 const float* __restrict__ gamma, float* __restrict__ coef,
-                                                                 float* __restrict__ dparam_partial, int slabs, int hw, int c,
-                                                                 int groups) {
-  extern __shared__ double sm[];      // [c] sum g, [c] sum g*x, then [groups] s1, [groups] s2
+__global__ void __launch_bounds__(1024) groupnorm_bwd_coef_kernel(const float* __restrict__ partial, const float* __restrict__ stats,
+                                                                  const float* __restrict__ gamma, float* __restrict__ coef,
+                                                                  float* __restrict__ dparam_partial, int slabs, int hw, int c,
+                                                                  int groups) {
+  extern __shared__ double sm[];      // [c] sum g, [c] sum g*x, [groups] s1, [groups] s2, then lane partials [L][c][2]
   const int b = blockIdx.x;
   const int cpg = c / groups;
   double* sg = sm; double* sgx = sm + c; double* s1 = sm + 2 * c; double* s2 = sm + 2 * c + groups;
+  double* lp = sm + 2 * c + 2 * groups;
+  const int L = max(1, (int)blockDim.x / c);
+  for (int idx = threadIdx.x; idx < c * L; idx += blockDim.x) {
+    const int l = idx / c, ch = idx - l * c;
+    double ts = 0.0, tq = 0.0;
+#pragma unroll 4
+    for (int sl = l; sl < slabs; sl += L) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partial + (((long long)b * slabs + sl) * c + ch) * 2));
+      ts += (double)v.x;
+      tq += (double)v.y;
+    }
+    lp[((long long)l * c + ch) * 2 + 0] = ts;
+    lp[((long long)l * c + ch) * 2 + 1] = tq;
+  }
+  __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     double ts = 0.0, tq = 0.0;
-    for (int sl = 0; sl < slabs; ++sl) {
-      const float* src = partial + (((long long)b * slabs + sl) * c + ch) * 2;
-      ts += (double)src[0];
-      tq += (double)src[1];
-    }
+    for (int l = 0; l < L; ++l) { ts += lp[((long long)l * c + ch) * 2]; tq += lp[((long long)l * c + ch) * 2 + 1]; }
     sg[ch] = ts; sgx[ch] = tq;
   }
   __syncthreads();
@@ -707,6 +800,20 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackItem*
     mean = s_mean; inv = s_inv;
   }
   T* fwd = static_cast<T*>(it.fwd);
+  if (it.taps == 1 && (it.c & 3) == 0 && (it.c_pad & 3) == 0) {
+    // linear / 1x1 layers (most of the parameters): four values per thread, 16-byte loads
+    T* dst = fwd + (long long)n * it.c_pad;
+    const float* src = it.w + (long long)n * it.c;
+    for (int c = threadIdx.x * 4; c < it.c_pad; c += blockDim.x * 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < it.n && c < it.c) {
+        v = *reinterpret_cast<const float4*>(src + c);
+        v.x = (v.x - mean) * inv; v.y = (v.y - mean) * inv; v.z = (v.z - mean) * inv; v.w = (v.w - mean) * inv;
+      }
+      st4(dst + c, v);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < it.c_pad * it.taps; i += blockDim.x) {
     const int t = i / it.c_pad, c = i - t * it.c_pad;
     float v = 0.f;
@@ -714,24 +821,43 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackItem*
     stf(fwd + (long long)n * it.taps * it.c_pad + i, v);
   }
 }
+// bwd[c][(taps-1-t) * n_pad + n] = fwd[n][t * c_pad + c]: 64 x 64 tiles through shared memory, element pairs both ways
+constexpr int kPackTile = 64;
 template <typename T>
 __global__ void __launch_bounds__(256) pack_transpose_multi_kernel(const PackItem* __restrict__ items, int n_items) {
   const PackItem it = items[find_item(items, n_items, (int)blockIdx.x, &PackItem::first_tile)];
-  __shared__ float tile[32][33];
+  __shared__ float tile[kPackTile][kPackTile + 1];
   int tl = blockIdx.x - it.first_tile;
-  const int tn = (it.n_pad + 31) / 32, tc = (it.c_pad + 31) / 32;
-  const int n0 = (tl % tn) * 32; tl /= tn;
-  const int c0 = (tl % tc) * 32;
+  const int tn = (it.n_pad + kPackTile - 1) / kPackTile, tc = (it.c_pad + kPackTile - 1) / kPackTile;
+  const int n0 = (tl % tn) * kPackTile; tl /= tn;
+  const int c0 = (tl % tc) * kPackTile;
   const int t = tl / tc;
   const T* fwd = static_cast<const T*>(it.fwd);
   T* bwd = static_cast<T*>(it.bwd);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8)
-    tile[r][tx] = (n0 + r < it.n_pad && c0 + tx < it.c_pad) ? ldf(fwd + ((long long)(n0 + r) * it.taps + t) * it.c_pad + c0 + tx) : 0.f;
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8)
-    if (c0 + r < it.c_pad && n0 + tx < it.n_pad)
-      stf(bwd + ((long long)(c0 + r) * it.taps + (it.taps - 1 - t)) * it.n_pad + n0 + tx, tile[tx][r]);
+  const bool pairs = ((it.n_pad | it.c_pad) & 1) == 0;
+  if (pairs) {
+    for (int r = ty; r < kPackTile; r += 8) {
+      float2 v = make_float2(0.f, 0.f);
+      if (n0 + r < it.n_pad && c0 + 2 * tx < it.c_pad) v = ld2(fwd + ((long long)(n0 + r) * it.taps + t) * it.c_pad + c0 + 2 * tx);
+      tile[r][2 * tx] = v.x;
+      tile[r][2 * tx + 1] = v.y;
+    }
+    __syncthreads();
+    for (int r = ty; r < kPackTile; r += 8)
+      if (c0 + r < it.c_pad && n0 + 2 * tx < it.n_pad)
+        st2(bwd + ((long long)(c0 + r) * it.taps + (it.taps - 1 - t)) * it.n_pad + n0 + 2 * tx,
+            make_float2(tile[2 * tx][r], tile[2 * tx + 1][r]));
+  } else {
+    for (int r = ty; r < kPackTile; r += 8)
+      for (int q = tx; q < kPackTile; q += 32)
+        tile[r][q] = (n0 + r < it.n_pad && c0 + q < it.c_pad) ? ldf(fwd + ((long long)(n0 + r) * it.taps + t) * it.c_pad + c0 + q) : 0.f;
+    __syncthreads();
+    for (int r = ty; r < kPackTile; r += 8)
+      for (int q = tx; q < kPackTile; q += 32)
+        if (c0 + r < it.c_pad && n0 + q < it.n_pad)
+          stf(bwd + ((long long)(c0 + r) * it.taps + (it.taps - 1 - t)) * it.n_pad + n0 + q, tile[q][r]);
+  }
 }
 __global__ void __launch_bounds__(256) unpack_wgrads_multi_kernel(const UnpackItem* __restrict__ items, int n_items, float eps) {
   extern __shared__ float row[];
@@ -793,19 +919,6 @@ __global__ void __launch_bounds__(256) clamp01_bwd_kernel(const float* __restric
 }
 
 // ---- small ordered reductions of per-block / per-image partials into parameter gradients
-__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       int blocks, int cols, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  double tg = 0.0, tb = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    tg += (double)partial[((long long)b * 2 + 0) * cols + c];
-    tb += (double)partial[((long long)b * 2 + 1) * cols + c];
-  }
-  if (accumulate) { tg += (double)dgamma[c]; tb += (double)dbeta[c]; }
-  dgamma[c] = (float)tg;
-  dbeta[c] = (float)tb;
-}
 __global__ void gn_param_reduce_kernel(const float* __restrict__ dpar, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        int batch, int c, int accumulate) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -819,11 +932,14 @@ __global__ void gn_param_reduce_kernel(const float* __restrict__ dpar, float* __
   dgamma[ch] = (float)tg;
   dbeta[ch] = (float)tb;
 }
-__global__ void head_param_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
-                                         int blocks, int head_c, int accumulate) {
-  for (int e = threadIdx.x; e < head_c * 33; e += blockDim.x) {
-    double t = 0.0;
-    for (int b = 0; b < blocks; ++b) t += (double)partial[(long long)b * head_c * 33 + e];
+// grid ceil(head_c * 33 / 32)
+__global__ void __launch_bounds__(256) head_param_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                                float* __restrict__ db, int blocks, int head_c, int accumulate) {
+  const int e = blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool active = e < head_c * 33;
+  const float* src = partial + e;
+  double t = ordered_sum8(blocks, active, [&](int b) { return __ldg(src + (long long)b * head_c * 33); });
+  if (threadIdx.x < 32 && active) {
     const int k = e / 33, j = e % 33;
     float* dst = j < 32 ? dw + k * 32 + j : db + k;
     if (accumulate) t += (double)*dst;
@@ -879,26 +995,25 @@ extern "C" int odb_gelu_bwd(const void* dy, const void* u, void* du, int64_t n, 
   return check_launch("gelu_bwd");
 }
 
-extern "C" int64_t odb_colsum_workspace_bytes(int32_t batches, int32_t n) {
-  return (int64_t)batches * kColsumSlabs * n * 4;
+extern "C" int64_t odb_colsum_workspace_bytes(int32_t batches, int64_t rows_per_batch, int32_t n) {
+  if (batches < 1 || rows_per_batch < 1 || n < 1) return -1;
+  return (int64_t)batches * colsum_slabs(batches, rows_per_batch, n) * n * 4;
 }
 
 extern "C" int odb_colsum(const void* x, float* out, void* workspace, int32_t batches, int64_t rows_per_batch, int32_t n,
                           int64_t row_stride, int64_t batch_stride, int32_t accumulate, int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!x || !out || !workspace || batches < 1 || rows_per_batch < 1 || n < 8 || n % 8 || row_stride % 8 || batch_stride % 8 ||
-      !aligned16(x))
+  if (!x || !out || !workspace || batches < 1 || batches > 65535 || rows_per_batch < 1 || n < 8 || n % 8 || row_stride % 8 ||
+      batch_stride % 8 || !aligned16(x))
     return fail(ODB_ERR_INVALID, "colsum: bad argument");
-  long long slabs = (rows_per_batch + 63) / 64;
-  if (slabs > kColsumSlabs) slabs = kColsumSlabs;
-  if (slabs < 1) slabs = 1;
+  const int slabs = colsum_slabs(batches, rows_per_batch, n);
   dim3 grid((n + 63) / 64, (unsigned)slabs, batches);
   float* partial = static_cast<float*>(workspace);
   ODB_DT(dtype, T, "colsum",
          colsum_partial_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), partial, rows_per_batch, n, row_stride,
-                                                            batch_stride, (int)slabs));
+                                                            batch_stride, slabs));
   count_launch();
-  reduce_partials_kernel<<<dim3((n + 255) / 256, batches), 256, 0, stream>>>(partial, out, (int)slabs, n, accumulate);
+  reduce_partials_kernel<<<dim3((n + 31) / 32, batches), 256, 0, stream>>>(partial, out, slabs, n, accumulate);
   count_launch();
   return check_launch("colsum");
 }
@@ -906,29 +1021,32 @@ extern "C" int odb_colsum(const void* x, float* out, void* workspace, int32_t ba
 extern "C" int odb_reduce_partials(const float* partial, float* out, int32_t batches, int32_t parts, int64_t n,
                                    int32_t accumulate, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!partial || !out || batches < 1 || parts < 1 || n < 1) return fail(ODB_ERR_INVALID, "reduce_partials: bad argument");
-  long long gx = (n + 255) / 256;
-  if (gx > 65535 * 16) gx = 65535 * 16;
-  reduce_partials_kernel<<<dim3((unsigned)gx, batches), 256, 0, stream>>>(partial, out, parts, n, accumulate);
+  if (!partial || !out || batches < 1 || batches > 65535 || parts < 1 || n < 1 || (n + 31) / 32 > 0x7fffffffLL)
+    return fail(ODB_ERR_INVALID, "reduce_partials: bad argument");
+  reduce_partials_kernel<<<dim3((unsigned)((n + 31) / 32), batches), 256, 0, stream>>>(partial, out, parts, n, accumulate);
   count_launch();
   return check_launch("reduce_partials");
 }
 
-constexpr int kLnBwdBlocks = 296;   // 2 per SM
-extern "C" int64_t odb_layernorm_bwd_workspace_bytes(int32_t cols) { return (int64_t)kLnBwdBlocks * 2 * cols * 4; }
+constexpr int kLnBwdMaxBlocks = 256;   // one block per SM (register-resident accumulators: 1 block of 8 warps per SM)
+extern "C" int64_t odb_layernorm_bwd_workspace_bytes(int32_t cols) { return (int64_t)kLnBwdMaxBlocks * 3 * cols * 4; }
 
 extern "C" int odb_layernorm_bwd(const void* dy, const float* x, const float* gamma, const float* ds_in, float* ds_out,
-                                 void* ds_copy, float* dgamma, float* dbeta, void* workspace, int64_t rows, int32_t cols,
-                                 float eps, int32_t accumulate, int32_t dtype, void* stream_) {
+                                 void* ds_copy, float* dgamma, float* dbeta, float* dcolsum, void* workspace, int64_t rows,
+                                 int32_t cols, float eps, int32_t accumulate, int32_t dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!dy || !x || !gamma || !ds_out || !dgamma || !dbeta || !workspace || rows < 1)
     return fail(ODB_ERR_INVALID, "layernorm_bwd: bad argument");
   float* partial = static_cast<float*>(workspace);
-  const int blocks = kLnBwdBlocks;
+  int blocks = num_sms();
+  if (blocks > kLnBwdMaxBlocks) blocks = kLnBwdMaxBlocks;
+  if ((long long)blocks * 8 > rows) blocks = (int)((rows + 7) / 8);
+  const int want_colsum = dcolsum != nullptr;
 #define ODB_LN_BWD(VPL)                                                                                              \
   ODB_DT(dtype, T, "layernorm_bwd",                                                                                  \
          layernorm_bwd_kernel<VPL, T><<<blocks, 256, 0, stream>>>(static_cast<const T*>(dy), x, gamma, ds_in, ds_out, \
-                                                                  static_cast<T*>(ds_copy), partial, (long long)rows, eps))
+                                                                  static_cast<T*>(ds_copy), partial, (long long)rows, eps, \
+                                                                  want_colsum))
   switch (cols) {
     case 256: ODB_LN_BWD(1); break;
     case 512: ODB_LN_BWD(2); break;
@@ -938,7 +1056,8 @@ extern "C" int odb_layernorm_bwd(const void* dy, const float* x, const float* ga
   }
 #undef ODB_LN_BWD
   count_launch();
-  ln_param_reduce_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(partial, dgamma, dbeta, blocks, cols, accumulate);
+  ln_param_reduce_kernel<<<((want_colsum ? 3 : 2) * cols + 31) / 32, 256, 0, stream>>>(partial, dgamma, dbeta, dcolsum, blocks,
+                                                                                       cols, accumulate);
   count_launch();
   return check_launch("layernorm_bwd");
 }
@@ -975,8 +1094,9 @@ extern "C" int odb_groupnorm_bwd(const void* dy, const void* mask, const void* x
          groupnorm_bwd_sums_kernel<T><<<dim3(slabs, b), 256, 2 * planes * c * sizeof(float), stream>>>(
              static_cast<const T*>(dy), static_cast<const T*>(mask), static_cast<const T*>(x), partial, hw, c, ppb));
   count_launch();
-  groupnorm_bwd_coef_kernel<<<b, 256, (2 * c + 2 * groups) * sizeof(double), stream>>>(partial, stats, gamma, coef, dpar,
-                                                                                        slabs, hw, c, groups);
+  const int coef_lanes = 1024 / c > 1 ? 1024 / c : 1;
+  groupnorm_bwd_coef_kernel<<<b, 1024, (size_t)(2 * c + 2 * groups + 2 * coef_lanes * c) * sizeof(double), stream>>>(
+      partial, stats, gamma, coef, dpar, slabs, hw, c, groups);
   count_launch();
   long long gx = ((long long)hw * (c / 8) + 255) / 256;
   const long long cap = ((long long)num_sms() * 8 + b - 1) / b;
@@ -1054,7 +1174,7 @@ extern "C" int odb_head_tail_bwd(const float* dout, const float* out, const void
          head_tail_bwd_kernel<T><<<kHeadBwdBlocks, 256, 0, stream>>>(dout, out, static_cast<const T*>(a), channel_stride, w,
                                                                      static_cast<T*>(da), partial, ppi, b, head_c, relu));
   count_launch();
-  head_param_reduce_kernel<<<1, 128, 0, stream>>>(partial, dw, dbias, kHeadBwdBlocks, head_c, accumulate);
+  head_param_reduce_kernel<<<(head_c * 33 + 31) / 32, 256, 0, stream>>>(partial, dw, dbias, kHeadBwdBlocks, head_c, accumulate);
   count_launch();
   return check_launch("head_tail_bwd");
 }

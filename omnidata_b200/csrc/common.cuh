@@ -364,4 +364,29 @@ ODB_DEVINL float warp_max(float v) {
   return v;
 }
 
+// ---- ordered reduction of per-block partials (256-thread blocks)
+// Block = 32 adjacent columns x 8 part lanes: lane l sums parts l, l+8, ... in fp64 (independent loads, four in flight),
+// then the lane-0 threads add the 8 lane sums in lane order.  The order is fixed for a given `parts`, so results are
+// bit-reproducible, and the dependent chain is parts / 8 long instead of parts.  The value is returned to the threads
+// of part lane 0 (threadIdx.x < 32).
+template <typename F>
+ODB_DEVINL double ordered_sum8(int parts, bool active, F&& part) {
+  __shared__ double sh_os8[8][33];
+  const int col = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  double t = 0.0;
+  if (active) {
+#pragma unroll 4
+    for (int p = pl; p < parts; p += 8) t += (double)part(p);
+  }
+  sh_os8[pl][col] = t;
+  __syncthreads();
+  double s = 0.0;
+  if (pl == 0) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) s += sh_os8[l][col];
+  }
+  return s;
+}
+
+
 }  // namespace odb

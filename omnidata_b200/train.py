@@ -219,7 +219,7 @@ class TrainEngine:
             fn(*args, out)
             ops.groupnorm_stats(out, st, scratch=self.gn_scratch)
         else:
-            fn(*args, out, gn_stats=(self.gn_part, st))
+            fn(*args, out, gn_stats=(self.gn_part, st, self.gn_counters))
 
     # ------------------------------------------------------------------ forward (activations kept)
     @torch.no_grad()
@@ -238,6 +238,9 @@ class TrainEngine:
         if "gn_scratch" not in self.bufs:
             self.bufs["gn_scratch"] = torch.zeros(4 << 20, dtype=torch.uint8, device=self.device)
         self.gn_scratch = self.bufs["gn_scratch"]
+        if "gn_counters" not in self.bufs or self.bufs["gn_counters"].numel() < B:
+            self.bufs["gn_counters"] = torch.zeros(max(B, 256), dtype=torch.int32, device=self.device)
+        self.gn_counters = self.bufs["gn_counters"]
         self.gn_part = buf("gn_partial", (B * ((H // 4) * (W // 4) // 32 + 64) * 4 * 32 * 2,), f32)
         n_gn = 1 + sum(3 * d + 1 for _, d in _STAGES)
         stats = buf("gn_stats", (n_gn, B, 32, 2), f32)
@@ -336,9 +339,13 @@ class TrainEngine:
             h2_ = buf(f"vit_h2_{i}", (B, ntok, D))
             ops.layernorm(xm[i], P[p + "norm2.weight"], P[p + "norm2.bias"], h2_)
             u = buf(f"vit_u_{i}", (B, ntok, 4 * D))
-            ops.linear(h2_.view(rows, -1), Wt[f"blk{i}.fc1"][0], u.view(rows, -1), bias=P[p + "mlp.fc1.bias"])
             mlp = buf(f"vit_mlp_{i}", (B, ntok, 4 * D))
-            bwd.gelu_fwd(u, mlp)
+            if self.fp32:
+                ops.linear(h2_.view(rows, -1), Wt[f"blk{i}.fc1"][0], u.view(rows, -1), bias=P[p + "mlp.fc1.bias"])
+                bwd.gelu_fwd(u, mlp)
+            else:       # one pass: the pre-activation (kept for the backward) and gelu of the same fp32 value
+                ops.linear(h2_.view(rows, -1), Wt[f"blk{i}.fc1"][0], u.view(rows, -1), bias=P[p + "mlp.fc1.bias"],
+                           out2=mlp.view(rows, -1), out2_act=ops.ACT_GELU)
             ops.linear(mlp.view(rows, -1), Wt[f"blk{i}.fc2"][0], xs[i + 1].view(rows, -1), bias=P[p + "mlp.fc2.bias"],
                        residual=xm[i].view(rows, -1))
             vit.append(dict(h1=h1, qkv=qkv, att=att, lse=lse, h2=h2_, u=u, mlp=mlp))
@@ -542,6 +549,7 @@ class TrainEngine:
         ds_b = buf("g.vit_ds_b", (B, ntok, D), f32)
         ds16 = buf("g.vit_ds16", (B, ntok, D)) if not self.fp32 else None
         bwd.add_cast(None, dtk4, ds, ds16)
+        hooked = (8, 11)                                             # blocks whose output gradient gets a readout gradient
         for i in range(11, -1, -1):
             p = f"{pm}blocks.{i}."
             v = vit[i]
@@ -554,25 +562,30 @@ class TrainEngine:
             dmlp = buf("g.vit_mlp", v["mlp"].shape)
             ops.linear(g16.view(rows, -1), Wt[f"blk{i}.fc2"][1], dmlp.view(rows, -1), bias=self._zb(Wt[f"blk{i}.fc2"][1]))
             self._wgrad(f"blk{i}.fc2", [v["mlp"].view(rows, -1)], bwd.TAPS_1, g16.view(rows, -1))
-            bwd.colsum(ds.view(rows, -1), G[p + "mlp.fc2.bias"].view(1, -1))
+            if i in hooked:                                          # else: written by block i+1's norm1 backward
+                bwd.colsum(ds.view(rows, -1), G[p + "mlp.fc2.bias"].view(1, -1))
             bwd.gelu_bwd(dmlp, v["u"], dmlp)
             dh = buf("g.vit_h", v["h2"].shape)
             ops.linear(dmlp.view(rows, -1), Wt[f"blk{i}.fc1"][1], dh.view(rows, -1), bias=self._zb(Wt[f"blk{i}.fc1"][1]))
             self._wgrad(f"blk{i}.fc1", [v["h2"].view(rows, -1)], bwd.TAPS_1, dmlp.view(rows, -1))
             self._bias_grad(p + "mlp.fc1.bias", dmlp.view(rows, -1))
-            bwd.layernorm_bwd(dh, xm[i], P[p + "norm2.weight"], ds, ds_b, ds16, G[p + "norm2.weight"], G[p + "norm2.bias"])
+            # ds_b = gradient at attn.proj's output: its column sums are proj's bias gradient (same pass)
+            bwd.layernorm_bwd(dh, xm[i], P[p + "norm2.weight"], ds, ds_b, ds16, G[p + "norm2.weight"], G[p + "norm2.bias"],
+                              dcolsum=G[p + "attn.proj.bias"])
             g16 = ds_b if self.fp32 else ds16
             # attention: xm = x_i + proj(attn(qkv(LN1(x_i))))
             datt = buf("g.vit_att", v["att"].shape)
             ops.linear(g16.view(rows, -1), Wt[f"blk{i}.proj"][1], datt.view(rows, -1), bias=self._zb(Wt[f"blk{i}.proj"][1]))
             self._wgrad(f"blk{i}.proj", [v["att"].view(rows, -1)], bwd.TAPS_1, g16.view(rows, -1))
-            bwd.colsum(ds_b.view(rows, -1), G[p + "attn.proj.bias"].view(1, -1))
             dqkv = buf("g.vit_qkv", v["qkv"].shape)
             bwd.attention_bwd(v["qkv"], v["att"], datt, v["lse"], dqkv, heads=12, scale=0.125)
             ops.linear(dqkv.view(rows, -1), Wt[f"blk{i}.qkv"][1], dh.view(rows, -1), bias=self._zb(Wt[f"blk{i}.qkv"][1]))
             self._wgrad(f"blk{i}.qkv", [v["h1"].view(rows, -1)], bwd.TAPS_1, dqkv.view(rows, -1))
             self._bias_grad(p + "attn.qkv.bias", dqkv.view(rows, -1))
-            bwd.layernorm_bwd(dh, xs[i], P[p + "norm1.weight"], ds_b, ds, ds16, G[p + "norm1.weight"], G[p + "norm1.bias"])
+            # ds = gradient at block i-1's output = at its mlp.fc2 output, unless a hook adds to it first
+            fc2_bias = G[f"{pm}blocks.{i - 1}.mlp.fc2.bias"] if i >= 1 and (i - 1) not in hooked else None
+            bwd.layernorm_bwd(dh, xs[i], P[p + "norm1.weight"], ds_b, ds, ds16, G[p + "norm1.weight"], G[p + "norm1.bias"],
+                              dcolsum=fc2_bias)
         # ---- tokens: cls / pos_embed, patch projection
         gpos = G[pm + "pos_embed"]
         bwd.colsum(ds.view(B, ntok * D), gpos.view(1, -1))

@@ -87,8 +87,10 @@ def main(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_issue = time.perf_counter()
     for i in range(args.steps):
         res = step.step(*devin[i % n_rot], full_mix=True)
+    host_issue_ms = (time.perf_counter() - t_issue) * 1e3 / args.steps   # CPU time to enqueue one step (no sync inside)
     e1.record()
     torch.cuda.synchronize()
     parallel.barrier()
@@ -204,6 +206,7 @@ def main(args):
             "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_bytes_per_step": B * IMG * IMG * 4 * 5, "d2h_bytes_per_step": 20},
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+            "host_issue_ms_per_step": round(host_issue_ms, 3),
             "clocks": clocks,
             "model_tflops": round(TRAIN_GFLOP_PER_IMAGE * 1e9 * value / 1e12, 2),
             "model_frac_of_sustained_peak": round(TRAIN_GFLOP_PER_IMAGE * 1e9 * value / world / 1e12 / peaks["tflops_sustained"], 4),

@@ -21,7 +21,7 @@ def test_c_abi_exports_every_declared_symbol(lib_built):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     from omnidata_b200 import _capi
     assert sorted(_capi.exported_symbols()) == declared
-    assert _capi.lib().odb_abi_version() == _capi.ABI_VERSION == 3
+    assert _capi.lib().odb_abi_version() == _capi.ABI_VERSION == 4
     assert _capi.launch_count() == 0
 
 

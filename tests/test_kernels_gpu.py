@@ -372,6 +372,33 @@ def test_conv_fused_groupnorm_stats(b, h, w_, c, n, pair):
     o.conv3x3(x, o.pack_conv_weight(w), out_g, gn_stats=(partial, stats_g), cta_pair=pair, block_n=bn, epilogue=-1)
     torch.cuda.synchronize()
     assert torch.equal(out, out_g) and torch.equal(stats, stats_g)
+    # producer-side finalize (default: the CTA that completes an image's last tile reduces the partial sums) against
+    # the separate reduction launch; caller-owned ticket buffer, left zero by the kernel
+    stats_s, stats_f = torch.full_like(stats, float("nan")), torch.full_like(stats, float("nan"))
+    counters = torch.zeros(b, dtype=torch.int32, device=dev())
+    o.conv3x3(x, o.pack_conv_weight(w), out_g, gn_stats=(partial, stats_s), cta_pair=pair, block_n=bn, gn_fold=False)
+    o.conv3x3(x, o.pack_conv_weight(w), out_g, gn_stats=(partial, stats_f, counters), cta_pair=pair, block_n=bn)
+    torch.cuda.synchronize()
+    assert torch.equal(stats_s, stats) and torch.equal(stats_f, stats) and int(counters.abs().sum()) == 0
+
+
+def test_conv_out2_gelu_copy():
+    """out keeps the pre-activation, out2 = exact-erf GELU of the same fp32 value (train-mode mlp.fc1)."""
+    o = ops()
+    rows, c, n = 2 * 577, 256, 1024
+    x = rnd(rows, c).to(torch.bfloat16)
+    w = rnd(n, c, scale=c ** -0.5).to(torch.bfloat16)
+    bias = rnd(n)
+    out = torch.empty((rows, n), device=dev(), dtype=torch.bfloat16)
+    out2 = torch.empty_like(out)
+    o.linear(x, w, out, bias=bias, out2=out2, out2_act=o.ACT_GELU)
+    act = torch.empty_like(out)
+    o.linear(x, w, act, bias=bias, act=o.ACT_GELU)            # the inference epilogue
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + bias
+    check(out, ref, "pre-activation")
+    check(out2, F.gelu(ref), "gelu copy")
+    assert torch.equal(out2, act)
 
 
 def test_stem_path():

@@ -57,6 +57,22 @@ def test_layernorm_bwd_kernel():
     bwd.layernorm_bwd(dy, x, g, ds_in, ds_out, None, dgam, dbet)
     torch.cuda.synchronize()
     assert rel(ds_out, gx + ds_in.double()) < 1e-5 and rel(dgam, gg) < 1e-5 and rel(dbet, gb) < 1e-5
+    # with the fused column sums of ds_out (bias gradient of the linear layer in front): same results + the sums
+    ds2, dgam2, dbet2, dcol = torch.empty_like(x), torch.empty(c, device=dev()), torch.empty(c, device=dev()), torch.empty(c, device=dev())
+    bwd.layernorm_bwd(dy, x, g, ds_in, ds2, None, dgam2, dbet2, dcolsum=dcol)
+    torch.cuda.synchronize()
+    assert torch.equal(ds2, ds_out) and torch.equal(dgam2, dgam) and torch.equal(dbet2, dbet)
+    assert rel(dcol, ds_out.double().sum(0)) < 1e-5
+    # accumulate: every parameter output adds to what is there
+    bwd.layernorm_bwd(dy, x, g, ds_in, ds2, None, dgam2, dbet2, accumulate=True, dcolsum=dcol)
+    torch.cuda.synchronize()
+    assert rel(dgam2, 2 * gg) < 1e-5 and rel(dbet2, 2 * gb) < 1e-5 and rel(dcol, 2 * ds_out.double().sum(0)) < 1e-5
+    # a row count that does not fill the grid (fewer rows than warps)
+    bwd.layernorm_bwd(dy[:5], x[:5], g, None, ds2[:5], None, dgam2, dbet2, dcolsum=dcol)
+    torch.cuda.synchronize()
+    y5 = F.layer_norm(xd[:5], (c,), gd, bd, 1e-6)
+    gx5, gg5 = torch.autograd.grad(y5, (xd, gd), dy[:5].double())
+    assert rel(ds2[:5], gx5[:5]) < 1e-5 and rel(dgam2, gg5) < 1e-5 and rel(dcol, gx5[:5].sum(0)) < 1e-5
     # bf16 incoming gradient + bf16 copy of the result
     dyb = dy.to(torch.bfloat16)
     cp = torch.empty(rows, c, device=dev(), dtype=torch.bfloat16)
@@ -114,6 +130,56 @@ def test_elementwise_bwd_kernels():
     bwd.colsum(x.view(-1, 768), o1); bwd.colsum(x[:, 1:, :], o2, batches=3)
     torch.cuda.synchronize()
     assert rel(o1[0], x.double().sum((0, 1))) < 1e-6 and rel(o2, x[:, 1:].double().sum(1)) < 1e-6
+    # many rows x few columns (a decoder convolution's output gradient, bf16: many slabs, ragged unroll tail), accumulate,
+    # and a handful of rows x many columns (pos_embed: one slab)
+    xb = rnd(40013, 64, seed=3).to(torch.bfloat16)
+    o3 = torch.full((1, 64), 2.0, device=dev())
+    bwd.colsum(xb, o3, accumulate=True)
+    xw = rnd(3, 577 * 768, seed=4)
+    o4 = torch.empty(1, 577 * 768, device=dev())
+    bwd.colsum(xw, o4)
+    torch.cuda.synchronize()
+    assert rel(o3[0], xb.double().sum(0) + 2.0) < 1e-6 and rel(o4[0], xw.double().sum(0)) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pack_table_multi(dtype):
+    """One-launch packing of several layers == the layer-by-layer definition (forward operand, rotated / transposed
+    dgrad operand, weight standardisation, zero padding); covers the vector paths and the odd-extent fallback."""
+    from omnidata_b200 import bwd
+    specs = [  # n, c, taps, n_pad, c_pad, standardize
+        (100, 768, 1, 128, 768, False),      # linear layer: float4 path, padded rows
+        (64, 64, 9, 64, 64, True),           # 3x3 with weight standardisation
+        (256, 64, 1, 256, 64, True),         # 1x1 with weight standardisation (vector path + statistics)
+        (24, 40, 9, 64, 64, False),          # padded channels both ways
+        (33, 35, 1, 33, 35, False),          # odd extents: scalar paths
+    ]
+    layers, refs = [], []
+    for i, (n, c, taps, n_pad, c_pad, std) in enumerate(specs):
+        w = rnd(n, c, taps, scale=0.05, seed=10 + i) + 0.01
+        fwd = torch.full((n_pad, taps * c_pad), 7.0, device=dev()).to(dtype)
+        bk = torch.full((c_pad, taps * n_pad), 7.0, device=dev()).to(dtype)
+        layers.append((w, fwd, bk, n, c, taps, n_pad, c_pad, std))
+        wh = w.double()
+        if std:
+            m = wh.mean(dim=(1, 2), keepdim=True)
+            sd = (wh.var(dim=(1, 2), unbiased=False, keepdim=True)).sqrt()
+            wh = (wh - m) / (sd + 1e-8)
+        rf = torch.zeros(n_pad, taps, c_pad, dtype=torch.float64, device=dev())
+        rf[:n, :, :c] = wh.permute(0, 2, 1)
+        rb = torch.zeros(c_pad, taps, n_pad, dtype=torch.float64, device=dev())
+        rb[:c, :, :n] = wh.permute(1, 2, 0).flip(1)
+        refs.append((rf.reshape(n_pad, -1), rb.reshape(c_pad, -1)))
+    bwd.PackTable(layers, dtype).run()
+    torch.cuda.synchronize()
+    tol = 1e-6 if dtype == torch.float32 else 4e-3
+    for (w, fwd, bk, *_), (rf, rb) in zip(layers, refs):
+        assert rel(fwd, rf) < tol and rel(bk, rb) < tol
+        assert torch.equal(fwd == 0, rf == 0) and torch.equal(bk == 0, rb == 0)          # padding is exactly zero
+        # the transposed operand holds exactly the forward operand's rounded values
+        n_pad, c_pad = fwd.shape[0], bk.shape[0]
+        taps = fwd.shape[1] // c_pad
+        assert torch.equal(bk.view(c_pad, taps, n_pad), fwd.view(n_pad, taps, c_pad).permute(2, 1, 0).flip(1))
 
 
 def test_stem_and_head_bwd_kernels():
