@@ -123,14 +123,6 @@ typedef struct odb_conv_gemm_desc {
    *                 partial sums combined in fp64; bias / act / residual / out2 as above, no gn_partial / head. */
   int32_t in_dtype;
   int32_t out_dtype;
-  /* With gn_partial: when gn_stats != NULL the call also delivers the finished statistics gn_stats[b][gn_groups][2] =
-   * (mean, 1/sqrt(var + gn_eps)), bit-identical to odb_groupnorm_finalize on gn_partial.  On the specialised epilogue the
-   * kernel does it itself: the CTA that completes the last tile of an image (per-image ticket in gn_counters: uint32 [b],
-   * zero before the first use, left zero by the kernel) reduces that image's partial sums — no second launch; on the
-   * generic epilogue odb_conv_gemm launches the reduction after the kernel. */
-  float* gn_stats;
-  uint32_t* gn_counters;
-  float gn_eps;
   /* Activation of the out2 copy: ODB_ACT_NONE / ODB_ACT_RELU = relu (ResidualConvUnit's `relu(out)` operand),
    * ODB_ACT_GELU = exact-erf GELU (train mode: out keeps the pre-activation of mlp.fc1 for the backward, out2 feeds fc2). */
   int32_t out2_act;
@@ -389,11 +381,16 @@ int odb_normal_loss_fwd(const float* prediction, const float* target, const uint
  * bytes, 256-byte aligned, zero-filled ONCE by the caller.  Deterministic (fixed-order fp64 partial sums).
  *
  * odb_adam_step: torch.optim.Adam update (betas, eps as given; no weight decay, no amsgrad), step = 1, 2, …;
- * clip2 = the out2 of odb_clip_grad_norm or NULL (no clipping). */
+ * clip2 = the out2 of odb_clip_grad_norm or NULL (no clipping).  step_scalars (device fp32 [2], may be NULL): when given,
+ * the two step-dependent scalars (lr / (1 - beta1^step), sqrt(1 - beta2^step)) are read from device memory instead of
+ * being computed from `step` — what a CUDA-graph replay of the train step needs; odb_adam_step_scalars (host function,
+ * host pointer) computes them exactly as odb_adam_step does. */
 int64_t odb_grad_norm_workspace_bytes(void);
 int odb_clip_grad_norm(const float* grads, int64_t n, float max_norm, void* workspace, float* out2, void* stream);
 int odb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                  const float* clip2, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
+                  const float* clip2, float lr, float beta1, float beta2, float eps, int64_t step,
+                  const float* step_scalars, void* stream);
+int odb_adam_step_scalars(float lr, float beta1, float beta2, int64_t step, float* out2_host);
 
 /* ---- 3-D refocus augmentation (data/refocus_augmentation.py) ------------------------------
  * odb_refocus_quantiles: compute_quantiles (:82-87): quantile_vals fp32 [b][n_quantiles + 1] = torch.quantile(depth[b],

@@ -59,9 +59,6 @@ class ConvGemmDesc(C.Structure):
         ("epilogue", C.c_int32),
         ("in_dtype", C.c_int32),
         ("out_dtype", C.c_int32),
-        ("gn_stats", C.c_void_p),
-        ("gn_counters", C.c_void_p),
-        ("gn_eps", C.c_float),
         ("out2_act", C.c_int32),
     ]
 
@@ -166,7 +163,8 @@ _SIGNATURES = {
     "odb_grad_norm_workspace_bytes": (C.c_int64, []),
     "odb_clip_grad_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "odb_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
-                                C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
+                                C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]),
+    "odb_adam_step_scalars": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     "odb_refocus_quantiles": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                         C.c_void_p]),
     "odb_refocus_compose": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 4 + [C.c_void_p] * 5),

@@ -479,7 +479,7 @@ int conv_wgrad_tc(const odb_wgrad_desc* d, cudaStream_t stream) {
   rc = bg_launch(p, stream);
   if (rc || direct) return rc;
   const long long total = (long long)n * pl.row_len;
-  if (pl.splits >= 16) {
+  if (pl.splits >= 16 && total <= 131072) {     // small gradient, many splits: the chain length is what costs
     bg_sum_splits_lanes_kernel<<<(unsigned)((total + 31) / 32), 256, 0, stream>>>(static_cast<const float*>(d->workspace), d->out,
                                                                                   pl.splits, total, d->accumulate);
   } else {

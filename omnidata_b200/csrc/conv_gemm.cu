@@ -57,13 +57,6 @@ struct ConvGemmParams {
   float* gn_partial;   // optional GroupNorm partial sums, [b][tiles_y*tiles_x][4 quadrants][groups][2]
   int gn_cpg;          // channels per group (2..32, power of two)
   int gn_groups;
-  // producer-side finalize (EPI_GN): the CTA that completes an image's last tile reduces the image's partials
-  float* gn_stats;             // [b][groups][2] (mean, rstd) or nullptr
-  unsigned int* gn_counters;   // [b] tickets, zero between launches
-  int gn_tiles_per_image;      // tiles_x * tiles_y * tiles_n
-  int gn_rows;                 // partial rows per image = tiles_x * tiles_y * 4
-  float gn_eps;
-  double gn_count;             // elements per (image, group)
   CUtensorMap res_map;        // EPI_BIAS_RES: the residual, boxed like out_map
   unsigned long long* trace;  // diagnostics (odb_debug_conv_trace): kTraceSlots globaltimer stamps per CTA
 };
@@ -147,35 +140,6 @@ ODB_DEVINL void gn_warp_partials(const float* v, int lane, float* dst /* [groups
   gn_row_group_sums<CPG>(v, vals);
   gn_lane_butterfly<V>(vals, lane);
   if ((lane & ((1 << (5 - LOGV)) - 1)) == 0) dst[lane >> (5 - LOGV)] = vals[0];
-}
-
-// Statistics of one image from its partial sums, by the 8 epilogue warps of the CTA that finished the image's last
-// tile: warp w takes groups w, w+8, ...; lane l sums rows l, l+32, ... in fp64, then a fixed shuffle tree — the
-// arithmetic (and therefore every bit of the result) of groupnorm_finalize_kernel (ops.cu).
-ODB_DEVINL void gn_finalize_image(const float* partial, float* stats, int b, int rows, int groups, double count, float eps,
-                                  int w, int lane) {
-  for (int g = w; g < groups; g += kEpiThreads / 32) {
-    const float* base = partial + ((long long)b * rows) * groups * 2 + g * 2;
-    double ts = 0.0, tq = 0.0;
-#pragma unroll 4
-    for (int r = lane; r < rows; r += 32) {
-      const float2 v = __ldcg(reinterpret_cast<const float2*>(base + (long long)r * groups * 2));
-      ts += (double)v.x;
-      tq += (double)v.y;
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      ts += __shfl_down_sync(0xffffffffu, ts, o);
-      tq += __shfl_down_sync(0xffffffffu, tq, o);
-    }
-    if (lane == 0) {
-      const double mean = ts / count;
-      double var = tq / count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      stats[((long long)b * groups + g) * 2 + 0] = (float)mean;
-      stats[((long long)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-  }
 }
 
 // HALO = true (3x3 stride-1 convolutions): instead of nine shifted 128-row boxes per K block, ONE
@@ -665,10 +629,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           // thread passes this barrier and starts writing chunk g+1 (with a residual the TMA load of
           // chunk g+1, issued after that store was read, orders it)
           if (!RES && store_leader) tma_store_wait_read<(NS >= 2 ? NS - 2 : 0)>();
-          if constexpr (EPI == EPI_GN) {
-            // producer-side finalize: this tile's partial sums must be visible device-wide before the ticket below
-            if (c == kChunks - 1 && p.gn_counters != nullptr) __threadfence();
-          }
           named_bar_sync(1, kEpiThreads);
           if (store_leader) {
             tma_store_4d(&p.out_map, buf, n0 + c * 64, x0, y0, tb);
@@ -677,24 +637,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             if constexpr (RES) {
               tma_store_wait_read<NS - D>();     // the store of chunk g+D-NS has read its slot
               issue_res_load();                  // residual of chunk g+D -> that slot
-            }
-          }
-        }
-        if constexpr (EPI == EPI_GN) {
-          // per-image ticket: whoever completes the image's last tile finalises its statistics (all eight epilogue
-          // warps of that CTA); tb is uniform over the CTA, so every epilogue thread takes the same branch
-          if (p.gn_counters != nullptr && tb < p.out_b) {
-            __shared__ int s_gn_last;
-            if (store_leader) {
-              const unsigned int ticket = atomicAdd(p.gn_counters + tb, 1u);
-              const int last = ticket == static_cast<unsigned int>(p.gn_tiles_per_image - 1);
-              if (last) p.gn_counters[tb] = 0u;          // every other tile of the image has drawn its ticket
-              s_gn_last = last;
-            }
-            named_bar_sync(2, kEpiThreads);
-            if (s_gn_last) {
-              __threadfence();
-              gn_finalize_image(p.gn_partial, p.gn_stats, tb, p.gn_rows, p.gn_groups, p.gn_count, p.gn_eps, warp - 2, lane);
             }
           }
         }
@@ -1128,21 +1070,9 @@ extern "C" int odb_conv_gemm_plan(const odb_conv_gemm_desc* d, int32_t* out4) {
   return ODB_OK;
 }
 
-// what is left to do after the launch when the caller asked for finalised GroupNorm statistics (desc.gn_stats)
-struct GnTail { bool pending; int rows; double count; };
-static int conv_gemm_launch(const odb_conv_gemm_desc* d, cudaStream_t stream, GnTail* tail);
-
 extern "C" int odb_conv_gemm(const odb_conv_gemm_desc* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (d != nullptr && d->in_dtype == ODB_DTYPE_F32) return conv_gemm_f32(d, stream);   // fp32 correctness mode
-  GnTail tail = {false, 0, 0.0};
-  int rc = conv_gemm_launch(d, stream, &tail);
-  if (rc == ODB_OK && tail.pending)   // generic epilogue: partial sums by the kernel, their reduction as a second launch
-    rc = odb_groupnorm_finalize(d->gn_partial, d->gn_stats, d->out.b, tail.rows, d->gn_groups, tail.count, d->gn_eps, stream_);
-  return rc;
-}
-
-static int conv_gemm_launch(const odb_conv_gemm_desc* d, cudaStream_t stream, GnTail* tail) {
   HostPlan hp;
   int rc = make_plan(d, &hp);
   if (rc) return rc;
@@ -1250,30 +1180,14 @@ static int conv_gemm_launch(const odb_conv_gemm_desc* d, cudaStream_t stream, Gn
     p.gn_partial = d->gn_partial;
     p.gn_cpg = cpg;
     p.gn_groups = g;
-    if (d->gn_stats != nullptr && d->gn_counters == nullptr)
-      return fail(ODB_ERR_INVALID, "conv_gemm: gn_stats needs gn_counters (uint32 [b], zeroed)");
-  } else if (d->gn_stats != nullptr) {
-    return fail(ODB_ERR_INVALID, "conv_gemm: gn_stats needs gn_partial");
   }
   p.trace = debug_trace();
 
   const long long total = m_tiles * p.tiles_n;
-  const int gn_rows = p.tiles_x * p.tiles_y * 4;
-  const double gn_count = (double)ow * (double)oh * (double)(p.gn_groups > 0 ? N / p.gn_groups : 1);
   // specialised epilogue when the flag combination allows it (see the EPI_* comment)
   if (!hp.halo && !head && block_n >= 64 && p.bias == nullptr && !p.has_out2 && p.gn_partial != nullptr &&
-      p.residual == nullptr && p.act == ODB_ACT_NONE && d->epilogue == 0) {
-    if (d->gn_stats != nullptr) {     // the kernel finalises the statistics itself
-      p.gn_stats = d->gn_stats;
-      p.gn_counters = d->gn_counters;
-      p.gn_tiles_per_image = p.tiles_x * p.tiles_y * p.tiles_n;
-      p.gn_rows = gn_rows;
-      p.gn_eps = d->gn_eps;
-      p.gn_count = gn_count;
-    }
+      p.residual == nullptr && p.act == ODB_ACT_NONE && d->epilogue == 0)
     return launch_fast<EPI_GN>(p, block_n, pair, m_tiles, total, stream);
-  }
-  if (d->gn_stats != nullptr) { tail->pending = true; tail->rows = gn_rows; tail->count = gn_count; }
   if (!hp.halo && !head && block_n >= 64 && p.bias != nullptr && !p.has_out2 && p.gn_partial == nullptr &&
       d->epilogue == 0) {
     if (p.residual == nullptr) {

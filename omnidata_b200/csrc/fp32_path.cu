@@ -265,7 +265,6 @@ int conv_gemm_f32(const odb_conv_gemm_desc* d, cudaStream_t stream) {
   fill_strides(d->out, &p.osx, &p.osy, &p.osb);
   p.ow = d->out.w; p.oh = d->out.h; p.ob = d->out.b;
   if (p.ow < 1 || p.oh < 1 || p.ob < 1) return fail(ODB_ERR_INVALID, "conv_gemm (fp32 mode): empty output extent");
-  if (d->gn_stats != nullptr) return fail(ODB_ERR_UNSUPPORTED, "conv_gemm (fp32 mode): no fused GroupNorm statistics");
   if (d->out2.ptr) {
     if (d->out2_act == ODB_ACT_GELU) return fail(ODB_ERR_UNSUPPORTED, "conv_gemm (fp32 mode): the out2 copy is relu only");
     if (!view_ok(d->out2)) return fail(ODB_ERR_INVALID, "conv_gemm (fp32 mode): bad out2 view");

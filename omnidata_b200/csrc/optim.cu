@@ -73,8 +73,13 @@ __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(float* __restric
                                                                 float* __restrict__ m, float* __restrict__ v,
                                                                 long long n, const float* __restrict__ clip2,
                                                                 float w1, float beta2, float w2, float step_size,
-                                                                float bc2_sqrt, float eps) {
+                                                                float bc2_sqrt, float eps,
+                                                                const float* __restrict__ step_scalars) {
   const float clip = clip2 != nullptr ? clip2[1] : 1.0f;
+  if (step_scalars != nullptr) {       // captured in a CUDA graph: the step-dependent scalars come from device memory
+    step_size = step_scalars[0];
+    bc2_sqrt = step_scalars[1];
+  }
   const long long stride = 4LL * gridDim.x * blockDim.x;
   for (long long i = 4LL * (blockIdx.x * (long long)blockDim.x + threadIdx.x); i < n; i += stride) {
     if (i + 3 < n) {
@@ -133,26 +138,36 @@ extern "C" int odb_clip_grad_norm(const float* grads, int64_t n, float max_norm,
   return check_launch("clip_grad_norm");
 }
 
+extern "C" int odb_adam_step_scalars(float lr, float beta1, float beta2, int64_t step, float* out2) {
+  if (out2 == nullptr || step < 1) return fail(ODB_ERR_INVALID, "adam_step_scalars: bad argument");
+  // scalar preparation as torch does it on the host (python floats = doubles), then one rounding to fp32
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  out2[0] = (float)((double)lr / bc1);
+  out2[1] = (float)sqrt(bc2);
+  return ODB_OK;
+}
+
 extern "C" int odb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                              const float* clip2, float lr, float beta1, float beta2, float eps, int64_t step,
-                             void* stream_) {
+                             const float* step_scalars, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (step_scalars != nullptr && step < 1) step = 1;     // unused: the scalars are read from device memory
   if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1 ||
       ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
         reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u))
     return fail(ODB_ERR_INVALID, "adam_step: bad argument (16-byte aligned flat fp32 buffers, step >= 1)");
   // scalar preparation as torch does it on the host (python floats = doubles), then one rounding to fp32
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  float host2[2];
+  odb_adam_step_scalars(lr, beta1, beta2, step, host2);
+  const float step_size = host2[0], bc2_sqrt = host2[1];
   const float w1 = (float)(1.0 - (double)beta1), w2 = (float)(1.0 - (double)beta2);
   long long blocks = (n / 4 + kOptThreads - 1) / kOptThreads;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adam_step_kernel<<<(unsigned)blocks, kOptThreads, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, clip2, w1, beta2,
-                                                                 w2, step_size, bc2_sqrt, eps);
+                                                                 w2, step_size, bc2_sqrt, eps, step_scalars);
   count_launch();
   return check_launch("adam_step");
 }

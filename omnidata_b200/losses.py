@@ -273,7 +273,11 @@ class DepthStepLoss:
         gv = None
         if full_mix:
             p1, p2, p3 = points if points is not None else self.vnl.select_index()
-            t1, t2, t3 = (torch.from_numpy(np.ascontiguousarray(q)).to(dev, non_blocking=True) for q in (p1, p2, p3))
+            # int32 index arrays: host NumPy (copied here) or already on the device (a captured step's static buffers)
+            t1, t2, t3 = (q if isinstance(q, torch.Tensor) and q.is_cuda else
+                          torch.from_numpy(np.ascontiguousarray(q)).to(dev, non_blocking=True) for q in (p1, p2, p3))
+            if any(t.dtype != torch.int32 or not t.is_contiguous() for t in (t1, t2, t3)):
+                raise _capi.OdbError("DepthStepLoss: VNL index arrays must be contiguous int32")
             npts = t1.numel()
             scratch = self._buf("vnl_scratch", (b * npts,), torch.float32, dev)
             vout = self._buf("vnl_out", (1,), torch.float32, dev)

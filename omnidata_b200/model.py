@@ -464,9 +464,6 @@ class DPTDepthModel(nn.Module):
         gn_scratch = ws.bufs.get("gn_scratch")
         if gn_scratch is None:                         # zeroed once; the kernel leaves it zeroed
             gn_scratch = ws.bufs["gn_scratch"] = torch.zeros(4 << 20, dtype=torch.uint8, device=x.device)
-        gn_counters = ws.bufs.get("gn_counters")       # tickets of the producer-side finalize; zeroed once, left zero
-        if gn_counters is None or gn_counters.numel() < B:
-            gn_counters = ws.bufs["gn_counters"] = torch.zeros(max(B, 256), dtype=torch.int32, device=x.device)
         stat_i = iter(range(n_gn))
         # fused statistics: the conv epilogue writes per-warp partial sums here (largest layer:
         # stage 0 at 96x96 -> 72 tiles x 4 quadrants x 32 groups x 2 per image)
@@ -474,14 +471,13 @@ class DPTDepthModel(nn.Module):
 
         def conv_stats(fn, *args, out, **kw):
             """conv + GroupNorm statistics of its (unrounded) output.  Tensor-core path: partial sums in the conv
-            epilogue, reduced by the CTA that finishes each image's last tile (no second launch); fp32 mode: the
-            deterministic standalone statistics kernel."""
+            epilogue + finalize; fp32 mode: the deterministic standalone statistics kernel."""
             st = stats_pool[next(stat_i)]
             if fp32:
                 fn(*args, out, **kw)
                 ops.groupnorm_stats(out, st, scratch=gn_scratch)
             else:
-                fn(*args, out, gn_stats=(gn_part, st, gn_counters), **kw)
+                fn(*args, out, gn_stats=(gn_part, st), **kw)
             return st
 
         cols = buf("stem_cols", (B * h2 * w2, 160))

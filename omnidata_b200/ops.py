@@ -115,14 +115,12 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
               out: Optional[torch.Tensor], *, bias: Optional[torch.Tensor] = None,
               bias_per_image: bool = False, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
               out2: Optional[torch.Tensor] = None, tile: Optional[Tuple[int, int]] = None, block_n: int = 0,
-              cta_pair: int = 0, halo: int = 0, epilogue: int = 0, gn_stats: Optional[Tuple[torch.Tensor, ...]] = None,
-              gn_groups: int = 32, gn_eps: float = 1e-5, gn_fold: bool = True, out2_act: int = ACT_RELU,
+              cta_pair: int = 0, halo: int = 0, epilogue: int = 0, gn_stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+              gn_groups: int = 32, gn_eps: float = 1e-5, out2_act: int = ACT_RELU,
               head: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, bool]] = None,
               out_extent: Optional[Tuple[int, int, int]] = None) -> None:
     """taps: (view index, dx, dy).  head = (w[head_c,32] f32, b[head_c] f32, out[B,head_c,H,W] f32, relu).
-    gn_stats = (partial, stats[, counters]): fused GroupNorm statistics; `counters` (int32 [>= B], zero, left zero) is the
-    per-image ticket buffer of the producer-side finalize (a per-device one is used if omitted); gn_fold=False keeps the
-    reduction as the separate odb_groupnorm_finalize launch.  out2_act: activation of the out2 copy (ACT_RELU / ACT_GELU)."""
+    out2_act: activation of the out2 copy (ACT_RELU, or ACT_GELU: `out` keeps the pre-activation)."""
     d = ConvGemmDesc()
     dev = _same_device(*views, weight, out, out2, bias, residual)
     in_t = views[0].dtype
@@ -178,10 +176,8 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
     if gn_stats is None:
         _call("odb_conv_gemm", info, lib().odb_conv_gemm, dev, C.byref(d))
         return
-    # fused GroupNorm statistics: the epilogue writes per-warp partial sums; the CTA that finishes an image's last tile
-    # reduces them (gn_fold) or a tiny second kernel does
-    partial, stats = gn_stats[0], gn_stats[1]
-    counters = gn_stats[2] if len(gn_stats) > 2 else None
+    # fused GroupNorm statistics: the epilogue writes per-warp partial sums, a tiny kernel reduces them
+    partial, stats = gn_stats
     _need(partial, torch.float32, "gn partial"); _need(stats, torch.float32, "gn stats")
     plan = (C.c_int32 * 4)()
     check(lib().odb_conv_gemm_plan(C.byref(d), plan), "odb_conv_gemm_plan")
@@ -190,32 +186,10 @@ def conv_gemm(views: Sequence[torch.Tensor], taps: Sequence[Tuple[int, int, int]
         raise _capi.OdbError("conv_gemm: gn partial buffer too small")
     d.gn_partial = partial.data_ptr()
     d.gn_groups = gn_groups
-    if stats.numel() < d.out.b * gn_groups * 2:
-        raise _capi.OdbError("conv_gemm: gn stats buffer too small")
-    if gn_fold:
-        if counters is None:
-            counters = _gn_counters(views[0].device, d.out.b)
-        if counters.dtype != torch.int32 or counters.numel() < d.out.b or counters.device != views[0].device:
-            raise _capi.OdbError("conv_gemm: gn counters must be int32 [>= batch] on the tensors' device")
-        d.gn_stats, d.gn_counters, d.gn_eps = stats.data_ptr(), counters.data_ptr(), gn_eps
-        _call("odb_conv_gemm", info, lib().odb_conv_gemm, dev, C.byref(d))
-        return
     _call("odb_conv_gemm", info, lib().odb_conv_gemm, dev, C.byref(d))
     count = float(d.out.w) * float(d.out.h) * (d.n // gn_groups)
     _call("odb_groupnorm_finalize", {}, lib().odb_groupnorm_finalize, dev, partial.data_ptr(), stats.data_ptr(),
           d.out.b, part_rows, gn_groups, count, gn_eps)
-
-
-_GN_COUNTERS = {}
-
-
-def _gn_counters(device, batch: int) -> torch.Tensor:
-    """Per-device zeroed ticket buffer of the producer-side GroupNorm finalize (the kernel leaves it zero).  Callers that
-    capture CUDA graphs pass their own buffer, allocated before the capture."""
-    t = _GN_COUNTERS.get(device)
-    if t is None or t.numel() < batch:
-        t = _GN_COUNTERS[device] = torch.zeros(max(4096, batch), dtype=torch.int32, device=device)
-    return t
 
 
 TAPS_1 = [(0, 0, 0)]

@@ -47,13 +47,28 @@ class FlatAdam:
         self.step_count = 0
         self._ws = torch.zeros(int(lib().odb_grad_norm_workspace_bytes()), device=flat_params.device, dtype=torch.uint8)
         self._clip = torch.zeros(2, device=flat_params.device, dtype=torch.float32)
+        # CUDA-graph replay: the step-dependent scalars live in device memory and are refreshed before each replay
+        self._scalars_dev = torch.zeros(2, device=flat_params.device, dtype=torch.float32)
+
+    def stage_step_scalars(self, host2: torch.Tensor) -> None:
+        """Advance the step counter and copy this step's (lr / (1 - beta1^t), sqrt(1 - beta2^t)) through the pinned
+        fp32[2] tensor `host2` (which must stay untouched until the copy has run) to the device buffer that
+        `step(..., scalars_on_device=True)` reads; call once before each replay of a captured step."""
+        self.step_count += 1
+        check(lib().odb_adam_step_scalars(self.lr, self.betas[0], self.betas[1], self.step_count, host2.data_ptr()),
+              "odb_adam_step_scalars")
+        self._scalars_dev.copy_(host2, non_blocking=True)
 
     @_capi.on_tensor_device
-    def step(self, flat_grads: torch.Tensor, max_norm: Optional[float] = 10.0) -> Optional[torch.Tensor]:
+    def step(self, flat_grads: torch.Tensor, max_norm: Optional[float] = 10.0,
+             scalars_on_device: bool = False) -> Optional[torch.Tensor]:
+        """scalars_on_device: the launch reads the step scalars staged by `stage_step_scalars` (the form a CUDA graph
+        captures); otherwise they are computed here from the step counter."""
         g = flat_grads
         if not g.is_cuda or g.dtype != torch.float32 or g.shape != self.params.shape or not g.is_contiguous():
             raise _capi.OdbError("FlatAdam.step: gradients must match the flat parameter buffer")
-        self.step_count += 1
+        if not scalars_on_device:
+            self.step_count += 1
         clip_ptr = None
         if max_norm is not None:
             check(lib().odb_clip_grad_norm(g.data_ptr(), g.numel(), float(max_norm), self._ws.data_ptr(),
@@ -61,5 +76,6 @@ class FlatAdam:
             clip_ptr = self._clip.data_ptr()
         check(lib().odb_adam_step(self.params.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(),
                                   self.exp_avg_sq.data_ptr(), g.numel(), clip_ptr, self.lr, self.betas[0],
-                                  self.betas[1], self.eps, self.step_count, _stream()), "odb_adam_step")
+                                  self.betas[1], self.eps, max(self.step_count, 1),
+                                  self._scalars_dev.data_ptr() if scalars_on_device else None, _stream()), "odb_adam_step")
         return self._clip[0] if max_norm is not None else None

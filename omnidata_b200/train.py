@@ -17,6 +17,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import bwd, ops
@@ -219,7 +220,7 @@ class TrainEngine:
             fn(*args, out)
             ops.groupnorm_stats(out, st, scratch=self.gn_scratch)
         else:
-            fn(*args, out, gn_stats=(self.gn_part, st, self.gn_counters))
+            fn(*args, out, gn_stats=(self.gn_part, st))
 
     # ------------------------------------------------------------------ forward (activations kept)
     @torch.no_grad()
@@ -238,9 +239,6 @@ class TrainEngine:
         if "gn_scratch" not in self.bufs:
             self.bufs["gn_scratch"] = torch.zeros(4 << 20, dtype=torch.uint8, device=self.device)
         self.gn_scratch = self.bufs["gn_scratch"]
-        if "gn_counters" not in self.bufs or self.bufs["gn_counters"].numel() < B:
-            self.bufs["gn_counters"] = torch.zeros(max(B, 256), dtype=torch.int32, device=self.device)
-        self.gn_counters = self.bufs["gn_counters"]
         self.gn_part = buf("gn_partial", (B * ((H // 4) * (W // 4) // 32 + 64) * 4 * 32 * 2,), f32)
         n_gn = 1 + sum(3 * d + 1 for _, d in _STAGES)
         stats = buf("gn_stats", (n_gn, B, 32, 2), f32)
@@ -744,6 +742,13 @@ class DepthTrainStep:
         self.global_step = 0
         self.allreduce_bytes = sum(e - s for s, e, _ in self.buckets) * 4 if self.dist else 0
         self._hooks_done: Dict[str, torch.cuda.Event] = {}
+        # The eager step issues ~1150 launches from Python and is host-bound at batch 16; with use_cuda_graph the whole
+        # launch sequence (forward, loss, backward, clip, Adam) is captured once per (shape, loss mix) and replayed.
+        # Single-process by default; graph_collectives=True also captures the NCCL all-reduces (fork / join of the
+        # communication stream inside the capture).
+        self.use_cuda_graph = False
+        self.graph_collectives = False
+        self._graphs: Dict[tuple, dict] = {}
 
     def _allreduce_bucket(self, tag: str):
         """called by the backward when the range `tag` of the flat gradient is final"""
@@ -760,17 +765,85 @@ class DepthTrainStep:
     def step(self, rgb: torch.Tensor, depth_gt: torch.Tensor, mask_float: torch.Tensor, points=None,
              full_mix: Optional[bool] = None) -> torch.Tensor:
         """-> fp32 [5] on the device: (loss, ssi, reg, vn, gradient norm before clipping); no host synchronisation."""
-        eng = self.engine
         if full_mix is None:
             full_mix = self.global_step >= 15000                     # train_depth.py:274-279
+        if self.use_cuda_graph and (self.dist is None or self.graph_collectives):
+            return self._step_graph(rgb, depth_gt, mask_float, points, bool(full_mix))
+        res = self._launch_sequence(rgb, depth_gt, mask_float, points, bool(full_mix), scalars_on_device=False)
+        self.global_step += 1
+        return res
+
+    def _launch_sequence(self, rgb, depth_gt, mask_float, points, full_mix: bool, scalars_on_device: bool) -> torch.Tensor:
+        eng = self.engine
         out = eng.forward(rgb)                                        # [B,1,H,W]
         losses, dpred = self.loss(out, depth_gt, mask_float, full_mix=full_mix, points=points)
         eng.backward(dpred, on_ready=self._allreduce_bucket)
         if self.dist is not None:
             torch.cuda.current_stream(eng.device).wait_stream(self.comm_stream)
-        norm = self.opt.step(eng.flat_grad, max_norm=self.clip)
-        self.global_step += 1
+        norm = self.opt.step(eng.flat_grad, max_norm=self.clip, scalars_on_device=scalars_on_device)
         res = torch.empty(5, device=eng.device, dtype=torch.float32)
         res[:4].copy_(losses)
         res[4:5].copy_(norm.reshape(1) if norm is not None else torch.zeros(1, device=eng.device))
         return res
+
+    # ------------------------------------------------------------------ captured step
+    _RING = 4           # host staging slots: the CPU may run at most _RING - 1 replays ahead of the GPU
+
+    def _capture(self, key, rgb, depth_gt, mask_float, points, full_mix: bool) -> dict:
+        eng, dev = self.engine, self.engine.device
+        g = {"rgb": rgb.detach().float().contiguous().clone(), "gt": depth_gt.detach().float().contiguous().clone(),
+             "mask": mask_float.detach().float().contiguous().clone(), "pts": None, "slot": 0,
+             "host": [dict(scal=torch.zeros(2, dtype=torch.float32).pin_memory(), pts=None, done=None)
+                      for _ in range(self._RING)]}
+        if full_mix:
+            arrs = [np.ascontiguousarray(q, dtype=np.int32) for q in points]
+            g["pts"] = [torch.from_numpy(a).to(dev) for a in arrs]
+            for h in g["host"]:
+                h["pts"] = [torch.empty(a.shape, dtype=torch.int32).pin_memory() for a in arrs]
+        # one eager step first (workspaces, kernel attributes, NCCL channels): a training step changes the weights and
+        # the optimizer state, so both are put back before the capture
+        snap = (eng.flat.clone(), self.opt.exp_avg.clone(), self.opt.exp_avg_sq.clone(), self.opt.step_count)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.opt.stage_step_scalars(g["host"][0]["scal"])
+            self._launch_sequence(g["rgb"], g["gt"], g["mask"], g["pts"], full_mix, scalars_on_device=True)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        eng.flat.copy_(snap[0]); self.opt.exp_avg.copy_(snap[1]); self.opt.exp_avg_sq.copy_(snap[2])
+        self.opt.step_count = snap[3]
+        del snap
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g["res"] = self._launch_sequence(g["rgb"], g["gt"], g["mask"], g["pts"], full_mix, scalars_on_device=True)
+        g["graph"] = graph
+        g["scratch"] = bwd._SCRATCH.buf        # the shared kernel workspace the captured launches point into stays alive
+        return g
+
+    def _step_graph(self, rgb, depth_gt, mask_float, points, full_mix: bool) -> torch.Tensor:
+        if full_mix and points is None:
+            points = self.loss.vnl.select_index()                   # host NumPy RNG, the reference's call sequence
+        key = (tuple(rgb.shape), tuple(depth_gt.shape), tuple(mask_float.shape), full_mix)
+        g = self._graphs.get(key)
+        if g is None:
+            # the engine's activation buffers are re-allocated when the input shape changes: graphs of other shapes
+            # would replay into freed memory
+            for k in [k for k in self._graphs if k[:3] != key[:3]]:
+                del self._graphs[k]
+            g = self._graphs[key] = self._capture(key, rgb, depth_gt, mask_float, points, full_mix)
+        h = g["host"][g["slot"]]
+        g["slot"] = (g["slot"] + 1) % self._RING
+        if h["done"] is not None:
+            h["done"].synchronize()                                 # the replay that last read this staging slot has run
+        g["rgb"].copy_(rgb); g["gt"].copy_(depth_gt); g["mask"].copy_(mask_float)
+        if full_mix:
+            for dst, hp, q in zip(g["pts"], h["pts"], points):
+                hp.copy_(torch.from_numpy(np.ascontiguousarray(q, dtype=np.int32)))
+                dst.copy_(hp, non_blocking=True)
+        self.opt.stage_step_scalars(h["scal"])
+        g["graph"].replay()
+        h["done"] = torch.cuda.Event()
+        h["done"].record(torch.cuda.current_stream(self.engine.device))
+        self.global_step += 1
+        return g["res"].clone()

@@ -72,10 +72,15 @@ def main(args):
     np.random.seed(1234 + rank)
 
     n0 = _capi.launch_count()
-    first = step.step(*devin[0], full_mix=True)
+    first = step.step(*devin[0], full_mix=True)                     # eager: counts the launches of one step
     torch.cuda.synchronize()
     launches_per_step = _capi.launch_count() - n0
     first = [float(v) for v in first.cpu()]
+    # the eager step is host-bound (~1150 launches issued from Python): replay it as one CUDA graph.  With more than one
+    # rank the NCCL all-reduces would have to be captured too: opt-in (ODB_TRAIN_GRAPH_COLLECTIVES=1), eager otherwise.
+    graph_collectives = os.environ.get("ODB_TRAIN_GRAPH_COLLECTIVES", "0") == "1"
+    step.graph_collectives = graph_collectives
+    step.use_cuda_graph = (not args.no_graph) and (world == 1 or graph_collectives)
     for i in range(max(args.warmup, 3) - 1):
         step.step(*devin[i % n_rot], full_mix=True)
     torch.cuda.synchronize()
@@ -144,6 +149,8 @@ def main(args):
     detail, roof, roof_w = {}, None, None
     # every rank runs the two instrumented steps (they contain the gradient all-reduce: a collective); rank 0 records
     import contextlib
+    graphed = step.use_cuda_graph
+    step.use_cuda_graph = False                                      # per-launch events need the eager launch sequence
     with (ops.LaunchTimer() if rank == 0 else contextlib.nullcontext()) as lt:
         for i in range(2):
             step.step(*devin[i % n_rot], full_mix=True)
@@ -197,6 +204,7 @@ def main(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": bench.WORKLOADS[4], "index": 4, "global_batch": B * world, "per_gpu_batch": B,
                        "parallelism": f"dp{world}: replicated fp32 master weights, gradient all-reduce (mean) over NCCL",
+                       "cuda_graph": bool(graphed),
                        "precision": "bf16 operands / activations, fp32 accumulation, fp32 ViT residual stream, fp32 master "
                                     "weights + Adam state", "optimizer": "clip_grad_norm_(10) + Adam(lr=1e-5)",
                        "loss": "ssi + 0.1 reg + 10 vn (the mix after step 15000)",

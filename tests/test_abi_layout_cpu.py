@@ -27,7 +27,6 @@ int main(void) {
   F(odb_conv_gemm_desc, head_c) F(odb_conv_gemm_desc, head_relu) F(odb_conv_gemm_desc, head_out)
   F(odb_conv_gemm_desc, gn_partial) F(odb_conv_gemm_desc, gn_groups) F(odb_conv_gemm_desc, epilogue)
   F(odb_conv_gemm_desc, in_dtype) F(odb_conv_gemm_desc, out_dtype)
-  F(odb_conv_gemm_desc, gn_stats) F(odb_conv_gemm_desc, gn_counters) F(odb_conv_gemm_desc, gn_eps)
   F(odb_conv_gemm_desc, out2_act)
   printf("abi %d\n", ODB_ABI_VERSION);
   return 0;

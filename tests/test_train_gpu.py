@@ -419,3 +419,25 @@ def test_train_step_runs_learns_and_is_deterministic():
         assert float((step.engine.flat - w0).abs().max()) > 0
         assert float(hist[0][4]) > 0                                # gradient norm
     assert all(torch.equal(a, b) for a, b in zip(runs[0][0], runs[1][0])) and torch.equal(runs[0][1], runs[1][1])
+    # the same three steps replayed as ONE CUDA graph (the eager step is host-bound): bit-identical losses, gradient
+    # norms, weights and optimizer state — including the capture's warm-up step being undone; then a change of the loss
+    # mix (a second graph over the same buffers) and new inputs through the static copies
+    model = DPTDepthModel()
+    model.load_state_dict(synthetic.make_state_dict(0, 1), strict=True)
+    model = model.to(dev()).train()
+    step = DepthTrainStep(model, lr=1e-4, clip=10.0, precision="bf16")
+    step.use_cuda_graph = True
+    np.random.seed(11)
+    hist = [step.step(rgb, gt, mask, full_mix=True).cpu() for _ in range(3)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(hist, runs[0][0])) and torch.equal(step.engine.flat, runs[0][1])
+    assert step.opt.step_count == 3 and step.global_step == 3 and len(step._graphs) == 1
+    ref = DepthTrainStep(DPTDepthModel().to(dev()).train(), lr=1e-4, clip=10.0, precision="bf16")
+    ref.engine.flat.copy_(step.engine.flat); ref.opt.exp_avg.copy_(step.opt.exp_avg); ref.opt.exp_avg_sq.copy_(step.opt.exp_avg_sq)
+    ref.opt.step_count = 3
+    rgb2, gt2 = rgb.flip(0).contiguous(), gt.flip(0).contiguous()
+    a = [step.step(rgb2, gt2, mask, full_mix=False).cpu(), step.step(rgb, gt, mask, full_mix=False).cpu()]
+    b = [ref.step(rgb2, gt2, mask, full_mix=False).cpu(), ref.step(rgb, gt, mask, full_mix=False).cpu()]
+    torch.cuda.synchronize()
+    assert len(step._graphs) == 2
+    assert all(torch.equal(x, y) for x, y in zip(a, b)) and torch.equal(step.engine.flat, ref.engine.flat)
