@@ -51,6 +51,7 @@ class TrainEngine:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         self.model = model
         self.fp32 = precision == "fp32"
+        self.fuse_gelu = True      # mlp.fc1 writes the pre-activation and its GELU in one epilogue (tensor-core path)
         self.adt = torch.float32 if self.fp32 else torch.bfloat16
         p0 = next(model.parameters())
         if not p0.is_cuda:
@@ -338,7 +339,7 @@ class TrainEngine:
             ops.layernorm(xm[i], P[p + "norm2.weight"], P[p + "norm2.bias"], h2_)
             u = buf(f"vit_u_{i}", (B, ntok, 4 * D))
             mlp = buf(f"vit_mlp_{i}", (B, ntok, 4 * D))
-            if self.fp32:
+            if self.fp32 or not self.fuse_gelu:
                 ops.linear(h2_.view(rows, -1), Wt[f"blk{i}.fc1"][0], u.view(rows, -1), bias=P[p + "mlp.fc1.bias"])
                 bwd.gelu_fwd(u, mlp)
             else:       # one pass: the pre-activation (kept for the backward) and gelu of the same fp32 value
