@@ -769,7 +769,8 @@ class DepthTrainStep:
         if full_mix is None:
             full_mix = self.global_step >= 15000                     # train_depth.py:274-279
         if self.use_cuda_graph and (self.dist is None or self.graph_collectives):
-            return self._step_graph(rgb, depth_gt, mask_float, points, bool(full_mix))
+            with torch.cuda.device(self.engine.device):             # capture / replay on the engine's device and stream
+                return self._step_graph(rgb, depth_gt, mask_float, points, bool(full_mix))
         res = self._launch_sequence(rgb, depth_gt, mask_float, points, bool(full_mix), scalars_on_device=False)
         self.global_step += 1
         return res
