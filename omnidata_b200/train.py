@@ -817,7 +817,10 @@ class DepthTrainStep:
         self.opt.step_count = snap[3]
         del snap
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # with NCCL in the capture, other threads of the process (the process group's watchdog) keep making CUDA calls:
+        # restrict the capture's error checking to this thread
+        mode = "thread_local" if self.dist is not None else "global"
+        with torch.cuda.graph(graph, capture_error_mode=mode):
             g["res"] = self._launch_sequence(g["rgb"], g["gt"], g["mask"], g["pts"], full_mix, scalars_on_device=True)
         g["graph"] = graph
         g["scratch"] = bwd._SCRATCH.buf        # the shared kernel workspace the captured launches point into stays alive
