@@ -76,11 +76,22 @@ def main(args):
     torch.cuda.synchronize()
     launches_per_step = _capi.launch_count() - n0
     first = [float(v) for v in first.cpu()]
-    # the eager step is host-bound (~1150 launches issued from Python): replay it as one CUDA graph.  With more than one
-    # rank the NCCL all-reduces would have to be captured too: opt-in (ODB_TRAIN_GRAPH_COLLECTIVES=1), eager otherwise.
-    graph_collectives = os.environ.get("ODB_TRAIN_GRAPH_COLLECTIVES", "0") == "1"
-    step.graph_collectives = graph_collectives
-    step.use_cuda_graph = (not args.no_graph) and (world == 1 or graph_collectives)
+    # the eager step is host-bound (~1200 launches issued from Python; with several ranks on one host their issue
+    # threads also compete: 74 ms / step measured at N=2 against 37 ms of GPU work): replay it as one CUDA graph.  With
+    # more than one rank the NCCL all-reduces are captured too (fork / join of the communication stream inside the
+    # capture; bit-identical to the eager step at N=2).  --no-graph, or a failed capture, leaves the eager step.
+    step.graph_collectives = True
+    step.use_cuda_graph = not args.no_graph
+    graph_error = None
+    if step.use_cuda_graph:
+        try:
+            step.step(*devin[1 % n_rot], full_mix=True)             # captures (after undoing its own warm-up step)
+            torch.cuda.synchronize()
+        except Exception as e:                                       # every rank runs the same code: all fall back alike
+            graph_error = f"{type(e).__name__}: {e}"[:300]
+            step.use_cuda_graph = False
+            step._graphs.clear()
+            torch.cuda.synchronize()
     for i in range(max(args.warmup, 3) - 1):
         step.step(*devin[i % n_rot], full_mix=True)
     torch.cuda.synchronize()
@@ -204,7 +215,7 @@ def main(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": bench.WORKLOADS[4], "index": 4, "global_batch": B * world, "per_gpu_batch": B,
                        "parallelism": f"dp{world}: replicated fp32 master weights, gradient all-reduce (mean) over NCCL",
-                       "cuda_graph": bool(graphed),
+                       "cuda_graph": bool(graphed), "cuda_graph_error": graph_error,
                        "precision": "bf16 operands / activations, fp32 accumulation, fp32 ViT residual stream, fp32 master "
                                     "weights + Adam state", "optimizer": "clip_grad_norm_(10) + Adam(lr=1e-5)",
                        "loss": "ssi + 0.1 reg + 10 vn (the mix after step 15000)",
