@@ -77,11 +77,14 @@ def main(args):
     launches_per_step = _capi.launch_count() - n0
     first = [float(v) for v in first.cpu()]
     # the eager step is host-bound (~1200 launches issued from Python; with several ranks on one host their issue
-    # threads also compete: 74 ms / step measured at N=2 against 37 ms of GPU work): replay it as one CUDA graph.  With
-    # more than one rank the NCCL all-reduces are captured too (fork / join of the communication stream inside the
-    # capture; bit-identical to the eager step at N=2).  --no-graph, or a failed capture, leaves the eager step.
-    step.graph_collectives = True
-    step.use_cuda_graph = not args.no_graph
+    # threads also compete: 74 ms / step measured at N=2 against 37 ms of GPU work): replay it as one CUDA graph.
+    # With more than one rank the NCCL all-reduces have to be captured too (fork / join of the communication stream
+    # inside the capture).  That works — 36.6 ms / step at N=2, the same losses and weights as the eager step — but a
+    # process that holds graphs with NCCL kernels did not terminate on its own (hang in the teardown after the JSON
+    # line), so it stays opt-in (ODB_TRAIN_GRAPH_COLLECTIVES=1, with a hard exit after the line); eager otherwise.
+    graph_collectives = os.environ.get("ODB_TRAIN_GRAPH_COLLECTIVES", "0") == "1"
+    step.graph_collectives = graph_collectives
+    step.use_cuda_graph = (not args.no_graph) and (world == 1 or graph_collectives)
     graph_error = None
     if step.use_cuda_graph:
         try:
@@ -235,5 +238,13 @@ def main(args):
             "roofline": roof, "roofline_wgrad": roof_w, "roofline_detail": detail,
         }
         print(json.dumps(line), flush=True)
+    if graphed and world > 1:
+        # graphs that captured NCCL kernels: drop them, drain, and leave without the communicator teardown (see above)
+        import sys
+        step._graphs.clear()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     if world > 1:
         torch.distributed.destroy_process_group()
