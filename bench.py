@@ -15,9 +15,12 @@ from rank 0 once, timings are reduced with MAX over ranks.
 One JSON line on stdout (rank 0):  value = whole-job images/s with inputs resident in HBM (CUDA
 events, device time, max over ranks);  e2e = the same metric through the public API
 (`DPTDepthModel.forward`) with pinned-host inputs, H2D copy and D2H read-back inside the timed
-region;  roofline = the ViT-block GEMM launches of the tcgen05 kernel, timed per launch with CUDA
-events on the launching stream in an instrumented pass;  cpu_baseline = the oracle (the
-reference's CPU PyTorch arithmetic, fp32) timed on the host cores on a bounded sample.
+region;  roofline = ALL launches of the dominant kernel (`conv_gemm_kernel`, the tcgen05 implicit GEMM), timed per
+launch with CUDA events on the launching stream in an instrumented eager pass (`roofline_vit_blocks`: its ViT-block
+subset);  cpu_baseline = the oracle (the reference's CPU PyTorch arithmetic, fp32) timed on the host cores on a
+bounded sample;  gpu_eager_baseline = the same arithmetic in eager torch on this GPU (fp32 and autocast bf16).
+`--config 4` (omnidata_b200/train_bench.py) times the whole train step, replayed as one CUDA graph on one GPU
+(`--no-graph`: the eager launch sequence).
 """
 from __future__ import annotations
 
