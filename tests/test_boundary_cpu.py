@@ -125,3 +125,23 @@ def test_every_host_module_refuses_cpu_tensors():
         refocus.compute_quantiles(torch.zeros(1, 1, 8, 8), 4)
     with pytest.raises((OdbError, RuntimeError, AssertionError)):
         imageproc.DevicePreprocessor("depth")(np.zeros((8, 8, 3), dtype=np.uint8))
+
+
+def test_adam_step_scalars_are_torchs_host_arithmetic(lib_built):
+    """odb_adam_step_scalars (host function; what a captured train step stages before each replay) reproduces
+    torch.optim.Adam's scalar preparation: python floats (doubles) for bias_correction1/2, step_size = lr / bc1 and
+    sqrt(bc2), then one rounding to fp32 — and refuses step < 1 / a null pointer."""
+    import ctypes as C
+    import math
+    import numpy as np
+    from omnidata_b200 import _capi
+    lib = _capi.lib()
+    out = (C.c_float * 2)()
+    for lr, b1, b2 in ((1e-5, 0.9, 0.999), (3e-4, 0.8, 0.99)):
+        lr32, b132, b232 = (float(np.float32(v)) for v in (lr, b1, b2))     # the C ABI takes fp32 scalars
+        for step in (1, 2, 10, 1000, 15000):
+            assert lib.odb_adam_step_scalars(lr, b1, b2, step, out) == 0
+            bc1, bc2 = 1.0 - b132 ** step, 1.0 - b232 ** step
+            assert out[0] == np.float32(lr32 / bc1) and out[1] == np.float32(math.sqrt(bc2))
+    assert lib.odb_adam_step_scalars(1e-5, 0.9, 0.999, 0, out) != 0
+    assert lib.odb_adam_step_scalars(1e-5, 0.9, 0.999, 1, None) != 0
