@@ -1,7 +1,12 @@
 """bench.py --config 4: the train_depth.py step (BASELINE.json configs[4]) — DPT-Hybrid forward + MiDaS SSI +
 gradient-matching + virtual-normal loss + backward + data-parallel gradient all-reduce + clip + Adam, batch 16 per GPU
-(128 at 8 GPUs), synthetic 384x384 inputs (gt = rand, mask = rand > 0.1, VNL indices from NumPy).
-One JSON line on stdout (rank 0), same contract as the inference configs."""
+(128 at 8 GPUs), synthetic 384x384 inputs (mask = rand > 0.1, VNL indices from NumPy's RNG).
+One deviation from that row, stated in the line's `config.targets`: SURVEY's `gt = rand` with the seeded checkpoint drives
+the network behind its final ReLU within a few Adam steps — torch autograd + torch.optim.Adam over the reference arithmetic
+collapses the same way (tests/diag_dynamics_gpu.py) — so the last 1x1 conv is rescaled to predict inside [0.1, 0.9] and
+the targets are the initial prediction, perturbed.  The arithmetic of a step does not depend on the values.
+One JSON line on stdout (rank 0), same contract as the inference configs; the step is replayed as one CUDA graph
+(--no-graph: the eager launch sequence; more than one rank: eager unless ODB_TRAIN_GRAPH_COLLECTIVES=1)."""
 from __future__ import annotations
 
 import json
